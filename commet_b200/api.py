@@ -1,0 +1,360 @@
+"""ctypes binding of include/commet_b200.h, named after the reference's operators.
+
+    ctx = Context(device=0)
+    idx = ctx.stage(bases, offs)                  # Alphabet/HashKey per-base coding on device
+    ctx.index_reads(idx, k)                       # include/index_reads.h:41
+    found, searched = ctx.search_reads(q, k, t, tags)   # include/search_reads.h:34
+    tags, info = ctx.index_and_search(k, t, (ibases, ioffs), [(qbases, qoffs), ...])
+    bv, counters = ctx.filter_reads(bases, offs, min_len, max_N, min_shannon, max_reads)
+    out = ctx.bvop(BV_AND, a, b); ones = ctx.nb_one(bv, n_bits)
+
+Everything here is plumbing (numpy buffers in, numpy buffers out); the compute
+is in commet_b200/csrc.  No function in this module falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+_LIB = PKG / "lib" / "libcommet_b200.so"
+
+BV_AND, BV_OR, BV_ANDNOT, BV_NOT = 0, 1, 2, 3
+
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+
+# every symbol include/commet_b200.h declares: (restype, argtypes)
+_SIGS = {
+    "commet_last_error": (C.c_char_p, []),
+    "commet_abi_version": (C.c_int, []),
+    "commet_device_count": (C.c_int, []),
+    "commet_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "commet_ctx_destroy": (None, [C.c_void_p]),
+    "commet_ctx_sync": (C.c_int, [C.c_void_p]),
+    "commet_ctx_stream": (C.c_void_p, [C.c_void_p]),
+    "commet_ctx_launches": (C.c_uint64, [C.c_void_p]),
+    "commet_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "commet_host_free": (None, [C.c_void_p]),
+    "commet_filter_bytes": (C.c_uint64, [C.c_int]),
+    "commet_max_kmer": (C.c_uint64, [C.c_int]),
+    "commet_reads_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "commet_reads_from_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
+                                           C.POINTER(C.c_void_p)]),
+    "commet_reads_free": (None, [C.c_void_p]),
+    "commet_reads_count": (C.c_uint64, [C.c_void_p]),
+    "commet_reads_bases": (C.c_uint64, [C.c_void_p]),
+    "commet_reads_kmer_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "commet_chunk_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64, _u64p, _u64p]),
+    "commet_index_begin": (C.c_int, [C.c_void_p, C.c_int]),
+    "commet_index_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "commet_index_filter_ptr": (C.c_void_p, [C.c_void_p]),
+    "commet_index_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "commet_index_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]),
+    "commet_index_or": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "commet_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, _u64p, _u64p]),
+    "commet_search_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "commet_index_and_search": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
+                                          C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
+    "commet_index_and_search_staged": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_int,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "commet_filter_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_float,
+                                      C.c_int64, C.c_void_p, C.c_void_p]),
+    "commet_filter_reads_staged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_int64,
+                                             C.c_void_p, C.c_void_p]),
+    "commet_bvop": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "commet_bv_popcount": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, _u64p]),
+    "commet_bvop_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "commet_bv_popcount_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, _u64p]),
+    "commet_bench_random_sectors": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+class CommetError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _LIB
+
+
+def load_library() -> C.CDLL:
+    """dlopen the CUDA extension; raises if it was not built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not _LIB.exists():
+            raise CommetError(f"{_LIB} is missing: build it with `python -m commet_b200.build` "
+                              "(nvcc, sm_100a). commet_b200 has no CPU fallback.")
+        lib = C.CDLL(str(_LIB))
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def filter_bytes(k: int) -> int:
+    return int(load_library().commet_filter_bytes(k))
+
+
+def max_kmer(k: int) -> int:
+    return int(load_library().commet_max_kmer(k))
+
+
+def _ptr(a):
+    """host numpy array, raw int (device address) or None -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data)
+
+
+def _as_stream(bases, offs):
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    if offs.ndim != 1 or offs.size < 1:
+        raise ValueError("offs must hold n_reads+1 offsets")
+    return bases, offs
+
+
+class ReadStream:
+    """A device-resident, 2-bit encoded valid-read stream (commet_reads*)."""
+
+    def __init__(self, ctx: "Context", handle: int):
+        self.ctx = ctx
+        self.handle = handle
+
+    @property
+    def n_reads(self) -> int:
+        return int(self.ctx.lib.commet_reads_count(self.handle))
+
+    @property
+    def n_bases(self) -> int:
+        return int(self.ctx.lib.commet_reads_bases(self.handle))
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.commet_reads_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU, one stream (commet_ctx*)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        if self.lib.commet_ctx_create(device, C.byref(h)) != 0:
+            raise CommetError(self.lib.commet_last_error().decode())
+        self.handle = h.value
+        self.device = device
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.commet_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise CommetError(self.lib.commet_last_error().decode())
+
+    # -- plumbing ---------------------------------------------------------
+    def sync(self):
+        self._ck(self.lib.commet_ctx_sync(self.handle))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.commet_ctx_stream(self.handle) or 0)
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.commet_ctx_launches(self.handle))
+
+    # -- staging ------------------------------------------------------------
+    def stage(self, bases, offs) -> ReadStream:
+        """Upload + encode a host read stream."""
+        bases, offs = _as_stream(bases, offs)
+        h = C.c_void_p()
+        self._ck(self.lib.commet_reads_upload(self.handle, _ptr(bases), _ptr(offs), offs.size - 1, C.byref(h)))
+        return ReadStream(self, h.value)
+
+    def stage_device(self, d_bases: int, d_offs: int, n_reads: int, n_bases: int) -> ReadStream:
+        """Encode a stream whose ASCII bases/offsets already sit in device memory."""
+        h = C.c_void_p()
+        self._ck(self.lib.commet_reads_from_device(self.handle, _ptr(d_bases), _ptr(d_offs), n_reads, n_bases,
+                                                   C.byref(h)))
+        return ReadStream(self, h.value)
+
+    def kmer_counts(self, reads: ReadStream, k: int) -> np.ndarray:
+        out = np.zeros(max(reads.n_reads, 1), dtype=np.uint32)
+        self._ck(self.lib.commet_reads_kmer_counts(self.handle, reads.handle, k, _ptr(out)))
+        return out[:reads.n_reads]
+
+    def chunk_plan(self, reads: ReadStream, k: int, maxk: int | None = None):
+        """[(first, end), ...] read ranges of the index chunks, and reads indexed."""
+        maxk = max_kmer(k) if maxk is None else maxk
+        cap = 1024
+        while True:
+            b = np.zeros(2 * cap, dtype=np.uint64)
+            nc, ni = C.c_uint64(0), C.c_uint64(0)
+            self._ck(self.lib.commet_chunk_plan(self.handle, reads.handle, k, maxk, _ptr(b), cap, C.byref(nc),
+                                                C.byref(ni)))
+            if nc.value <= cap:
+                return [(int(b[2 * i]), int(b[2 * i + 1])) for i in range(nc.value)], int(ni.value)
+            cap = int(nc.value)
+
+    # -- stage 1 --------------------------------------------------------------
+    def index_begin(self, k: int):
+        self._ck(self.lib.commet_index_begin(self.handle, k))
+
+    def index_add(self, reads: ReadStream, first: int = 0, count: int | None = None):
+        count = reads.n_reads - first if count is None else count
+        self._ck(self.lib.commet_index_add(self.handle, reads.handle, first, count))
+
+    def index_reads(self, reads: ReadStream, k: int, first: int = 0, count: int | None = None):
+        """BloomFilter(k) + feed every k-mer of reads[first:first+count] (index_reads.h:41-63 without the stop rule;
+        the stop rule is chunk_plan)."""
+        self.index_begin(k)
+        self.index_add(reads, first, count)
+
+    def filter_download(self, k: int) -> np.ndarray:
+        out = np.zeros(filter_bytes(k), dtype=np.uint8)
+        self._ck(self.lib.commet_index_download(self.handle, _ptr(out), out.size))
+        return out
+
+    def filter_upload(self, k: int, filt: np.ndarray):
+        filt = np.ascontiguousarray(filt, dtype=np.uint8)
+        self._ck(self.lib.commet_index_upload(self.handle, k, _ptr(filt), filt.size))
+
+    @property
+    def filter_ptr(self) -> int:
+        return int(self.lib.commet_index_filter_ptr(self.handle) or 0)
+
+    def index_or(self, d_other: int, offset: int, nbytes: int):
+        self._ck(self.lib.commet_index_or(self.handle, _ptr(d_other), offset, nbytes))
+
+    # -- stage 2 --------------------------------------------------------------
+    def search_reads(self, reads: ReadStream, k: int, t: int, tags: np.ndarray):
+        """search_reads.h:34-87 against the current filter; tags (n/8+1 bytes) updated in place.
+        Returns (newly found, searched)."""
+        assert tags.dtype == np.uint8 and tags.size >= reads.n_reads // 8 + 1
+        nf, ns = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self.lib.commet_search(self.handle, reads.handle, k, t, _ptr(tags), C.byref(nf), C.byref(ns)))
+        return int(nf.value), int(ns.value)
+
+    def search_reads_device(self, reads: ReadStream, k: int, t: int, d_tags: int, d_counters: int):
+        self._ck(self.lib.commet_search_dev(self.handle, reads.handle, k, t, _ptr(d_tags), _ptr(d_counters)))
+
+    # -- the chunk loop ---------------------------------------------------------
+    def index_and_search(self, k: int, t: int, index_stream, query_streams, maxk: int | None = None):
+        """src/index_and_search.cpp:241-277 on host streams.
+        Returns (tags: list of .bv payloads, info dict)."""
+        maxk = max_kmer(k) if maxk is None else maxk
+        ib, io = _as_stream(*index_stream)
+        qs = [_as_stream(b, o) for b, o in query_streams]
+        ns = len(qs)
+        tags = [np.zeros((o.size - 1) // 8 + 1, dtype=np.uint8) for _, o in qs]
+        qb = (C.c_void_p * max(ns, 1))(*[b.ctypes.data for b, _ in qs])
+        qo = (C.c_void_p * max(ns, 1))(*[o.ctypes.data for _, o in qs])
+        tg = (C.c_void_p * max(ns, 1))(*[t_.ctypes.data for t_ in tags])
+        nq = np.array([o.size - 1 for _, o in qs] or [0], dtype=np.uint64)
+        searched = np.zeros(max(ns, 1), dtype=np.uint64)
+        shared = np.zeros(max(ns, 1), dtype=np.uint64)
+        stats = np.zeros(8, dtype=np.uint64)
+        self._ck(self.lib.commet_index_and_search(self.handle, k, t, maxk, _ptr(ib), _ptr(io), io.size - 1, ns,
+                                                  C.cast(qb, C.c_void_p), C.cast(qo, C.c_void_p), _ptr(nq),
+                                                  C.cast(tg, C.c_void_p), _ptr(searched), _ptr(shared), _ptr(stats)))
+        info = dict(chunks=int(stats[0]), indexed=int(stats[1]), kmers=int(stats[2]), index_ns=int(stats[3]),
+                    search_ns=int(stats[4]), searched=[int(x) for x in searched[:ns]],
+                    shared=[int(x) for x in shared[:ns]])
+        return tags, info
+
+    def index_and_search_staged(self, k: int, t: int, index: ReadStream, queries, d_tags, maxk: int | None = None):
+        """Same loop on staged streams; d_tags: device addresses of zeroed u32 tag words."""
+        maxk = max_kmer(k) if maxk is None else maxk
+        ns = len(queries)
+        qh = (C.c_void_p * max(ns, 1))(*[q.handle for q in queries])
+        th = (C.c_void_p * max(ns, 1))(*d_tags)
+        searched = np.zeros(max(ns, 1), dtype=np.uint64)
+        shared = np.zeros(max(ns, 1), dtype=np.uint64)
+        stats = np.zeros(8, dtype=np.uint64)
+        self._ck(self.lib.commet_index_and_search_staged(self.handle, k, t, maxk, index.handle, ns,
+                                                         C.cast(qh, C.c_void_p), C.cast(th, C.c_void_p),
+                                                         _ptr(searched), _ptr(shared), _ptr(stats)))
+        return dict(chunks=int(stats[0]), indexed=int(stats[1]), kmers=int(stats[2]), index_ns=int(stats[3]),
+                    search_ns=int(stats[4]), searched=[int(x) for x in searched[:ns]],
+                    shared=[int(x) for x in shared[:ns]])
+
+    # -- stage 3 --------------------------------------------------------------
+    def filter_reads(self, bases, offs, min_len=0, max_N=-1, min_shannon=0.0, max_reads=-1):
+        """src/filter_reads.cpp:181-205. Returns (.bv payload, counters dict)."""
+        bases, offs = _as_stream(bases, offs)
+        n = offs.size - 1
+        bv = np.zeros(n // 8 + 1, dtype=np.uint8)
+        cnt = np.zeros(4, dtype=np.uint64)
+        self._ck(self.lib.commet_filter_reads(self.handle, _ptr(bases), _ptr(offs), n, min_len, max_N,
+                                              C.c_float(min_shannon), max_reads, _ptr(bv), _ptr(cnt)))
+        return bv, dict(rm_length=int(cnt[0]), rm_N=int(cnt[1]), rm_shannon=int(cnt[2]), selected=int(cnt[3]))
+
+    def filter_reads_staged(self, reads: ReadStream, d_bv: int, min_len=0, max_N=-1, min_shannon=0.0, max_reads=-1):
+        cnt = np.zeros(4, dtype=np.uint64)
+        self._ck(self.lib.commet_filter_reads_staged(self.handle, reads.handle, min_len, max_N, C.c_float(min_shannon),
+                                                     max_reads, _ptr(d_bv), _ptr(cnt)))
+        return dict(rm_length=int(cnt[0]), rm_N=int(cnt[1]), rm_shannon=int(cnt[2]), selected=int(cnt[3]))
+
+    # -- stage 4 --------------------------------------------------------------
+    def bvop(self, op: int, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:
+        """BooleanVector::full_and/or/and_not/not over all payload bytes."""
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        if op != BV_NOT:
+            b = np.ascontiguousarray(b, dtype=np.uint8)
+            if b.size != a.size:
+                raise CommetError("Error: the two vectors are not the same size")
+        out = np.empty_like(a)
+        self._ck(self.lib.commet_bvop(self.handle, op, _ptr(a), _ptr(b), _ptr(out), a.size))
+        return out
+
+    def nb_one(self, bv: np.ndarray, n_bits: int) -> int:
+        bv = np.ascontiguousarray(bv, dtype=np.uint8)
+        assert bv.size >= n_bits // 8 + 1
+        ones = C.c_uint64(0)
+        self._ck(self.lib.commet_bv_popcount(self.handle, _ptr(bv), n_bits, C.byref(ones)))
+        return int(ones.value)
+
+    def bvop_device(self, op: int, d_a: int, d_b: int | None, d_out: int, n_bytes: int):
+        self._ck(self.lib.commet_bvop_dev(self.handle, op, _ptr(d_a), _ptr(d_b), _ptr(d_out), n_bytes))
+
+    def nb_one_device(self, d_bv: int, n_bits: int) -> int:
+        ones = C.c_uint64(0)
+        self._ck(self.lib.commet_bv_popcount_dev(self.handle, _ptr(d_bv), n_bits, C.byref(ones)))
+        return int(ones.value)
+
+    # -- measurement ------------------------------------------------------------
+    def random_sector_rate(self, nbytes: int, n_ops: int, atomic: bool = False) -> float:
+        """G sectors/s of independent random 32-byte-sector loads (or RED.OR) over a buffer."""
+        ns = C.c_double(0)
+        self._ck(self.lib.commet_bench_random_sectors(self.handle, nbytes, n_ops, int(atomic), C.byref(ns)))
+        return n_ops / ns.value

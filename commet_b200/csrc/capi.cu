@@ -1,0 +1,745 @@
+// C-ABI of the B200-native Commet hot path: context, read staging, chunk
+// loop, and the launchers of the kernels in kernels.cuh.  See
+// include/commet_b200.h for the contract of every entry point and the
+// reference interface it replaces.  There is no CPU fallback in this file:
+// every data-path operation is a kernel launch on the context's stream.
+#include "../../include/commet_b200.h"
+#include "kernels.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+using namespace commet;
+
+// ------------------------------------------------------------------ errors --
+static thread_local std::string g_err;
+
+static int fail(const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return -1;
+}
+
+#define CK(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define CKR(call)                     \
+    do {                              \
+        int rc_ = (call);             \
+        if (rc_ != 0) return rc_;     \
+    } while (0)
+
+// ------------------------------------------------------------------ types ---
+struct commet_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    uint32_t *filter = nullptr;       // bloom_filter.h byte array, device
+    uint64_t filter_cap = 0;          // allocated bytes
+    uint64_t filter_bytes = 0;        // 2^(k-1)
+    int k = 0;
+    unsigned long long *scratch = nullptr;   // 64 u64 of device counters
+    uint64_t launches = 0;
+};
+
+struct commet_reads {
+    commet_ctx *ctx = nullptr;
+    uint64_t n_reads = 0, n_bases = 0, n_words = 0;
+    uint4 *planes = nullptr;          // n_words + 4 (zero tail)
+    uint64_t *offs = nullptr;         // n_reads + 1, device
+    int k_prepared = 0;               // W plane valid for this k (0: none)
+};
+
+namespace {
+
+struct DevBuf {                       // scoped device allocation
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <class T> T *as() { return static_cast<T *>(p); }
+};
+
+inline unsigned grid_for(const commet_ctx *c, uint64_t items, unsigned block, unsigned blocks_per_sm)
+{
+    uint64_t need = (items + block - 1) / block;
+    uint64_t cap = (uint64_t)c->sm_count * blocks_per_sm;
+    if (need < 1) need = 1;
+    return (unsigned)std::min<uint64_t>(need, cap);
+}
+
+inline int set_device(const commet_ctx *c)
+{
+    CK(cudaSetDevice(c->device));
+    return 0;
+}
+
+inline uint64_t tag_words(uint64_t n_reads) { return (n_reads / 8 + 1 + 3) / 4; }
+
+}  // namespace
+
+// ---------------------------------------------------------------- context ---
+extern "C" const char *commet_last_error(void) { return g_err.c_str(); }
+extern "C" int commet_abi_version(void) { return COMMET_B200_ABI_VERSION; }
+
+extern "C" int commet_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int commet_ctx_create(int device, commet_ctx **out)
+{
+    if (!out) return fail("commet_ctx_create: null out");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail("commet_b200 needs a CUDA device (B200, sm_100a); none visible: %s -- there is no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail("device %d out of range (0..%d)", device, n - 1);
+    CK(cudaSetDevice(device));
+    commet_ctx *c = new commet_ctx;
+    c->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&c->scratch, 64 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(c->scratch, 0, 64 * sizeof(unsigned long long), c->stream));
+    *out = c;
+    return 0;
+}
+
+extern "C" void commet_ctx_destroy(commet_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->filter) cudaFree(c->filter);
+    if (c->scratch) cudaFree(c->scratch);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int commet_ctx_sync(commet_ctx *c)
+{
+    CKR(set_device(c));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" void *commet_ctx_stream(commet_ctx *c) { return (void *)c->stream; }
+extern "C" uint64_t commet_ctx_launches(commet_ctx *c) { return c->launches; }
+
+extern "C" void *commet_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void commet_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" uint64_t commet_filter_bytes(int k) { return (uint64_t)1 << (k - 1); }
+extern "C" uint64_t commet_max_kmer(int k) { return (uint64_t)(1000000000.0 / pow(2, 33 - k)); }
+
+// ----------------------------------------------------------- read staging ---
+static int reads_alloc(commet_ctx *c, uint64_t n_reads, uint64_t n_bases, commet_reads **out)
+{
+    commet_reads *r = new commet_reads;
+    r->ctx = c;
+    r->n_reads = n_reads;
+    r->n_bases = n_bases;
+    r->n_words = (n_bases + 31) / 32;
+    cudaError_t e = cudaMalloc(&r->planes, (r->n_words + 4) * sizeof(uint4));
+    if (e == cudaSuccess) e = cudaMalloc(&r->offs, (n_reads + 1) * sizeof(uint64_t));
+    if (e != cudaSuccess) {
+        commet_reads_free(r);
+        return fail("device allocation for %llu bases failed: %s", (unsigned long long)n_bases,
+                    cudaGetErrorString(e));
+    }
+    CK(cudaMemsetAsync(r->planes + r->n_words, 0, 4 * sizeof(uint4), c->stream));
+    *out = r;
+    return 0;
+}
+
+static int launch_encode(commet_ctx *c, const uint8_t *d_bases_padded, commet_reads *r)
+{
+    if (r->n_words == 0) return 0;
+    k_encode<<<grid_for(c, r->n_words, 256, 8), 256, 0, c->stream>>>(
+        reinterpret_cast<const uint4 *>(d_bases_padded), r->planes, r->n_words);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int commet_reads_upload(commet_ctx *c, const uint8_t *bases, const uint64_t *offs,
+                                   uint64_t n_reads, commet_reads **out)
+{
+    if (!c || !offs || !out) return fail("commet_reads_upload: null argument");
+    CKR(set_device(c));
+    uint64_t n_bases = offs[n_reads] - offs[0];
+    if (offs[0] != 0) return fail("commet_reads_upload: offs[0] must be 0");
+    commet_reads *r = nullptr;
+    CKR(reads_alloc(c, n_reads, n_bases, &r));
+    DevBuf ascii;
+    uint64_t padded = r->n_words * 32;
+    if (ascii.alloc(padded) != cudaSuccess) {
+        commet_reads_free(r);
+        return fail("device allocation of %llu staging bytes failed", (unsigned long long)padded);
+    }
+    if (padded > n_bases) CK(cudaMemsetAsync(ascii.as<uint8_t>() + n_bases, 0, padded - n_bases, c->stream));
+    if (n_bases) CK(cudaMemcpyAsync(ascii.p, bases, n_bases, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(r->offs, offs, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    int rc = launch_encode(c, ascii.as<uint8_t>(), r);
+    if (rc == 0 && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail("encode failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc != 0) { commet_reads_free(r); return rc; }
+    *out = r;
+    return 0;
+}
+
+extern "C" int commet_reads_from_device(commet_ctx *c, const uint8_t *d_bases, const uint64_t *d_offs,
+                                        uint64_t n_reads, uint64_t n_bases, commet_reads **out)
+{
+    if (!c || !d_offs || !out) return fail("commet_reads_from_device: null argument");
+    CKR(set_device(c));
+    commet_reads *r = nullptr;
+    CKR(reads_alloc(c, n_reads, n_bases, &r));
+    CK(cudaMemcpyAsync(r->offs, d_offs, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
+    uint64_t padded = r->n_words * 32;
+    int rc = 0;
+    if (padded == n_bases && ((uintptr_t)d_bases & 15) == 0) {
+        rc = launch_encode(c, d_bases, r);                 // already vector-aligned: encode in place
+        if (rc == 0) CK(cudaStreamSynchronize(c->stream));
+    } else {
+        DevBuf ascii;
+        if (ascii.alloc(padded) != cudaSuccess) { commet_reads_free(r); return fail("staging allocation failed"); }
+        CK(cudaMemsetAsync(ascii.as<uint8_t>() + n_bases, 0, padded - n_bases, c->stream));
+        if (n_bases) CK(cudaMemcpyAsync(ascii.p, d_bases, n_bases, cudaMemcpyDeviceToDevice, c->stream));
+        rc = launch_encode(c, ascii.as<uint8_t>(), r);
+        if (rc == 0) CK(cudaStreamSynchronize(c->stream));
+    }
+    if (rc != 0) { commet_reads_free(r); return rc; }
+    *out = r;
+    return 0;
+}
+
+extern "C" void commet_reads_free(commet_reads *r)
+{
+    if (!r) return;
+    if (r->ctx) cudaSetDevice(r->ctx->device);
+    if (r->planes) cudaFree(r->planes);
+    if (r->offs) cudaFree(r->offs);
+    delete r;
+}
+
+extern "C" uint64_t commet_reads_count(const commet_reads *r) { return r ? r->n_reads : 0; }
+extern "C" uint64_t commet_reads_bases(const commet_reads *r) { return r ? r->n_bases : 0; }
+
+// W plane for k (cached per stream)
+static int prepare(commet_ctx *c, commet_reads *r, int k)
+{
+    if (k < 1 || k > kMaxK) return fail("k=%d unsupported (1..%d)", k, kMaxK);
+    if (r->k_prepared == k) return 0;
+    if (r->n_words) {
+        DevBuf S;
+        if (S.alloc((r->n_words + 3) * sizeof(uint32_t)) != cudaSuccess) return fail("allocation of start marks failed");
+        CK(cudaMemsetAsync(S.p, 0, (r->n_words + 3) * sizeof(uint32_t), c->stream));
+        if (r->n_reads) {
+            k_mark_starts<<<grid_for(c, r->n_reads, 256, 8), 256, 0, c->stream>>>(r->offs, r->n_reads, S.as<uint32_t>());
+            c->launches++;
+        }
+        k_windows<<<grid_for(c, r->n_words * 32, 256, 8), 256, 0, c->stream>>>(r->planes, S.as<uint32_t>(), r->n_words,
+                                                                                 r->n_bases, k);
+        c->launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(c->stream));      // S is freed on return
+    }
+    r->k_prepared = k;
+    return 0;
+}
+
+extern "C" int commet_reads_kmer_counts(commet_ctx *c, commet_reads *r, int k, uint32_t *counts)
+{
+    CKR(set_device(c));
+    CKR(prepare(c, r, k));
+    if (r->n_reads == 0) return 0;
+    DevBuf d;
+    if (d.alloc(r->n_reads * sizeof(uint32_t)) != cudaSuccess) return fail("allocation of k-mer counts failed");
+    CK(cudaMemsetAsync(c->scratch, 0, sizeof(unsigned long long), c->stream));
+    k_kmer_counts<<<grid_for(c, r->n_reads, 256, 8), 256, 0, c->stream>>>(r->planes, r->offs, r->n_reads,
+                                                                         d.as<uint32_t>(), c->scratch);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(counts, d.p, r->n_reads * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------- chunk plan ---
+static int chunk_plan(commet_ctx *c, commet_reads *r, int k, uint64_t max_kmer,
+                      std::vector<uint64_t> &bounds, uint64_t *n_indexed, uint64_t *n_kmers)
+{
+    bounds.clear();
+    uint64_t n = r->n_reads;
+    if (n_indexed) *n_indexed = 0;
+    if (n_kmers) *n_kmers = 0;
+    if (n == 0) return 0;
+    CKR(prepare(c, r, k));
+    DevBuf d;
+    if (d.alloc(n * sizeof(uint32_t)) != cudaSuccess) return fail("allocation of k-mer counts failed");
+    CK(cudaMemsetAsync(c->scratch, 0, sizeof(unsigned long long), c->stream));
+    k_kmer_counts<<<grid_for(c, n, 256, 8), 256, 0, c->stream>>>(r->planes, r->offs, n, d.as<uint32_t>(), c->scratch);
+    c->launches++;
+    CK(cudaGetLastError());
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, c->scratch, sizeof total, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (n_kmers) *n_kmers = total;
+    if (total < max_kmer) {            // the limit is never reached: one chunk, nothing dropped
+        bounds.push_back(0);
+        bounds.push_back(n);
+        if (n_indexed) *n_indexed = n;
+        return 0;
+    }
+    // index_reads.h:48-49,60 + index_and_search.cpp:255: walk the per-read counts
+    std::vector<uint32_t> cnt(n);
+    CK(cudaMemcpy(cnt.data(), d.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    uint64_t i = 0, indexed = 0;
+    while (i < n) {
+        uint64_t start = i, cum = 0;
+        while (i < n && cum < max_kmer) cum += cnt[i++];
+        bounds.push_back(start);
+        bounds.push_back(i);
+        indexed += i - start;
+        if (i < n && cum >= max_kmer) i++;     // fetched, then lost
+    }
+    if (n_indexed) *n_indexed = indexed;
+    return 0;
+}
+
+extern "C" int commet_chunk_plan(commet_ctx *c, commet_reads *r, int k, uint64_t max_kmer, uint64_t *bounds,
+                                 uint64_t cap, uint64_t *n_chunks, uint64_t *n_indexed)
+{
+    CKR(set_device(c));
+    std::vector<uint64_t> b;
+    CKR(chunk_plan(c, r, k, max_kmer, b, n_indexed, nullptr));
+    uint64_t nc = b.size() / 2;
+    if (n_chunks) *n_chunks = nc;
+    for (uint64_t i = 0; i < std::min(nc, cap) * 2; i++) bounds[i] = b[i];
+    return 0;
+}
+
+// ---------------------------------------------------------- stage 1: index --
+extern "C" int commet_index_begin(commet_ctx *c, int k)
+{
+    CKR(set_device(c));
+    if (k < 1 || k > kMaxK) return fail("k=%d unsupported (1..%d)", k, kMaxK);
+    uint64_t bytes = commet_filter_bytes(k);
+    uint64_t cap = std::max<uint64_t>((bytes + 255) & ~255ull, 256);
+    if (c->filter_cap < cap) {
+        if (c->filter) { cudaFree(c->filter); c->filter = nullptr; c->filter_cap = 0; }
+        cudaError_t e = cudaMalloc(&c->filter, cap);
+        if (e != cudaSuccess)
+            return fail("Index memory allocation impossible (%llu bytes for k=%d): %s",
+                        (unsigned long long)cap, k, cudaGetErrorString(e));
+        c->filter_cap = cap;
+    }
+    c->filter_bytes = bytes;
+    c->k = k;
+    CK(cudaMemsetAsync(c->filter, 0, cap, c->stream));
+    return 0;
+}
+
+static int index_range(commet_ctx *c, commet_reads *r, uint64_t first, uint64_t count, unsigned long long *d_kmers)
+{
+    if (c->k == 0) return fail("commet_index_add before commet_index_begin");
+    if (first + count > r->n_reads) return fail("index range out of bounds");
+    if (count == 0 || r->n_words == 0) return 0;
+    CKR(prepare(c, r, c->k));
+    uint64_t hb[2];
+    // the two range offsets are read back so the grid can be sized; 16 bytes
+    CK(cudaMemcpyAsync(&hb[0], r->offs + first, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&hb[1], r->offs + first + count, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (hb[1] <= hb[0]) return 0;
+    uint64_t positions = hb[1] - hb[0] + 32;
+    k_index<<<grid_for(c, positions, 256, 8), 256, 0, c->stream>>>(c->filter, r->planes, hb[0], hb[1], c->k, d_kmers);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int commet_index_add(commet_ctx *c, commet_reads *r, uint64_t first, uint64_t count)
+{
+    CKR(set_device(c));
+    return index_range(c, r, first, count, nullptr);
+}
+
+extern "C" void *commet_index_filter_ptr(commet_ctx *c) { return c->filter; }
+
+extern "C" int commet_index_download(commet_ctx *c, uint8_t *out, uint64_t bytes)
+{
+    CKR(set_device(c));
+    if (bytes > c->filter_bytes) return fail("filter is %llu bytes", (unsigned long long)c->filter_bytes);
+    CK(cudaMemcpyAsync(out, c->filter, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int commet_index_upload(commet_ctx *c, int k, const uint8_t *filter, uint64_t bytes)
+{
+    CKR(commet_index_begin(c, k));
+    if (bytes != c->filter_bytes) return fail("filter for k=%d must be %llu bytes", k, (unsigned long long)c->filter_bytes);
+    CK(cudaMemcpyAsync(c->filter, filter, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int commet_index_or(commet_ctx *c, const void *d_other, uint64_t offset, uint64_t bytes)
+{
+    CKR(set_device(c));
+    if ((offset & 15) || offset + bytes > c->filter_cap) return fail("commet_index_or: bad range");
+    uint64_t n_vec = (bytes + 15) / 16;
+    if (n_vec == 0) return 0;
+    k_or_into<<<grid_for(c, n_vec, 256, 8), 256, 0, c->stream>>>(
+        reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(c->filter) + offset),
+        reinterpret_cast<const uint4 *>(d_other), n_vec);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// --------------------------------------------------------- stage 2: search --
+static int search_launch(commet_ctx *c, commet_reads *r, int k, int t, uint32_t *d_tags, unsigned long long *d_counters)
+{
+    if (c->k != k || !c->filter) return fail("commet_search: no filter for k=%d (current k=%d)", k, c->k);
+    if (r->n_reads == 0) return 0;
+    CKR(prepare(c, r, k));
+    k_search<<<grid_for(c, r->n_reads, 256, 8), 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t,
+                                                                    d_tags, d_counters);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int commet_search_dev(commet_ctx *c, commet_reads *r, int k, int t, uint32_t *d_tags, uint64_t *d_counters)
+{
+    CKR(set_device(c));
+    CK(cudaMemsetAsync(d_counters + 1, 0, sizeof(uint64_t), c->stream));
+    return search_launch(c, r, k, t, d_tags, reinterpret_cast<unsigned long long *>(d_counters));
+}
+
+extern "C" int commet_search(commet_ctx *c, commet_reads *r, int k, int t, uint8_t *tags, uint64_t *n_found,
+                             uint64_t *n_searched)
+{
+    CKR(set_device(c));
+    uint64_t nb = r->n_reads / 8 + 1, nw = tag_words(r->n_reads);
+    DevBuf d;
+    if (d.alloc(nw * 4) != cudaSuccess) return fail("tag allocation failed");
+    CK(cudaMemsetAsync(d.p, 0, nw * 4, c->stream));
+    CK(cudaMemcpyAsync(d.p, tags, nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->scratch, 0, 2 * sizeof(unsigned long long), c->stream));
+    CKR(search_launch(c, r, k, t, d.as<uint32_t>(), c->scratch));
+    unsigned long long cnt[2] = {0, 0};
+    CK(cudaMemcpyAsync(tags, d.p, nb, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(cnt, c->scratch, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (n_found) *n_found = cnt[0];
+    if (n_searched) *n_searched = cnt[1];
+    return 0;
+}
+
+// ------------------------------------------------------------- chunk loop ---
+extern "C" int commet_index_and_search_staged(commet_ctx *c, int k, int t, uint64_t max_kmer, commet_reads *index,
+                                              int n_sets, commet_reads *const *queries, uint32_t *const *d_tags,
+                                              uint64_t *searched, uint64_t *shared, uint64_t *stats)
+{
+    CKR(set_device(c));
+    if (n_sets < 0 || n_sets > 30) return fail("n_sets=%d unsupported (0..30)", n_sets);
+    std::vector<uint64_t> bounds;
+    uint64_t n_indexed = 0, n_kmers = 0;
+    CKR(chunk_plan(c, index, k, max_kmer, bounds, &n_indexed, &n_kmers));
+    for (int s = 0; s < n_sets; s++) CKR(prepare(c, queries[s], k));
+    uint64_t n_chunks = bounds.size() / 2;
+    // scratch: [2+2s] found total, [3+2s] searched in the last chunk
+    CK(cudaMemsetAsync(c->scratch, 0, 64 * sizeof(unsigned long long), c->stream));
+    const bool timed = stats && n_chunks <= 64;
+    std::vector<cudaEvent_t> ev;
+    if (n_chunks) CKR(commet_index_begin(c, k));
+    for (uint64_t ch = 0; ch < n_chunks; ch++) {
+        if (ch) CK(cudaMemsetAsync(c->filter, 0, c->filter_cap, c->stream));
+        cudaEvent_t e0, e1, e2;
+        if (timed) {
+            CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+            ev.push_back(e0); ev.push_back(e1); ev.push_back(e2);
+            CK(cudaEventRecord(e0, c->stream));
+        }
+        CKR(index_range(c, index, bounds[2 * ch], bounds[2 * ch + 1] - bounds[2 * ch], nullptr));
+        if (timed) CK(cudaEventRecord(e1, c->stream));
+        for (int s = 0; s < n_sets; s++) {
+            CK(cudaMemsetAsync(c->scratch + 3 + 2 * s, 0, sizeof(unsigned long long), c->stream));
+            CKR(search_launch(c, queries[s], k, t, d_tags[s], c->scratch + 2 + 2 * s));
+        }
+        if (timed) CK(cudaEventRecord(e2, c->stream));
+    }
+    unsigned long long h[64];
+    CK(cudaMemcpyAsync(h, c->scratch, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < n_sets; s++) {
+        if (shared) shared[s] = h[2 + 2 * s];
+        if (searched) searched[s] = h[3 + 2 * s];
+    }
+    if (stats) {
+        double t_index = 0, t_search = 0;
+        for (size_t i = 0; i + 2 < ev.size(); i += 3) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); t_index += ms;
+            cudaEventElapsedTime(&ms, ev[i + 1], ev[i + 2]); t_search += ms;
+        }
+        stats[0] = n_chunks; stats[1] = n_indexed; stats[2] = n_kmers;
+        stats[3] = (uint64_t)(t_index * 1e6); stats[4] = (uint64_t)(t_search * 1e6);
+        stats[5] = stats[6] = stats[7] = 0;
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    return 0;
+}
+
+extern "C" int commet_index_and_search(commet_ctx *c, int k, int t, uint64_t max_kmer, const uint8_t *ibases,
+                                       const uint64_t *ioffs, uint64_t n_index, int n_sets,
+                                       const uint8_t *const *qbases, const uint64_t *const *qoffs,
+                                       const uint64_t *n_query, uint8_t *const *tags, uint64_t *searched,
+                                       uint64_t *shared, uint64_t *stats)
+{
+    CKR(set_device(c));
+    if (n_sets < 0 || n_sets > 30) return fail("n_sets=%d unsupported (0..30)", n_sets);
+    commet_reads *idx = nullptr;
+    std::vector<commet_reads *> q(n_sets, nullptr);
+    std::vector<uint32_t *> dt(n_sets, nullptr);
+    int rc = commet_reads_upload(c, ibases, ioffs, n_index, &idx);
+    for (int s = 0; rc == 0 && s < n_sets; s++) {
+        rc = commet_reads_upload(c, qbases[s], qoffs[s], n_query[s], &q[s]);
+        if (rc == 0) {
+            uint64_t nw = tag_words(n_query[s]);
+            if (cudaMalloc(&dt[s], nw * 4) != cudaSuccess) rc = fail("tag allocation failed");
+            else if (cudaMemsetAsync(dt[s], 0, nw * 4, c->stream) != cudaSuccess) rc = fail("tag memset failed");
+        }
+    }
+    if (rc == 0) rc = commet_index_and_search_staged(c, k, t, max_kmer, idx, n_sets, q.data(), dt.data(), searched, shared, stats);
+    for (int s = 0; rc == 0 && s < n_sets; s++)
+        if (cudaMemcpyAsync(tags[s], dt[s], n_query[s] / 8 + 1, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+            rc = fail("tag download failed");
+    if (rc == 0 && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail("stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    commet_reads_free(idx);
+    for (int s = 0; s < n_sets; s++) { commet_reads_free(q[s]); if (dt[s]) cudaFree(dt[s]); }
+    return rc;
+}
+
+// --------------------------------------------------- stage 3: filter_reads --
+// exact shannon_index (filter_reads.cpp:265-306) from the device's counts, for
+// the few reads whose device value lies within the log-implementation margin
+// of the threshold: glibc's double log is what the reference calls.
+static float shannon_from_counts(const unsigned int cnt[5], unsigned int len)
+{
+    float index = 0;
+    for (int j = 0; j < 5; j++) {
+        float f = (float)cnt[j] / (float)len;
+        if (f != 0) index += (double)f * ::log((double)f) / ::log(2.0);
+    }
+    return fabsf(index);
+}
+
+extern "C" int commet_filter_reads_staged(commet_ctx *c, commet_reads *r, int64_t min_len, int64_t max_N,
+                                          float min_shannon, int64_t max_reads, uint32_t *d_bv, uint64_t *counters)
+{
+    CKR(set_device(c));
+    uint64_t n = r->n_reads;
+    uint64_t n_bv_words = tag_words(n);
+    uint64_t n_blocks = std::max<uint64_t>((std::max(n, n_bv_words * 32) + kFilterBlock - 1) / kFilterBlock, 1);
+    if (n_blocks > 0x7fffffffull) return fail("too many reads for one filter call");
+    FilterParams fp;
+    fp.min_len = min_len;
+    fp.max_N = max_N < 0 ? 2147483647LL : max_N;
+    fp.min_shannon = min_shannon;
+    fp.margin = 2e-5f;
+    if (max_reads < -1) max_reads = 0;          // `selected < max_reads` is false at once: nothing kept
+    const bool cut = max_reads >= 0 && (uint64_t)max_reads < n;
+    DevBuf totals, classes, border, nb, patch;
+    const unsigned int border_cap = 1u << 20;
+    if (totals.alloc(n_blocks * 4 * sizeof(unsigned int)) != cudaSuccess ||
+        border.alloc(border_cap * sizeof(BorderRec)) != cudaSuccess || nb.alloc(sizeof(unsigned int)) != cudaSuccess)
+        return fail("filter scratch allocation failed");
+    // class bytes are needed to locate a -m cutoff and to patch undecided reads' totals
+    if (classes.alloc(n ? n : 1) != cudaSuccess) return fail("filter class allocation failed");
+    CK(cudaMemsetAsync(nb.p, 0, sizeof(unsigned int), c->stream));
+    k_filter<<<(unsigned)n_blocks, kFilterBlock, 0, c->stream>>>(r->planes, r->offs, n, fp, d_bv, n_bv_words,
+                                                                 classes.as<uint8_t>(), totals.as<unsigned int>(),
+                                                                 border.as<BorderRec>(), border_cap, nb.as<unsigned int>());
+    c->launches++;
+    CK(cudaGetLastError());
+    unsigned int n_border = 0;
+    CK(cudaMemcpyAsync(&n_border, nb.p, sizeof n_border, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (n_border > border_cap)
+        return fail("%u reads sit within %g of the Shannon threshold (capacity %u): choose another -e", n_border,
+                    (double)fp.margin, border_cap);
+    if (n_border) {
+        std::vector<BorderRec> recs(n_border);
+        std::vector<uint8_t> cls(n_border);
+        CK(cudaMemcpy(recs.data(), border.p, n_border * sizeof(BorderRec), cudaMemcpyDeviceToHost));
+        for (unsigned int i = 0; i < n_border; i++)
+            cls[i] = shannon_from_counts(recs[i].cnt, recs[i].len) < min_shannon ? 3 : 0;
+        if (patch.alloc(n_border) != cudaSuccess) return fail("patch allocation failed");
+        CK(cudaMemcpyAsync(patch.p, cls.data(), n_border, cudaMemcpyHostToDevice, c->stream));
+        k_filter_patch<<<(n_border + 255) / 256, 256, 0, c->stream>>>(border.as<BorderRec>(), patch.as<uint8_t>(), n_border,
+                                                                     d_bv, classes.as<uint8_t>(), totals.as<unsigned int>());
+        c->launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    unsigned long long *out = c->scratch + 8;
+    k_filter_cutoff<<<1, 1024, 0, c->stream>>>(totals.as<unsigned int>(), n_blocks, classes.as<uint8_t>(), n,
+                                               cut ? (long long)max_reads : -1LL, out);
+    c->launches++;
+    CK(cudaGetLastError());
+    if (cut) {
+        k_clear_from<<<grid_for(c, n_bv_words, 256, 8), 256, 0, c->stream>>>(d_bv, out + 4, n_bv_words);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    unsigned long long h[5];
+    CK(cudaMemcpyAsync(h, out, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (counters) for (int i = 0; i < 4; i++) counters[i] = h[i];
+    return 0;
+}
+
+extern "C" int commet_filter_reads(commet_ctx *c, const uint8_t *bases, const uint64_t *offs, uint64_t n_reads,
+                                   int64_t min_len, int64_t max_N, float min_shannon, int64_t max_reads, uint8_t *bv,
+                                   uint64_t *counters)
+{
+    CKR(set_device(c));
+    commet_reads *r = nullptr;
+    CKR(commet_reads_upload(c, bases, offs, n_reads, &r));
+    DevBuf d;
+    uint64_t nw = tag_words(n_reads);
+    int rc = 0;
+    if (d.alloc(nw * 4) != cudaSuccess) rc = fail("bv allocation failed");
+    if (rc == 0) rc = commet_filter_reads_staged(c, r, min_len, max_N, min_shannon, max_reads, d.as<uint32_t>(), counters);
+    if (rc == 0 && cudaMemcpy(bv, d.p, n_reads / 8 + 1, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("bv download failed");
+    commet_reads_free(r);
+    return rc;
+}
+
+// ----------------------------------------------------------- stage 4: bvop --
+extern "C" int commet_bvop_dev(commet_ctx *c, int op, const void *d_a, const void *d_b, void *d_out, uint64_t n_bytes)
+{
+    CKR(set_device(c));
+    if (op < 0 || op > 3) return fail("unknown bv op %d", op);
+    if (n_bytes == 0) return 0;
+    if (((uintptr_t)d_a | (uintptr_t)d_out | (op == 3 ? 0 : (uintptr_t)d_b)) & 15) return fail("bvop buffers must be 16-byte aligned");
+    uint64_t n_vec = n_bytes / 16;
+    unsigned g = grid_for(c, std::max<uint64_t>(n_vec, 16), 256, 8);
+    const uint4 *a = static_cast<const uint4 *>(d_a), *b = static_cast<const uint4 *>(d_b);
+    uint4 *o = static_cast<uint4 *>(d_out);
+    switch (op) {
+    case 0: k_bvop<0><<<g, 256, 0, c->stream>>>(a, b, o, n_vec, n_bytes); break;
+    case 1: k_bvop<1><<<g, 256, 0, c->stream>>>(a, b, o, n_vec, n_bytes); break;
+    case 2: k_bvop<2><<<g, 256, 0, c->stream>>>(a, b, o, n_vec, n_bytes); break;
+    default: k_bvop<3><<<g, 256, 0, c->stream>>>(a, a, o, n_vec, n_bytes); break;
+    }
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int commet_bv_popcount_dev(commet_ctx *c, const void *d_bv, uint64_t n_bits, uint64_t *ones)
+{
+    CKR(set_device(c));
+    uint64_t n_bytes = n_bits / 8 + 1;
+    if ((uintptr_t)d_bv & 15) return fail("bv buffer must be 16-byte aligned");
+    unsigned long long *tot = c->scratch + 16;
+    CK(cudaMemsetAsync(tot, 0, sizeof *tot, c->stream));
+    uint64_t n_vec = n_bytes / 16;
+    k_popcount<<<grid_for(c, std::max<uint64_t>(n_vec, 16), 256, 8), 256, 0, c->stream>>>(static_cast<const uint4 *>(d_bv),
+                                                                                         n_vec, n_bytes, tot);
+    c->launches++;
+    CK(cudaGetLastError());
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, tot, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (ones) *ones = h > n_bits ? n_bits : h;      // boolean_vector.h:266-268
+    return 0;
+}
+
+extern "C" int commet_bvop(commet_ctx *c, int op, const uint8_t *a, const uint8_t *b, uint8_t *out, uint64_t n_bytes)
+{
+    CKR(set_device(c));
+    if (n_bytes == 0) return 0;
+    DevBuf da, db, dout;
+    if (da.alloc(n_bytes) != cudaSuccess || dout.alloc(n_bytes) != cudaSuccess || (op != 3 && db.alloc(n_bytes) != cudaSuccess))
+        return fail("bvop allocation failed");
+    CK(cudaMemcpyAsync(da.p, a, n_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (op != 3) CK(cudaMemcpyAsync(db.p, b, n_bytes, cudaMemcpyHostToDevice, c->stream));
+    CKR(commet_bvop_dev(c, op, da.p, db.p, dout.p, n_bytes));
+    CK(cudaMemcpyAsync(out, dout.p, n_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int commet_bv_popcount(commet_ctx *c, const uint8_t *bv, uint64_t n_bits, uint64_t *ones)
+{
+    CKR(set_device(c));
+    uint64_t n_bytes = n_bits / 8 + 1;
+    DevBuf d;
+    if (d.alloc(n_bytes) != cudaSuccess) return fail("popcount allocation failed");
+    CK(cudaMemcpyAsync(d.p, bv, n_bytes, cudaMemcpyHostToDevice, c->stream));
+    return commet_bv_popcount_dev(c, d.p, n_bits, ones);
+}
+
+// ------------------------------------------------------------ measurement ---
+extern "C" int commet_bench_random_sectors(commet_ctx *c, uint64_t bytes, uint64_t n_ops, int atomic_or, double *ns)
+{
+    CKR(set_device(c));
+    if (bytes < 4096 || (bytes & (bytes - 1))) return fail("bytes must be a power of two >= 4096");
+    DevBuf buf;
+    if (buf.alloc(bytes) != cudaSuccess) return fail("allocation of %llu bytes failed", (unsigned long long)bytes);
+    CK(cudaMemsetAsync(buf.p, 0, bytes, c->stream));
+    uint64_t mask = bytes / 4 - 1;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    unsigned g = grid_for(c, n_ops / 4, 256, 8);
+    for (int rep = 0; rep < 2; rep++) {          // first pass warms up, second is timed
+        if (rep == 1) CK(cudaEventRecord(e0, c->stream));
+        if (atomic_or) k_random_sectors<true><<<g, 256, 0, c->stream>>>(buf.as<uint32_t>(), mask, n_ops, c->scratch + 20);
+        else k_random_sectors<false><<<g, 256, 0, c->stream>>>(buf.as<uint32_t>(), mask, n_ops, c->scratch + 20);
+        c->launches++;
+    }
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ns) *ns = (double)ms * 1e6;
+    return 0;
+}

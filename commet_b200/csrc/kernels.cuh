@@ -1,0 +1,648 @@
+// Device code of the B200-native Commet hot path (sm_100a).
+//
+// Data layout in HBM:
+//   planes : uint4 per 32 consecutive bases of a read stream
+//            .x = H  bit-plane (1 for G,T)   -> key a   (hash_key.h:65-91)
+//            .y = L  bit-plane (1 for C,T)   -> key b ; c = H^L ; d = H|L
+//            .z = V  validity  (1 for ACGTacgt, alphabet.h:44-58)
+//            .w = W  "a k-mer starts here" for the k the stream was prepared
+//                    for: k valid bases that do not cross a read boundary
+//            bit j of a word = base 32*word + j (LSB first).
+//   filter : the bloom_filter.h byte array viewed as little-endian u32 words:
+//            key -> word key>>3, bit 8*((key>>1)&3) + (key&1 ? 3-j : 7-j).
+//   tags   : u32 words, bit r%32 of word r/32 = read r (= .bv payload bytes).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace commet {
+
+constexpr int kMaxK = 61;          // 64-bit window + batch of 4 positions
+constexpr int kSearchBatch = 4;    // a-probes issued together per lane
+
+// ---------------------------------------------------------------- loads ----
+__device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_nc_u4(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// 64 stream bits starting `sh` (0..31) bits into the 96-bit register window x0:x1:x2
+__device__ __forceinline__ uint64_t window64(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t sh)
+{
+    uint32_t lo = __funnelshift_r(x0, x1, sh);
+    uint32_t hi = __funnelshift_r(x1, x2, sh);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// ----------------------------------------------------------------- keys ----
+// hv/lv: k-mer window of the H and L planes, bit 0 = first base of the window.
+// Forward keys (HashKey::add, hash_key.h:65-91): first base most significant.
+// Reverse keys (HashKey::rv_add, hash_key.h:99-125): complement coding, first
+// base least significant -> no bit reversal needed.
+struct Keys { uint64_t a, b, c, d; };
+
+__device__ __forceinline__ Keys make_keys(uint64_t hv, uint64_t lv, int k, uint64_t mask, bool rev)
+{
+    Keys q;
+    if (rev) {
+        q.a = ~hv & mask;
+        q.b = ~lv & mask;
+    } else {
+        q.a = __brevll(hv) >> (64 - k);
+        q.b = __brevll(lv) >> (64 - k);
+    }
+    q.c = q.a ^ q.b;
+    q.d = q.a | q.b;
+    return q;
+}
+
+// BloomFilter byte/mask (bloom_filter.h:112-131) in the u32-word view
+__device__ __forceinline__ uint64_t key_word(uint64_t key) { return key >> 3; }
+__device__ __forceinline__ uint32_t key_bit(uint64_t key, int j)
+{
+    uint32_t byte = (uint32_t)(key >> 1) & 3u;
+    uint32_t in_byte = (key & 1) ? (3 - j) : (7 - j);
+    return 1u << (byte * 8 + in_byte);
+}
+
+// ------------------------------------------------------------- staging ----
+// ASCII -> H/L/V planes, 32 bases per thread via two 16-byte vector loads.
+// `bases` is zero-padded to a multiple of 32 bytes.
+__device__ __forceinline__ uint32_t gather4(uint32_t x)   // bits 0,8,16,24 -> bits 0..3
+{
+    return ((x * 0x00204081u) >> 21) & 0xFu;
+}
+
+__global__ void __launch_bounds__(256)
+k_encode(const uint4 *__restrict__ bases16, uint4 *__restrict__ planes, uint64_t n_words)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
+        uint4 q0 = ld_nc_u4(bases16 + 2 * i);
+        uint4 q1 = ld_nc_u4(bases16 + 2 * i + 1);
+        uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        uint32_t H = 0, L = 0, V = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            uint32_t c = w[j];
+            uint32_t h = (c >> 2) & 0x01010101u;                 // A,C ->0  G,T ->1
+            uint32_t l = ((c >> 1) ^ (c >> 2)) & 0x01010101u;    // A,G ->0  C,T ->1
+            uint32_t x = c | 0x20202020u;                         // fold case
+            uint32_t v = (__vcmpeq4(x, 0x61616161u) | __vcmpeq4(x, 0x63636363u) |
+                          __vcmpeq4(x, 0x67676767u) | __vcmpeq4(x, 0x74747474u)) & 0x01010101u;
+            H |= gather4(h) << (4 * j);
+            L |= gather4(l) << (4 * j);
+            V |= gather4(v) << (4 * j);
+        }
+        planes[i] = make_uint4(H, L, V, 0u);
+    }
+}
+
+// start-of-read marks: bit offs[r] of S for every read r
+__global__ void __launch_bounds__(256)
+k_mark_starts(const uint64_t *__restrict__ offs, uint64_t n_reads, uint32_t *__restrict__ S)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += stride) {
+        uint64_t o = offs[r];
+        atomicOr(&S[o >> 5], 1u << (o & 31));
+    }
+}
+
+// W plane: position b starts a k-mer iff V[b..b+k) are all set and no read
+// starts at b+1..b+k-1 (index_reads.h:52-58: hash.clear() per read and per
+// non-ACGT char; a k-mer is fed once hash_size >= k).  One warp per word.
+__global__ void __launch_bounds__(256)
+k_windows(uint4 *__restrict__ planes, const uint32_t *__restrict__ S, uint64_t n_words,
+          uint64_t n_bases, int k)
+{
+    const uint64_t mask = (k >= 64) ? ~0ull : ((1ull << k) - 1);
+    uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    const uint32_t *P = reinterpret_cast<const uint32_t *>(planes);
+    for (uint64_t wi = warp; wi < n_words; wi += n_warps) {
+        uint32_t v0 = P[4 * wi + 2], v1 = P[4 * (wi + 1) + 2], v2 = P[4 * (wi + 2) + 2];
+        uint32_t s0 = S[wi], s1 = S[wi + 1], s2 = S[wi + 2];
+        uint64_t vw = window64(v0, v1, v2, lane);
+        uint64_t sw = window64(s0, s1, s2, lane);
+        uint64_t b = 32 * wi + lane;
+        bool ok = ((vw & mask) == mask) && ((sw & mask & ~1ull) == 0) && (b + k <= n_bases);
+        uint32_t W = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) reinterpret_cast<uint32_t *>(planes)[4 * wi + 3] = W;
+    }
+}
+
+// per-read k-mer count = popcount of W over the read's positions
+__global__ void __launch_bounds__(256)
+k_kmer_counts(const uint4 *__restrict__ planes, const uint64_t *__restrict__ offs,
+              uint64_t n_reads, uint32_t *__restrict__ counts, unsigned long long *__restrict__ total)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long local = 0;
+    const uint32_t *P = reinterpret_cast<const uint32_t *>(planes);
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += stride) {
+        uint64_t o = offs[r], e = offs[r + 1];
+        uint32_t c = 0;
+        for (uint64_t wi = o >> 5; (wi << 5) < e; wi++) {
+            uint32_t W = P[4 * wi + 3];
+            uint64_t lo = wi << 5;
+            if (lo < o) W &= ~0u << (o - lo);
+            if (lo + 32 > e) W &= ~0u >> (lo + 32 - e);
+            c += __popc(W);
+        }
+        counts[r] = c;
+        local += c;
+    }
+    for (int d = 16; d; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(total, local);
+}
+
+// ------------------------------------------------------- stage 1: index ----
+// index_reads inner loop (index_reads.h:52-58) + BloomFilter::feed
+// (bloom_filter.h:112-118), flat over stream positions [b0, b1): one warp per
+// 32-position word, plane words are warp-uniform (broadcast) loads, each lane
+// owns one k-mer start and issues four fire-and-forget 32-bit RED.OR.
+__global__ void __launch_bounds__(256)
+k_index(uint32_t *__restrict__ filter, const uint4 *__restrict__ planes, uint64_t b0, uint64_t b1,
+        int k, unsigned long long *__restrict__ n_kmers)
+{
+    const uint64_t mask = (1ull << k) - 1;
+    uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    uint64_t w_first = b0 >> 5, w_end = (b1 + 31) >> 5;
+    unsigned long long local = 0;
+    for (uint64_t wi = w_first + warp; wi < w_end; wi += n_warps) {
+        uint4 q0 = planes[wi];
+        uint32_t W = q0.w;
+        uint64_t lo = wi << 5;
+        if (lo < b0) W &= ~0u << (b0 - lo);
+        if (lo + 32 > b1) W &= ~0u >> (lo + 32 - b1);
+        if (W == 0) continue;                       // warp-uniform
+        uint4 q1 = planes[wi + 1], q2 = planes[wi + 2];
+        if ((W >> lane) & 1u) {
+            uint64_t hv = window64(q0.x, q1.x, q2.x, lane);
+            uint64_t lv = window64(q0.y, q1.y, q2.y, lane);
+            Keys q = make_keys(hv, lv, k, mask, false);
+            atomicOr(filter + key_word(q.a), key_bit(q.a, 0));
+            atomicOr(filter + key_word(q.b), key_bit(q.b, 1));
+            atomicOr(filter + key_word(q.c), key_bit(q.c, 2));
+            atomicOr(filter + key_word(q.d), key_bit(q.d, 3));
+        }
+        local += __popc(W);
+    }
+    if (lane == 0 && local && n_kmers) atomicAdd(n_kmers, local);
+}
+
+// ------------------------------------------------------ stage 2: search ----
+// BloomFilter::is_found (bloom_filter.h:124-131): b, c, d after a passed,
+// short-circuit in the reference's order.
+__device__ __forceinline__ bool probe_bcd(const uint32_t *__restrict__ filter, const Keys &q)
+{
+    if (!(ld_nc_u32(filter + key_word(q.b)) & key_bit(q.b, 1))) return false;
+    if (!(ld_nc_u32(filter + key_word(q.c)) & key_bit(q.c, 2))) return false;
+    return (ld_nc_u32(filter + key_word(q.d)) & key_bit(q.d, 3)) != 0;
+}
+
+// One strand of search_reads (search_reads.h:46-64 forward, :66-83 reverse):
+// left-to-right greedy scan; on a hit seen++ and, unless seen >= t, the next
+// candidate is k positions later (hash.clear()).  The lane keeps a 96-bit
+// register window of the H/L/W planes and issues kSearchBatch a-probes at once.
+__device__ __forceinline__ bool scan_strand(const uint32_t *__restrict__ filter,
+                                            const uint4 *__restrict__ planes, uint64_t o,
+                                            uint32_t npos, int k, int t, uint64_t mask, bool rev)
+{
+    constexpr int U = kSearchBatch;
+    uint64_t wi = o >> 5;
+    uint4 q0 = planes[wi], q1 = planes[wi + 1], q2 = planes[wi + 2];
+    int seen = 0;
+    uint32_t p = 0;
+    while (p < npos) {
+        uint64_t b = o + p;
+        uint64_t need = b >> 5;
+        if (need != wi) {
+            if (need - wi >= 3) {
+                wi = need;
+                q0 = planes[wi]; q1 = planes[wi + 1]; q2 = planes[wi + 2];
+            } else {
+                do {
+                    q0 = q1; q1 = q2; q2 = planes[wi + 3]; wi++;
+                } while (wi != need);
+            }
+        }
+        uint32_t sh = (uint32_t)b & 31u;
+        uint32_t rem = npos - p;
+        uint32_t wv = __funnelshift_r(q0.w, q1.w, sh);
+        uint32_t m = wv & ((rem >= (uint32_t)U) ? ((1u << U) - 1u) : ((1u << rem) - 1u));
+        if (m == 0) {
+            // no k-mer starts in this batch: jump to the next W bit among the 32 visible ones
+            uint32_t vis = rem < 32u ? rem : 32u;
+            uint32_t mv = (vis >= 32u) ? wv : (wv & ((1u << vis) - 1u));
+            p += mv ? (uint32_t)(__ffs(mv) - 1) : vis;
+            continue;
+        }
+        uint64_t hv = window64(q0.x, q1.x, q2.x, sh);
+        uint64_t lv = window64(q0.y, q1.y, q2.y, sh);
+        uint32_t av[U];
+        uint64_t ka[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (rev) ka[u] = ~(hv >> u) & mask;
+            else ka[u] = __brevll(hv >> u) >> (64 - k);
+            av[u] = 0;
+            if ((m >> u) & 1u) av[u] = ld_nc_u32(filter + key_word(ka[u]));
+        }
+        bool hit = false;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!hit && ((m >> u) & 1u) && (av[u] & key_bit(ka[u], 0))) {
+                Keys q = make_keys(hv >> u, lv >> u, k, mask, rev);
+                if (probe_bcd(filter, q)) {
+                    hit = true;
+                    seen++;
+                    p += (uint32_t)u + (uint32_t)k;
+                }
+            }
+        }
+        if (hit) {
+            if (seen >= t) return true;
+        } else {
+            p += U;
+        }
+    }
+    return false;
+}
+
+// search_reads (search_reads.h:34-87): one lane per read, grid-stride.
+// counters[0] += newly found, counters[1] += reads scanned.
+__global__ void __launch_bounds__(256)
+k_search(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
+         const uint64_t *__restrict__ offs, uint64_t n_reads, int k, int t,
+         uint32_t *__restrict__ tags, unsigned long long *__restrict__ counters)
+{
+    const uint64_t mask = (1ull << k) - 1;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned int found = 0, searched = 0;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += stride) {
+        if ((tags[r >> 5] >> (r & 31)) & 1u) continue;        // file_manager.h:99
+        searched++;
+        uint64_t o = offs[r];
+        uint64_t len = offs[r + 1] - o;
+        if (len < (uint64_t)k) continue;
+        uint32_t npos = (uint32_t)(len - k + 1);
+        bool f = scan_strand(filter, planes, o, npos, k, t, mask, false);
+        if (!f) f = scan_strand(filter, planes, o, npos, k, t, mask, true);
+        if (f) {
+            atomicOr(&tags[r >> 5], 1u << (r & 31));
+            found++;
+        }
+    }
+    for (int d = 16; d; d >>= 1) {
+        found += __shfl_xor_sync(0xffffffffu, found, d);
+        searched += __shfl_xor_sync(0xffffffffu, searched, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (found) atomicAdd(&counters[0], (unsigned long long)found);
+        if (searched) atomicAdd(&counters[1], (unsigned long long)searched);
+    }
+}
+
+// ------------------------------------------------ stage 3: filter_reads ----
+// classes: 0 selected, 1 too short, 2 too many N, 3 low Shannon, 4 undecided
+// (|H - e| within the device/glibc log margin: resolved by the host from the
+// exact counts written to `border`).
+struct FilterParams {
+    long long min_len;
+    long long max_N;
+    float min_shannon;
+    float margin;
+};
+struct BorderRec { unsigned long long read; unsigned int cnt[5]; unsigned int len; };
+
+__device__ __forceinline__ void base_counts(const uint4 *__restrict__ planes, uint64_t o, uint64_t e,
+                                            unsigned int cnt[5])
+{
+    unsigned int a = 0, c = 0, g = 0, tt = 0;
+    for (uint64_t wi = o >> 5; (wi << 5) < e; wi++) {
+        uint4 q = planes[wi];
+        uint32_t m = q.z;
+        uint64_t lo = wi << 5;
+        if (lo < o) m &= ~0u << (o - lo);
+        if (lo + 32 > e) m &= ~0u >> (lo + 32 - e);
+        a += __popc(~q.x & ~q.y & m);
+        c += __popc(~q.x & q.y & m);
+        g += __popc(q.x & ~q.y & m);
+        tt += __popc(q.x & q.y & m);
+    }
+    cnt[0] = a; cnt[1] = c; cnt[2] = g; cnt[3] = tt;
+    cnt[4] = (unsigned int)(e - o) - (a + c + g + tt);
+}
+
+// shannon_index (filter_reads.cpp:265-306): float freq, double term, float sum.
+__device__ __forceinline__ float shannon_dev(const unsigned int cnt[5], unsigned int len)
+{
+    float idx = 0.f;
+    const float flen = (float)len;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        float f = __fdiv_rn((float)cnt[j], flen);
+        if (f != 0.f) {
+            double term = __ddiv_rn(__dmul_rn((double)f, log((double)f)), 0.6931471805599453);
+            idx = __double2float_rn(__dadd_rn((double)idx, term));
+        }
+    }
+    return fabsf(idx);
+}
+
+__device__ __forceinline__ int classify_read(const uint4 *__restrict__ planes, uint64_t o, uint64_t e,
+                                             const FilterParams &fp, unsigned int cnt[5])
+{
+    long long len = (long long)(e - o);
+    if (len < fp.min_len) return 1;                       // filter_reads.cpp:189
+    base_counts(planes, o, e, cnt);
+    if ((long long)cnt[4] > fp.max_N) return 2;           // :192
+    if (fp.min_shannon > 0.f) {                           // fabs() >= 0: e <= 0 never drops
+        float h = shannon_dev(cnt, (unsigned int)len);
+        if (fabsf(h - fp.min_shannon) <= fp.margin) return 4;
+        if (h < fp.min_shannon) return 3;                 // :195
+    }
+    return 0;
+}
+
+// One block = 1024 consecutive reads.  Writes the selection bits (ballot,
+// one store per 32 reads), the class of every read (1 byte, only when
+// `classes` != null, i.e. when a -m cutoff must be located) and per-block
+// class totals [4].
+constexpr int kFilterBlock = 1024;
+
+__global__ void __launch_bounds__(kFilterBlock)
+k_filter(const uint4 *__restrict__ planes, const uint64_t *__restrict__ offs, uint64_t n_reads,
+         FilterParams fp, uint32_t *__restrict__ bv, uint64_t n_bv_words,
+         uint8_t *__restrict__ classes,
+         unsigned int *__restrict__ block_totals, BorderRec *__restrict__ border,
+         unsigned int border_cap, unsigned int *__restrict__ n_border)
+{
+    __shared__ unsigned int tot[4];
+    if (threadIdx.x < 4) tot[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t r = (uint64_t)blockIdx.x * kFilterBlock + threadIdx.x;
+    int cls = -1;
+    if (r < n_reads) {
+        unsigned int cnt[5];
+        cls = classify_read(planes, offs[r], offs[r + 1], fp, cnt);
+        if (cls == 4) {
+            unsigned int slot = atomicAdd(n_border, 1u);
+            if (slot < border_cap) {
+                BorderRec br;
+                br.read = r;
+                for (int j = 0; j < 5; j++) br.cnt[j] = cnt[j];
+                br.len = (unsigned int)(offs[r + 1] - offs[r]);
+                border[slot] = br;
+            }
+            cls = 0;    // provisional; the host patches classes/bits/totals
+        }
+        if (classes) classes[r] = (uint8_t)cls;
+    }
+    uint32_t sel = __ballot_sync(0xffffffffu, cls == 0);
+    if ((threadIdx.x & 31) == 0 && (r >> 5) < n_bv_words) bv[r >> 5] = sel;   // padding bits stay 0
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        uint32_t mc = __ballot_sync(0xffffffffu, cls == (c == 3 ? 0 : c + 1));
+        if ((threadIdx.x & 31) == 0 && mc) atomicAdd(&tot[c], __popc(mc));
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) block_totals[4 * (uint64_t)blockIdx.x + threadIdx.x] = tot[threadIdx.x];
+}
+
+// apply host decisions for the undecided reads: newcls[i] for border[i].read
+__global__ void k_filter_patch(const BorderRec *__restrict__ border, const uint8_t *__restrict__ newcls,
+                               unsigned int n, uint32_t *__restrict__ bv, uint8_t *__restrict__ classes,
+                               unsigned int *__restrict__ block_totals)
+{
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (newcls[i] == 0) return;                      // stays selected
+    uint64_t r = border[i].read;
+    atomicAnd(&bv[r >> 5], ~(1u << (r & 31)));
+    if (classes) classes[r] = newcls[i];
+    uint64_t blk = r / kFilterBlock;
+    atomicSub(&block_totals[4 * blk + 3], 1u);       // selected--
+    atomicAdd(&block_totals[4 * blk + (newcls[i] - 1)], 1u);
+}
+
+// The -m cutoff (filter_reads.cpp:188,203-205): the loop stops once
+// max_reads reads are selected; counters only cover reads before the stop and
+// every later bit is cleared.  Single block: locate the stop from the block
+// totals, then the exact read inside that block from the class bytes.
+// out[0..3] = rm_len, rm_N, rm_shannon, selected ; out[4] = cutoff position.
+__global__ void __launch_bounds__(1024)
+k_filter_cutoff(const unsigned int *__restrict__ block_totals, uint64_t n_blocks,
+                const uint8_t *__restrict__ classes, uint64_t n_reads, long long max_reads,
+                unsigned long long *__restrict__ out)
+{
+    __shared__ unsigned long long part[1024][4];
+    __shared__ unsigned long long base[4];
+    __shared__ unsigned long long stop_block;
+    const unsigned int tid = threadIdx.x;
+    uint64_t per = (n_blocks + 1023) / 1024;
+    uint64_t lo = tid * per, hi = lo + per < n_blocks ? lo + per : n_blocks;
+    unsigned long long s[4] = {0, 0, 0, 0};
+    for (uint64_t b = lo; b < hi; b++)
+        for (int c = 0; c < 4; c++) s[c] += block_totals[4 * b + c];
+    for (int c = 0; c < 4; c++) part[tid][c] = s[c];
+    if (tid == 0) stop_block = n_blocks;
+    __syncthreads();
+    if (tid == 0) {
+        // serial scan over 1024 partials, then over the owning thread's range
+        unsigned long long acc[4] = {0, 0, 0, 0};
+        unsigned int owner = 1024;
+        for (unsigned int i = 0; i < 1024; i++) {
+            if (max_reads >= 0 && acc[3] + part[i][3] >= (unsigned long long)max_reads) { owner = i; break; }
+            for (int c = 0; c < 4; c++) acc[c] += part[i][c];
+        }
+        if (owner < 1024) {
+            uint64_t b = owner * per, e = b + per < n_blocks ? b + per : n_blocks;
+            for (; b < e; b++) {
+                if (acc[3] + block_totals[4 * b + 3] >= (unsigned long long)max_reads) break;
+                for (int c = 0; c < 4; c++) acc[c] += block_totals[4 * b + c];
+            }
+            stop_block = b;
+        }
+        for (int c = 0; c < 4; c++) base[c] = acc[c];
+    }
+    __syncthreads();
+    if (stop_block >= n_blocks) {            // never reached: counters are the grand totals
+        if (tid == 0) {
+            for (int c = 0; c < 4; c++) out[c] = base[c];
+            out[4] = n_reads;
+        }
+        return;
+    }
+    // inside the stop block: inclusive scan of selected flags over its 1024 reads
+    __shared__ unsigned int scan[1024];
+    uint64_t r = stop_block * kFilterBlock + tid;
+    int cls = (r < n_reads) ? classes[r] : -1;
+    scan[tid] = (cls == 0);
+    __syncthreads();
+    for (unsigned int d = 1; d < 1024; d <<= 1) {
+        unsigned int v = (tid >= d) ? scan[tid - d] : 0;
+        __syncthreads();
+        scan[tid] += v;
+        __syncthreads();
+    }
+    unsigned long long need = (unsigned long long)max_reads - base[3];   // >= 1 selected reads from this block
+    __shared__ unsigned int cut;     // index within block of the read that reaches max_reads
+    if (tid == 0) cut = 1024;
+    __syncthreads();
+    if (max_reads == 0) { if (tid == 0) cut = 0; }
+    else if (cls == 0 && scan[tid] == need) cut = tid;
+    __syncthreads();
+    // reads [0, cut] of the block are processed (cut itself is the last selected one);
+    // with max_reads == 0 nothing is processed at all.
+    unsigned int last = (max_reads == 0) ? 0 : cut + 1;     // number of processed reads in block
+    __shared__ unsigned int cnt[4];
+    if (tid < 4) cnt[tid] = 0;
+    __syncthreads();
+    if (tid < last && cls >= 0) atomicAdd(&cnt[cls == 0 ? 3 : cls - 1], 1u);
+    __syncthreads();
+    if (tid == 0) {
+        for (int c = 0; c < 4; c++) out[c] = base[c] + cnt[c];
+        out[4] = stop_block * kFilterBlock + last;
+    }
+}
+
+// clear bits [cutoff, n) (untag_last_reads, read_file.h:76-81)
+__global__ void __launch_bounds__(256)
+k_clear_from(uint32_t *__restrict__ bv, const unsigned long long *__restrict__ cutoff_p, uint64_t n_words)
+{
+    uint64_t cutoff = *cutoff_p;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t w = (cutoff >> 5) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+        if ((w << 5) >= cutoff) bv[w] = 0;
+        else bv[w] &= ~(~0u << (cutoff - (w << 5)));
+    }
+}
+
+// --------------------------------------------------------- stage 4: bvop ----
+// BooleanVector::full_and/or/and_not/not (boolean_vector.h:418-462): 16-byte
+// vectors grid-stride, byte tail by the last threads.
+template <int OP>
+__device__ __forceinline__ uint32_t bv_apply(uint32_t a, uint32_t b)
+{
+    if (OP == 0) return a & b;
+    if (OP == 1) return a | b;
+    if (OP == 2) return a & ~b;
+    return ~a;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256)
+k_bvop(const uint4 *__restrict__ a, const uint4 *__restrict__ b, uint4 *__restrict__ out,
+       uint64_t n_vec, uint64_t n_bytes)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint64_t i = i0; i < n_vec; i += stride) {
+        uint4 x = ld_nc_u4(a + i);
+        uint4 y = (OP == 3) ? x : ld_nc_u4(b + i);
+        uint4 r;
+        r.x = bv_apply<OP>(x.x, y.x); r.y = bv_apply<OP>(x.y, y.y);
+        r.z = bv_apply<OP>(x.z, y.z); r.w = bv_apply<OP>(x.w, y.w);
+        out[i] = r;
+    }
+    const uint8_t *a8 = reinterpret_cast<const uint8_t *>(a);
+    const uint8_t *b8 = reinterpret_cast<const uint8_t *>(b);
+    uint8_t *o8 = reinterpret_cast<uint8_t *>(out);
+    for (uint64_t j = n_vec * 16 + i0; j < n_bytes; j += stride)
+        o8[j] = (uint8_t)bv_apply<OP>(a8[j], (OP == 3) ? 0u : b8[j]);
+}
+
+// nb_one (boolean_vector.h:244-270): popcount of all n_bytes (clamp on host)
+__global__ void __launch_bounds__(256)
+k_popcount(const uint4 *__restrict__ a, uint64_t n_vec, uint64_t n_bytes,
+           unsigned long long *__restrict__ total)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long local = 0;
+    for (uint64_t i = i0; i < n_vec; i += stride) {
+        uint4 x = ld_nc_u4(a + i);
+        local += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+    }
+    const uint8_t *a8 = reinterpret_cast<const uint8_t *>(a);
+    for (uint64_t j = n_vec * 16 + i0; j < n_bytes; j += stride) local += __popc((uint32_t)a8[j]);
+    for (int d = 16; d; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+    __shared__ unsigned long long ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long s = 0;
+        for (int i = 0; i < 8; i++) s += ws[i];
+        if (s) atomicAdd(total, s);
+    }
+}
+
+// filter |= other (multi-GPU merge of partial filters; `other` may be peer memory)
+__global__ void __launch_bounds__(256)
+k_or_into(uint4 *__restrict__ dst, const uint4 *__restrict__ src, uint64_t n_vec)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+        uint4 s = ld_nc_u4(src + i);
+        if ((s.x | s.y | s.z | s.w) == 0) continue;      // sparse partials: skip the write
+        uint4 d = dst[i];
+        d.x |= s.x; d.y |= s.y; d.z |= s.z; d.w |= s.w;
+        dst[i] = d;
+    }
+}
+
+// ------------------------------------------------- measurement kernels ----
+// random 32-byte-sector ceilings: every lane touches an independent random
+// sector (one u32 load, or one RED.OR) of a `n_words`-word buffer.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+template <bool ATOMIC>
+__global__ void __launch_bounds__(256)
+k_random_sectors(uint32_t *__restrict__ buf, uint64_t n_words_mask, uint64_t n_ops,
+                 unsigned long long *__restrict__ sink)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t acc = 0;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n_ops; i += 4 * stride) {
+        uint64_t x0 = splitmix64(i) & n_words_mask, x1 = splitmix64(i + stride) & n_words_mask;
+        uint64_t x2 = splitmix64(i + 2 * stride) & n_words_mask, x3 = splitmix64(i + 3 * stride) & n_words_mask;
+        if (ATOMIC) {
+            atomicOr(buf + x0, 1u << (x0 & 31)); atomicOr(buf + x1, 1u << (x1 & 31));
+            atomicOr(buf + x2, 1u << (x2 & 31)); atomicOr(buf + x3, 1u << (x3 & 31));
+        } else {
+            uint32_t v0 = ld_nc_u32(buf + x0), v1 = ld_nc_u32(buf + x1);
+            uint32_t v2 = ld_nc_u32(buf + x2), v3 = ld_nc_u32(buf + x3);
+            acc += v0 + v1 + v2 + v3;
+        }
+    }
+    for (; i < n_ops; i += stride) {
+        uint64_t x = splitmix64(i) & n_words_mask;
+        if (ATOMIC) atomicOr(buf + x, 1u << (x & 31));
+        else acc += ld_nc_u32(buf + x);
+    }
+    if (!ATOMIC && acc == 0x12345678u) atomicAdd(sink, 1ull);
+}
+
+}  // namespace commet

@@ -1,0 +1,178 @@
+/*
+ * commet_b200.h -- C-ABI of the B200-native Commet hot path.
+ *
+ * The reference (pierrepeterlongo/commet) has no plugin/FFI API: its tools
+ * #include header-only classes.  This ABI is what a maintainer would bind in
+ * place of those headers; each entry point names the reference interface it
+ * replaces (file:line relative to the reference root).  INTEGRATION.md shows
+ * the reference-side call sites.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; the message is in
+ *     commet_last_error() (thread-local).  There is NO CPU fallback: without
+ *     a CUDA device commet_ctx_create fails.
+ *   - plain pointers are caller-owned HOST memory; `d_` pointers are DEVICE
+ *     memory of the context's device.
+ *   - a read stream is `bases` (concatenated sequence bytes, no separators)
+ *     plus `offs[0..n_reads]` byte offsets; read i = bases[offs[i]..offs[i+1]).
+ *     It is the "valid read stream" of a set: what FileManager::
+ *     get_next_read_to_compare yields (include/file_manager.h:88-112).
+ *   - boolean vectors use the .bv payload layout of include/boolean_vector.h:
+ *     n/8+1 bytes, bit i of the vector = bit (i%8) of byte i/8.
+ *   - one context = one GPU = one CUDA stream; a context is not thread-safe.
+ */
+#ifndef COMMET_B200_H_
+#define COMMET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COMMET_B200_ABI_VERSION 1
+
+typedef struct commet_ctx commet_ctx;
+typedef struct commet_reads commet_reads;   /* device-resident, 2-bit encoded read stream */
+
+/* ---- context ------------------------------------------------------------ */
+const char *commet_last_error(void);
+int commet_abi_version(void);
+int commet_device_count(void);
+int commet_ctx_create(int device, commet_ctx **out);
+void commet_ctx_destroy(commet_ctx *ctx);
+int commet_ctx_sync(commet_ctx *ctx);
+/* CUDA stream of the context as a void* (cudaStream_t); for event timing by the host language. */
+void *commet_ctx_stream(commet_ctx *ctx);
+/* number of kernels launched by this context since creation */
+uint64_t commet_ctx_launches(commet_ctx *ctx);
+
+/* pinned host staging memory (cudaHostAlloc) for read buffers */
+void *commet_host_alloc(size_t bytes);
+void commet_host_free(void *p);
+
+/* ---- parameters fixed by the reference ---------------------------------- */
+/* filter size in bytes = 2^(k-1)            include/bloom_filter.h:73-76 */
+uint64_t commet_filter_bytes(int k);
+/* max k-mers per index chunk = (unsigned long)(1e9 / 2^(33-k))
+ *                                            src/index_and_search.cpp:73,146 */
+uint64_t commet_max_kmer(int k);
+
+/* ---- read staging: Alphabet + HashKey's per-base coding ------------------
+ * Replaces Alphabet::is_in (include/alphabet.h:44-58) and the per-char
+ * branches of HashKey::add/rv_add (include/hash_key.h:65-125): bases are
+ * turned on the device into bit-planes H (G,T), L (C,T), V (ACGTacgt).
+ * upload: H2D copy from host memory + encode.  from_device: encode only. */
+int commet_reads_upload(commet_ctx *ctx, const uint8_t *bases, const uint64_t *offs,
+                        uint64_t n_reads, commet_reads **out);
+int commet_reads_from_device(commet_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offs,
+                             uint64_t n_reads, uint64_t n_bases, commet_reads **out);
+void commet_reads_free(commet_reads *r);
+uint64_t commet_reads_count(const commet_reads *r);
+uint64_t commet_reads_bases(const commet_reads *r);
+
+/* Number of k-mers index_reads would feed for each read (windows of k
+ * consecutive ACGTacgt chars, include/index_reads.h:52-58). counts: n_reads u32. */
+int commet_reads_kmer_counts(commet_ctx *ctx, commet_reads *r, int k, uint32_t *counts);
+
+/* ---- chunk plan: the stop rule of index_reads -----------------------------
+ * include/index_reads.h:48-49,60 + src/index_and_search.cpp:255: a chunk ends
+ * after the read at which the cumulative k-mer count reaches max_kmer; the
+ * next read is fetched and lost.  Fills bounds[2*c] = first read, bounds[2*c+1]
+ * = one past the last read of chunk c (cap = capacity in chunks); *n_chunks =
+ * number of chunks (may exceed cap: call again with a larger buffer);
+ * *n_indexed = reads indexed over all chunks. */
+int commet_chunk_plan(commet_ctx *ctx, commet_reads *r, int k, uint64_t max_kmer,
+                      uint64_t *bounds, uint64_t cap, uint64_t *n_chunks, uint64_t *n_indexed);
+
+/* ---- stage 1: BloomFilter + index_reads ----------------------------------
+ * begin: BloomFilter::BloomFilter (include/bloom_filter.h:61-81): 2^(k-1)
+ *        zeroed bytes on the device (re-used across calls with the same k).
+ * add:   index_reads' inner loop (include/index_reads.h:49-61) for reads
+ *        [first, first+count): HashKey::add + BloomFilter::feed
+ *        (include/bloom_filter.h:112-118) for every k-mer.
+ * filter_ptr: device address of the bloom_filter.h-layout byte array. */
+int commet_index_begin(commet_ctx *ctx, int k);
+int commet_index_add(commet_ctx *ctx, commet_reads *r, uint64_t first, uint64_t count);
+void *commet_index_filter_ptr(commet_ctx *ctx);
+/* copy the filter to host memory (tests) */
+int commet_index_download(commet_ctx *ctx, uint8_t *out, uint64_t bytes);
+/* copy a host-built filter to the device (tests: probe a reference-built filter) */
+int commet_index_upload(commet_ctx *ctx, int k, const uint8_t *filter, uint64_t bytes);
+/* multi-GPU merge step: filter |= d_other (word-wise OR of a peer's partial
+ * filter, n bytes from byte offset `offset`); d_other may be peer memory. */
+int commet_index_or(commet_ctx *ctx, const void *d_other, uint64_t offset, uint64_t bytes);
+
+/* ---- stage 2: search_reads ------------------------------------------------
+ * include/search_reads.h:34-87 against the context's current filter: for
+ * every read whose bit in `tags` is 0 (FileManager skips tagged reads,
+ * include/file_manager.h:99): forward greedy scan, then reverse-complement
+ * scan; sets the read's bit when >= t non-overlapping k-mers are found.
+ * tags: n_reads/8+1 bytes, read AND written.  *n_found = newly tagged reads
+ * (search_reads' return value), *n_searched = reads scanned (:39,44).
+ * _dev: tags live on the device as ceil(n/32) u32 words; counters[0]+=found,
+ * counters[1]=searched (device u64[2]); nothing is copied to the host. */
+int commet_search(commet_ctx *ctx, commet_reads *r, int k, int t, uint8_t *tags,
+                  uint64_t *n_found, uint64_t *n_searched);
+int commet_search_dev(commet_ctx *ctx, commet_reads *r, int k, int t, uint32_t *d_tags,
+                      uint64_t *d_counters);
+
+/* ---- the chunk loop of index_and_search's main ------------------------------
+ * src/index_and_search.cpp:241-277: while reads remain: index one chunk,
+ * search every query set against it.  tags[s]: n_query[s]/8+1 bytes each,
+ * zero-initialised by the callee (file_bvs.set_all_false, file_manager.h:169).
+ * searched[s] = last chunk's count, shared[s] = sum over chunks, exactly the
+ * numbers of the "[indexed X, searched Y, shared Z]" log line (:286).
+ * stats (optional, u64[8]): [0] chunks [1] indexed reads [2] indexed k-mers
+ * [3] ns index kernels [4] ns search kernels (device time, CUDA events). */
+int commet_index_and_search(commet_ctx *ctx, int k, int t, uint64_t max_kmer,
+                            const uint8_t *ibases, const uint64_t *ioffs, uint64_t n_index,
+                            int n_sets, const uint8_t *const *qbases,
+                            const uint64_t *const *qoffs, const uint64_t *n_query,
+                            uint8_t *const *tags, uint64_t *searched, uint64_t *shared,
+                            uint64_t *stats);
+/* same loop on already-staged streams (device-resident inputs) */
+int commet_index_and_search_staged(commet_ctx *ctx, int k, int t, uint64_t max_kmer,
+                                   commet_reads *index, int n_sets, commet_reads *const *queries,
+                                   uint32_t *const *d_tags, uint64_t *searched, uint64_t *shared,
+                                   uint64_t *stats);
+
+/* ---- stage 3: filter_reads --------------------------------------------------
+ * The per-read selection of src/filter_reads.cpp:181-205: length < min_len ->
+ * drop; #non-ACGTacgt > max_N -> drop (max_N<0: infinite); shannon_index
+ * (:265-306, float/double mixed precision reproduced exactly) < min_shannon
+ * -> drop; stop after max_reads selected (<0: all) and clear every later bit
+ * (untag_last_reads, include/read_file.h:76-81).  bv: n_reads/8+1 bytes out.
+ * counters[4] = removed by length, by N, by shannon, selected.
+ * Reads must be non-empty: the reference loop stops at the first empty read
+ * (:188); callers truncate the stream there. */
+int commet_filter_reads(commet_ctx *ctx, const uint8_t *bases, const uint64_t *offs,
+                        uint64_t n_reads, int64_t min_len, int64_t max_N, float min_shannon,
+                        int64_t max_reads, uint8_t *bv, uint64_t *counters);
+int commet_filter_reads_staged(commet_ctx *ctx, commet_reads *r, int64_t min_len, int64_t max_N,
+                               float min_shannon, int64_t max_reads, uint32_t *d_bv,
+                               uint64_t *counters);
+
+/* ---- stage 4: bvop ------------------------------------------------------------
+ * BooleanVector::full_and/or/and_not/not (include/boolean_vector.h:418-462)
+ * over ALL n_bytes = n/8+1 payload bytes (padding bits included), and nb_one
+ * (:244-270): popcount of all bytes clamped to n_bits. */
+enum { COMMET_BV_AND = 0, COMMET_BV_OR = 1, COMMET_BV_ANDNOT = 2, COMMET_BV_NOT = 3 };
+int commet_bvop(commet_ctx *ctx, int op, const uint8_t *a, const uint8_t *b, uint8_t *out,
+                uint64_t n_bytes);
+int commet_bv_popcount(commet_ctx *ctx, const uint8_t *bv, uint64_t n_bits, uint64_t *ones);
+int commet_bvop_dev(commet_ctx *ctx, int op, const void *d_a, const void *d_b, void *d_out,
+                    uint64_t n_bytes);
+int commet_bv_popcount_dev(commet_ctx *ctx, const void *d_bv, uint64_t n_bits, uint64_t *ones);
+
+/* ---- measurement helpers (bench.py / profiles) ---------------------------------
+ * random 32-byte-sector gather / atomic-OR ceilings over a `bytes`-sized
+ * buffer: n_ops random accesses, returns elapsed ns of the kernel. */
+int commet_bench_random_sectors(commet_ctx *ctx, uint64_t bytes, uint64_t n_ops, int atomic_or,
+                                double *ns);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMMET_B200_H_ */

@@ -1,0 +1,202 @@
+"""GPU parity: every kernel stage through the C-ABI against the CPU oracle, bit for bit."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import commet_b200
+    from commet_b200 import build
+    build.build_lib()
+    c = commet_b200.Context(0)
+    yield c
+    c.close()
+
+
+DIRT = [dict(), dict(p_N=0.02), dict(p_N=0.01, p_lower=0.3, p_other=0.01)]
+
+
+def oracle_filter(k, stream, first=0, count=None):
+    bases, offs = stream
+    n = len(offs) - 1
+    count = n - first if count is None else count
+    f = np.zeros(oracle.filter_bytes(k), dtype=np.uint8)
+    sub_offs = offs[first:first + count + 1]
+    # index exactly reads [first, first+count): no stop rule (max_kmer huge)
+    o2 = (sub_offs - sub_offs[0]).astype(np.uint64)
+    b2 = bases[int(sub_offs[0]):int(sub_offs[-1])]
+    oracle.index_chunk(f, k, b2, o2, 0, 1 << 62)
+    return f
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 8, 13, 16, 20, 24])
+@pytest.mark.parametrize("dirt", range(3))
+def test_index_filter_bit_exact(ctx, k, dirt):
+    rng = np.random.default_rng(100 * k + dirt)
+    reads = H.make_ref_set(rng, 300, max(1, k - 3), 3 * k + 40, **DIRT[dirt])
+    stream = H.to_stream(reads)
+    rs = ctx.stage(*stream)
+    ctx.index_reads(rs, k)
+    got = ctx.filter_download(k)
+    assert np.array_equal(got, oracle_filter(k, stream))
+    # a sub-range of reads
+    ctx.index_reads(rs, k, 17, 101)
+    assert np.array_equal(ctx.filter_download(k), oracle_filter(k, stream, 17, 101))
+
+
+@pytest.mark.parametrize("k", [3, 9, 12, 17, 21])
+def test_kmer_counts(ctx, k):
+    rng = np.random.default_rng(k)
+    reads = H.make_ref_set(rng, 500, 1, 4 * k, p_N=0.03, p_lower=0.2)
+    stream = H.to_stream(reads)
+    rs = ctx.stage(*stream)
+    got = ctx.kmer_counts(rs, k)
+    exp = []
+    for r in reads:
+        _, size = oracle.keys(r, k)
+        exp.append(int((size >= k).sum()))
+    assert got.tolist() == exp
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_search_against_reference_built_filter(ctx, seed):
+    """The filter is built by the ORACLE and uploaded: isolates search_reads."""
+    rng = np.random.default_rng(7000 + seed)
+    k = int(rng.integers(6, 25))
+    t = int(rng.integers(0, 5))
+    L = int(rng.integers(k, 5 * k))
+    dirt = DIRT[seed % 3]
+    ref = H.make_ref_set(rng, 200, max(1, L - 20), L + 20, **dirt)
+    qry = H.make_query_set(rng, ref, 400, max(1, L - 20), L + 20, frac_shared=0.6, sub_rate=0.03, **dirt)
+    f = oracle_filter(k, H.to_stream(ref))
+    qs = H.to_stream(qry)
+    exp = np.zeros(len(qry), dtype=np.uint8)
+    exp[::7] = 1                                   # pre-tagged reads must be skipped
+    st = oracle.search(f, k, t, *qs, exp)
+    ctx.filter_upload(k, f)
+    rs = ctx.stage(*qs)
+    tags = np.zeros(len(qry) // 8 + 1, dtype=np.uint8)
+    pre = np.zeros(len(qry), dtype=np.uint8); pre[::7] = 1
+    tags[:] = oracle.tags_to_bv(pre)
+    found, searched = ctx.search_reads(rs, k, t, tags)
+    assert np.array_equal(tags, oracle.tags_to_bv(exp)), (k, t)
+    assert (found, searched) == (st["found"], st["searched"])
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_index_and_search_chunk_loop(ctx, seed):
+    """Full chunk loop incl. the dropped read at every chunk boundary and the log counters."""
+    rng = np.random.default_rng(8000 + seed)
+    k = int(rng.integers(8, 19))
+    t = int(rng.integers(0, 4))
+    L = int(rng.integers(k, 4 * k))
+    dirt = DIRT[seed % 3]
+    maxk = oracle.max_kmer(k)
+    n_ref = int(min(3000, max(20, 4 * maxk // max(1, (L - k + 1)) + 5)))
+    ref = H.make_ref_set(rng, n_ref, max(1, L - 10), L + 10, **dirt)
+    queries = [H.make_query_set(rng, ref, int(rng.integers(1, 400)), max(1, L - 10), L + 10, **dirt)
+               for _ in range(int(rng.integers(1, 4)))]
+    exp_tags, exp = oracle.index_and_search(k, t, H.to_stream(ref), [H.to_stream(q) for q in queries])
+    tags, info = ctx.index_and_search(k, t, H.to_stream(ref), [H.to_stream(q) for q in queries])
+    assert info["chunks"] == exp["chunks"] and info["indexed"] == exp["indexed"] and info["kmers"] == exp["kmers"]
+    for s in range(len(queries)):
+        assert np.array_equal(tags[s], oracle.tags_to_bv(exp_tags[s])), (seed, k, t, s)
+    assert info["searched"] == exp["searched"] and info["shared"] == exp["shared"]
+
+
+def test_chunk_plan_matches_oracle_walk(ctx):
+    rng = np.random.default_rng(5)
+    k = 14
+    reads = H.make_ref_set(rng, 2000, 10, 80, p_N=0.02)
+    stream = H.to_stream(reads)
+    rs = ctx.stage(*stream)
+    chunks, indexed = ctx.chunk_plan(rs, k)
+    f = np.zeros(oracle.filter_bytes(k), dtype=np.uint8)
+    pos, exp, tot = 0, [], 0
+    while pos < len(reads):
+        nxt, ni, _ = oracle.index_chunk(f, k, *stream, pos, oracle.max_kmer(k))
+        exp.append((pos, pos + ni)); tot += ni; pos = nxt
+    assert chunks == exp and indexed == tot and len(chunks) > 3
+
+
+def test_empty_and_degenerate_inputs(ctx):
+    k, t = 11, 2
+    empty = (np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    one = H.to_stream([b"ACGTACGTACGTACGTACGT"])
+    short = H.to_stream([b"ACG", b"A", b"ACGTACGTAC"])      # all shorter than k
+    tags, info = ctx.index_and_search(k, t, empty, [one])
+    assert info["chunks"] == 0 and tags[0].tolist() == [0]
+    tags, info = ctx.index_and_search(k, t, one, [empty, short, one])
+    e_tags, e = oracle.index_and_search(k, t, one, [empty, short, one])
+    assert [x.tolist() for x in tags] == [oracle.tags_to_bv(x).tolist() for x in e_tags]
+    assert info["searched"] == e["searched"] and info["shared"] == e["shared"]
+
+
+def test_k33_dram_resident_filter(ctx):
+    """k=33 (4 GiB filter, 33-bit keys): bit-exact against the oracle on 60k reads."""
+    rng = np.random.default_rng(33)
+    ref = H.make_ref_set(rng, 30000, 100)
+    qry = H.make_query_set(rng, ref, 30000, 100)
+    e_tags, e = oracle.index_and_search(33, 2, H.to_stream(ref), [H.to_stream(qry)])
+    tags, info = ctx.index_and_search(33, 2, H.to_stream(ref), [H.to_stream(qry)])
+    assert np.array_equal(tags[0], oracle.tags_to_bv(e_tags[0]))
+    assert info["shared"] == e["shared"] and 0.4 < info["shared"][0] / len(qry) < 0.6
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_filter_reads(ctx, seed):
+    rng = np.random.default_rng(6000 + seed)
+    n = int(rng.integers(1, 5000))
+    reads = []
+    for _ in range(n):
+        L = int(rng.integers(1, 200))
+        kind = rng.random()
+        if kind < 0.15:
+            r = np.full(L, ord(rng.choice(list("ACGTacgtN"))), dtype=np.uint8)
+        elif kind < 0.3:
+            r = np.tile(np.frombuffer(bytes(rng.choice([b"AC", b"AT", b"ACGT", b"AAC", b"AACG"])), dtype=np.uint8), L)[:L]
+        else:
+            r = H.dirty(rng, H.random_read(rng, L), p_N=float(rng.choice([0, 0.05])),
+                        p_lower=float(rng.choice([0, 0.4])), p_other=float(rng.choice([0, 0.02])))
+        reads.append(r.tobytes())
+    kw = {}
+    if rng.random() < 0.8: kw["min_len"] = int(rng.integers(0, 120))
+    if rng.random() < 0.6: kw["max_N"] = int(rng.integers(0, 6))
+    if rng.random() < 0.85: kw["min_shannon"] = float(np.float32(rng.choice([1.0, 1.5, 2.0, 0.5, float(rng.uniform(0, 2.1))])))
+    if rng.random() < 0.5: kw["max_reads"] = int(rng.choice([0, 1, n // 3, n, n + 5, 1024, 1023, 1025]))
+    stream = H.to_stream(reads)
+    exp_bv, exp_cnt = oracle.filter_reads(*stream, **kw)
+    bv, cnt = ctx.filter_reads(*stream, **kw)
+    assert cnt == exp_cnt, (seed, kw)
+    assert np.array_equal(bv, exp_bv), (seed, kw)
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 127, 128, 129, 4099, 1_000_003])
+def test_bvop_and_popcount(ctx, n):
+    import commet_b200 as cb
+    rng = np.random.default_rng(n)
+    a = rng.integers(0, 256, size=n // 8 + 1).astype(np.uint8)
+    b = rng.integers(0, 256, size=n // 8 + 1).astype(np.uint8)
+    for op, oop in ((cb.BV_AND, oracle.BV_AND), (cb.BV_OR, oracle.BV_OR), (cb.BV_ANDNOT, oracle.BV_ANDNOT),
+                    (cb.BV_NOT, oracle.BV_NOT)):
+        exp = oracle.bvop(oop, a, b)
+        got = ctx.bvop(op, a, b)
+        assert np.array_equal(got, exp)
+        assert ctx.nb_one(got, n) == oracle.nb_one(exp, n)
+    with pytest.raises(cb.CommetError):
+        ctx.bvop(cb.BV_AND, a, np.zeros(a.size + 1, np.uint8))
+
+
+def test_bvop_known_answer_not_counts_padding(ctx):
+    """NOT of a 2000/10000 vector reports 8008 (padding bits flipped, clamped popcount)."""
+    import commet_b200 as cb
+    n = 10000
+    tags = np.zeros(n, np.uint8); tags[:2000] = 1
+    bv = oracle.tags_to_bv(tags)
+    out = ctx.bvop(cb.BV_NOT, bv)
+    assert ctx.nb_one(out, n) == 8008 and out[-1] == 0xFF
