@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py -- Commet index_and_search hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--len L] [-k 33] [-t 2]
+    python bench.py --impl reference ...       # the reference's own CPU tool on this box's cores
+
+One "step" = one index_and_search pass: stage (2-bit encode) the reference set
+and the query set, index every k-mer of the reference set into the
+bloom_filter.h-layout bit array, then search every query read (forward +
+reverse-complement greedy scan).  Workload at N=1 = BASELINE.json configs[1]:
+2 synthetic sets x 10M reads x 100 bp, k=33, t=2.
+
+At N>1 (weak scaling): every rank owns its own 10M-read query set; the
+reference set is sharded N ways, each rank builds a partial filter from its
+shard, partials are merged (all_gather over NCCL + word-wise OR kernel), then
+each rank probes locally.  value = total query reads / max-over-ranks time.
+
+`value`   : inputs (ASCII bases + offsets) already resident in HBM.
+`e2e`     : same pass through Context.index_and_search with HOST buffers
+            (H2D of both sets and D2H of the tag vector inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "query_reads_per_s"
+UNIT = "reads/s"
+
+
+# ----------------------------------------------------------------------------
+# synthetic sets: i.i.d. ACGT reference; queries = 50 % copies of
+# reference reads (half reverse-complemented, 1 % substitutions) + 50 % random
+# ----------------------------------------------------------------------------
+def make_sets_torch(n_reads: int, length: int, seed: int, device, qseed: int | None = None):
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(1000 + seed)
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    comp = torch.zeros(256, dtype=torch.uint8, device=device)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    ref = torch.empty((n_reads, length), dtype=torch.uint8, device=device)
+    qry = torch.empty((n_reads, length), dtype=torch.uint8, device=device)
+    step = 1 << 20
+    for s in range(0, n_reads, step):
+        e = min(n_reads, s + step)
+        ref[s:e] = acgt[torch.randint(0, 4, (e - s, length), generator=g, device=device)]
+    g.manual_seed(2000 + (seed if qseed is None else qseed))
+    for s in range(0, n_reads, step):
+        e = min(n_reads, s + step)
+        m = e - s
+        src = torch.randint(0, n_reads, (m,), generator=g, device=device)
+        cp = ref[src]
+        rc = torch.rand(m, generator=g, device=device) < 0.5
+        cp = torch.where(rc[:, None], comp[cp.flip(1).long()], cp)
+        mut = torch.rand((m, length), generator=g, device=device) < 0.01
+        rnd = acgt[torch.randint(0, 4, (m, length), generator=g, device=device)]
+        cp = torch.where(mut, rnd, cp)
+        shared = torch.rand(m, generator=g, device=device) < 0.5
+        fresh = acgt[torch.randint(0, 4, (m, length), generator=g, device=device)]
+        qry[s:e] = torch.where(shared[:, None], cp, fresh)
+    offs = torch.arange(0, n_reads + 1, dtype=torch.int64, device=device) * length
+    return ref.reshape(-1), qry.reshape(-1), offs
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------
+# CPU arms
+# ----------------------------------------------------------------------------
+def write_fasta(path, bases: np.ndarray, n: int, length: int):
+    arr = bases[:n * length].reshape(n, length)
+    hdr = np.char.add(np.char.add(">", np.arange(n).astype(str)), "\n").astype("S")
+    with open(path, "wb") as f:
+        step = 100000
+        for s in range(0, n, step):
+            e = min(n, s + step)
+            rows = [hdr[i] + arr[i].tobytes() + b"\n" for i in range(s, e)]
+            f.write(b"".join(rows))
+
+
+def cpu_reference_run(ref_b, qry_b, length, n_ref, n_qry, k, t, procs: int):
+    """The reference's own index_and_search (oracle/_ref, compiled from /root/reference) as `procs`
+    independent processes -- the only parallelism it supports: each indexes the reference sample and
+    searches its share of the queries.  Returns (wall seconds, kind, cores)."""
+    from oracle import oracle
+    tool = oracle.REF_DIR / "index_and_search"
+    if not tool.exists():
+        return None
+    with tempfile.TemporaryDirectory(prefix="commet_cpu_") as td:
+        td = Path(td)
+        write_fasta(td / "ref.fa", ref_b, n_ref, length)
+        (td / "ref.txt").write_text(f"ref:{td}/ref.fa\n")
+        per = (n_qry + procs - 1) // procs
+        cmds = []
+        for p in range(procs):
+            s, e = p * per, min(n_qry, (p + 1) * per)
+            if s >= e:
+                break
+            write_fasta(td / f"q{p}.fa", qry_b[s * length:e * length], e - s, length)
+            (td / f"q{p}.txt").write_text(f"q{p}:{td}/q{p}.fa\n")
+            cmds.append([str(tool), "-i", str(td / "ref.txt"), "-s", str(td / f"q{p}.txt"), "-o", str(td / f"o{p}"),
+                         "-l", str(td / f"o{p}"), "-k", str(k), "-t", str(t)])
+        t0 = time.perf_counter()
+        ps = [subprocess.Popen(c, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for c in cmds]
+        rcs = [p.wait() for p in ps]
+        wall = time.perf_counter() - t0
+        if any(rcs):
+            return None
+        return wall, "reference", len(cmds)
+
+
+def cpu_port_run(ref_b, qry_b, length, n_ref, n_qry, k, t):
+    from oracle import oracle
+    io = np.arange(n_ref + 1, dtype=np.uint64) * length
+    qo = np.arange(n_qry + 1, dtype=np.uint64) * length
+    t0 = time.perf_counter()
+    oracle.index_and_search(k, t, (ref_b[:n_ref * length], io), [(qry_b[:n_qry * length], qo)])
+    return time.perf_counter() - t0, "port", 1
+
+
+def cpu_baseline(ref_b, qry_b, length, k, t, sample: int, procs: int = 1):
+    r = cpu_reference_run(ref_b, qry_b, length, sample, sample, k, t, procs)
+    if r is None:
+        r = cpu_port_run(ref_b, qry_b, length, sample, sample, k, t)
+    wall, kind, cores = r
+    return {"value": sample / wall, "unit": UNIT, "cores": cores, "kind": kind, "seconds": round(wall, 3),
+            "sample": f"first {sample} reference reads indexed + first {sample} query reads searched "
+                      f"(same generator, {length} bp, k={k}, t={t}); value = query reads / wall"}
+
+
+# ----------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000)
+    ap.add_argument("--len", type=int, default=100, dest="length")
+    ap.add_argument("-k", type=int, default=33)
+    ap.add_argument("-t", type=int, default=2)
+    ap.add_argument("--cpu-sample", type=int, default=200_000)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"C2: 2 synthetic sets x {args.reads} reads x {args.length} bp, k={args.k} t={args.t}, "
+                "single index_and_search" + (f", reference set sharded over {world} GPUs, one query set per GPU" if world > 1 else ""))
+    config = {"workload": workload, "reads_per_set": args.reads, "read_len": args.length, "k": args.k, "t": args.t,
+              "filter_bytes": 1 << (args.k - 1), "l2_policy": "inputs larger than L2 (2 GB of bases + 4 GiB filter per step)"}
+
+    if args.impl == "reference":
+        return reference_arm(args, rank, world, config)
+
+    import torch
+    import torch.distributed as dist
+    import commet_b200
+    from commet_b200 import build
+    build.build_lib()
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = commet_b200.Context(local_rank)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    n, L, k, t = args.reads, args.length, args.k, args.t
+    ref_d, qry_d, offs_d = make_sets_torch(n, L, seed=0, device=dev, qseed=rank)
+    torch.cuda.synchronize()
+    n_tag_words = (n // 8 + 1 + 3) // 4
+    tags_d = torch.zeros(n_tag_words, dtype=torch.int32, device=dev)
+
+    # reference-set shard of this rank (contiguous reads)
+    r0, r1 = rank * n // world, (rank + 1) * n // world
+    fbytes = 1 << (k - 1)
+    gather_buf = None
+    if world > 1:
+        gather_buf = torch.empty((world, fbytes), dtype=torch.uint8, device=dev)
+
+    def step_device():
+        """one pass with inputs resident in HBM; returns info dict"""
+        tags_d.zero_()
+        ext.wait_stream(torch.cuda.current_stream())
+        q = ctx.stage_device(qry_d.data_ptr(), offs_d.data_ptr(), n, n * L)
+        if world == 1:
+            idx = ctx.stage_device(ref_d.data_ptr(), offs_d.data_ptr(), n, n * L)
+            info = ctx.index_and_search_staged(k, t, idx, [q], [tags_d.data_ptr()])
+            idx.free()
+        else:
+            sub = ref_d[r0 * L:r1 * L]
+            idx = ctx.stage_device(sub.data_ptr(), offs_d.data_ptr(), r1 - r0, (r1 - r0) * L)
+            ctx.index_reads(idx, k)
+            ctx.sync()
+            mine = torch.as_tensor(_FilterView(ctx.filter_ptr, fbytes, local_rank), device=dev)
+            dist.all_gather_into_tensor(gather_buf.view(-1), mine)
+            torch.cuda.current_stream().synchronize()
+            for p in range(world):
+                if p != rank:
+                    ctx.index_or(gather_buf[p].data_ptr(), 0, fbytes)
+            counters = torch.zeros(2, dtype=torch.int64, device=dev)
+            ext.wait_stream(torch.cuda.current_stream())
+            ctx.search_reads_device(q, k, t, tags_d.data_ptr(), counters.data_ptr())
+            ctx.sync()
+            info = {"shared": [int(counters[0])], "searched": [int(counters[1])], "chunks": 1, "index_ns": 0, "search_ns": 0,
+                    "kmers": 0}
+            idx.free()
+        q.free()
+        return info
+
+    # pinned host copies for the end-to-end leg
+    ref_h = torch.empty(n * L, dtype=torch.uint8).pin_memory()
+    qry_h = torch.empty(n * L, dtype=torch.uint8).pin_memory()
+    ref_h.copy_(ref_d); qry_h.copy_(qry_d)
+    offs_h = np.arange(n + 1, dtype=np.uint64) * L
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            e0.record()
+        infos = [fn() for _ in range(steps)]
+        with torch.cuda.stream(ext):
+            e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt)
+        return ms / steps, infos
+
+    for _ in range(args.warmup):
+        info = step_device()
+    launches0 = ctx.launches
+    with ClockSampler(local_rank) as cs:
+        ms_dev, infos = timed(step_device, args.steps)
+    launches = (ctx.launches - launches0) // args.steps
+    info = infos[-1]
+    shared = info["shared"][0]
+
+    # end-to-end leg (single GPU path of the public API; at N>1 every rank runs it on its own query set
+    # against the full reference set -- no sharding of the host->device copies)
+    def step_e2e():
+        tags, inf = ctx.index_and_search(k, t, (ref_h.numpy(), offs_h), [(qry_h.numpy(), offs_h)])
+        return int(np.unpackbits(tags[0]).sum())
+
+    e2e = None
+    if world == 1:
+        step_e2e()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            ones = step_e2e()
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        assert ones == shared, (ones, shared)
+        e2e = {"value": n / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": int(2 * n * L + 2 * 8 * (n + 1)),
+               "d2h_bytes_per_step": int(n // 8 + 1)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peaks()
+    kmers = info["kmers"] or n * max(0, L - k + 1)
+    idx_ms, srch_ms = info["index_ns"] / 1e6, info["search_ns"] / 1e6
+    line = {
+        "metric": METRIC, "value": n * world / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic", "config": config, "gpu_launches": int(launches),
+        "clocks": cs.summary(), "shared_reads": int(shared), "chunks": info["chunks"],
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if world == 1 and idx_ms > 0:
+        ins_bytes = kmers * 4 * 64            # 64 B per key insert, 4 keys per k-mer
+        ach = ins_bytes / (idx_ms / 1e3) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": "k_index", "achieved": ach, "peak": peak, "unit": "GB/s",
+                            "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                            "algorithmic": f"{kmers} k-mers x 4 keys x 64 B (32 B sector read + 32 B write-back)",
+                            "ms_per_launch": idx_ms}
+        line["kernels"] = {"index_ms": idx_ms, "search_ms": srch_ms, "kmers_per_s": kmers / (idx_ms / 1e3),
+                           "key_inserts_per_s": 4 * kmers / (idx_ms / 1e3)}
+    if not args.no_cpu and world == 1:
+        line["cpu_baseline"] = cpu_baseline(ref_h.numpy(), qry_h.numpy(), L, k, t, min(args.cpu_sample, n))
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+class _FilterView:
+    """the context's filter exposed to torch (zero-copy) through __cuda_array_interface__"""
+
+    def __init__(self, ptr, nbytes, device):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _mem_procs(filter_bytes: int) -> int:
+    """how many reference processes fit in RAM: each callocs (and touches) the whole filter"""
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable"):
+                avail = int(ln.split()[1]) * 1024
+                return max(1, int(avail * 0.5 // (filter_bytes + (1 << 30))))
+    except Exception:
+        pass
+    return 1
+
+
+def reference_arm(args, rank, world, config):
+    """bench.py --impl reference: the reference's CPU index_and_search on the host cores."""
+    if rank != 0:
+        return 0
+    n, L, k, t = args.reads, args.length, args.k, args.t
+    sample = min(args.cpu_sample, n)
+    rng = np.random.default_rng(1000)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    ref = acgt[rng.integers(0, 4, size=sample * L)]
+    # same query recipe as make_sets_torch, on the sample
+    comp = np.zeros(256, dtype=np.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    r2 = ref.reshape(sample, L)
+    src = rng.integers(0, sample, size=sample)
+    cp = r2[src]
+    rc = rng.random(sample) < 0.5
+    cp = np.where(rc[:, None], comp[cp[:, ::-1]], cp)
+    mut = rng.random((sample, L)) < 0.01
+    cp = np.where(mut, acgt[rng.integers(0, 4, size=(sample, L))], cp)
+    shared = rng.random(sample) < 0.5
+    qry = np.where(shared[:, None], cp, acgt[rng.integers(0, 4, size=(sample, L))]).astype(np.uint8).reshape(-1)
+    procs = max(1, min(os.cpu_count() or 1, 16, _mem_procs(1 << (k - 1))))
+    vals = []
+    for _ in range(max(1, min(args.steps, 2))):
+        r = cpu_reference_run(ref, qry, L, sample, sample, k, t, procs)
+        if r is None:
+            r = cpu_port_run(ref, qry, L, sample, sample, k, t)
+        vals.append(r)
+    wall, kind, cores = min(vals)
+    v = sample / wall
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{sample} reference reads indexed by each of {cores} processes, {sample} query "
+                                       f"reads split across them ({L} bp, k={k}, t={t}); value = query reads / wall"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

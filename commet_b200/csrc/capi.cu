@@ -322,16 +322,18 @@ static int chunk_plan(commet_ctx *c, commet_reads *r, int k, uint64_t max_kmer,
     // index_reads.h:48-49,60 + index_and_search.cpp:255: walk the per-read counts
     std::vector<uint32_t> cnt(n);
     CK(cudaMemcpy(cnt.data(), d.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    uint64_t i = 0, indexed = 0;
+    uint64_t i = 0, indexed = 0, kmers = 0;
     while (i < n) {
         uint64_t start = i, cum = 0;
         while (i < n && cum < max_kmer) cum += cnt[i++];
         bounds.push_back(start);
         bounds.push_back(i);
         indexed += i - start;
+        kmers += cum;
         if (i < n && cum >= max_kmer) i++;     // fetched, then lost
     }
     if (n_indexed) *n_indexed = indexed;
+    if (n_kmers) *n_kmers = kmers;             // k-mers actually fed (lost reads excluded)
     return 0;
 }
 
