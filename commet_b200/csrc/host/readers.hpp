@@ -1,0 +1,158 @@
+// FASTA / FASTQ (plain or gzip) readers producing, in ONE pass, what the
+// reference obtains with a counting pass plus a reading pass:
+//   - the record count            (fasta_file.h:61-68: lines starting with '>';
+//                                  fastq_file.h:60-67: non-empty lines / 4)
+//   - every record's sequence     (fasta_file.h:166-175: non-empty lines up to the next '>' line, concatenated;
+//                                  fastq_file.h:132-180: the line after the '@' line)
+// Sequences are appended to one contiguous byte buffer (`seq`) with `off`
+// giving record boundaries, ready to be handed to commet_reads_upload.
+#pragma once
+#include <stdint.h>
+#include <zlib.h>
+
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+namespace commet_host {
+
+enum class Format { Fasta, Fastq, Unknown };
+
+struct ParsedFile {
+    std::string fname;
+    Format format = Format::Unknown;
+    bool gz = false;
+    uint64_t nb_reads = 0;            // the reference's count (bit-vector size)
+    std::vector<uint64_t> off;        // nb_reads+1 offsets into seq
+    std::vector<uint8_t> seq;
+};
+
+inline bool slurp_plain(const std::string &fname, std::string &out)
+{
+    std::ifstream f(fname.c_str(), std::ios::binary);
+    if (!f.good()) return false;
+    f.seekg(0, std::ios::end);
+    std::streamoff sz = f.tellg();
+    f.seekg(0);
+    out.resize((size_t)sz);
+    if (sz) f.read(&out[0], sz);
+    return true;
+}
+
+inline bool slurp_gz(const std::string &fname, std::string &out)
+{
+    gzFile g = gzopen(fname.c_str(), "r");
+    if (!g) return false;
+    gzbuffer(g, 1 << 20);
+    out.clear();
+    std::vector<char> buf(1 << 22);
+    int n;
+    while ((n = gzread(g, buf.data(), (unsigned)buf.size())) > 0) out.append(buf.data(), (size_t)n);
+    gzclose(g);
+    return true;
+}
+
+// Sniffing of file_manager.h:117-156 / filter_reads.cpp:121-154: first byte '>' or '@', else gzip.
+// Returns false (with the reference's message on stderr) when the file cannot be used.
+inline bool load_text(const std::string &fname, std::string &text, Format &fmt, bool &gz, const char *who)
+{
+    std::ifstream probe(fname.c_str());
+    if (!probe.good()) {
+        std::cerr << "Cannot open file " << fname << who;
+        return false;
+    }
+    int c = probe.get();
+    probe.close();
+    gz = false;
+    if (c == '>' || c == '@') {
+        if (!slurp_plain(fname, text)) return false;
+    } else {
+        if (!slurp_gz(fname, text)) {
+            std::cerr << "Cannot open file " << fname << who;
+            return false;
+        }
+        gz = true;
+        c = text.empty() ? -1 : (unsigned char)text[0];
+    }
+    fmt = c == '>' ? Format::Fasta : c == '@' ? Format::Fastq : Format::Unknown;
+    if (fmt == Format::Unknown) {
+        std::cerr << "Unknown format: " << fname << who;
+        return false;
+    }
+    return true;
+}
+
+inline void parse_fasta(const std::string &t, ParsedFile &pf)
+{
+    const char *p = t.data(), *end = p + t.size();
+    pf.seq.reserve(t.size());
+    bool in_record = false;
+    while (p < end) {
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+        const char *le = nl ? nl : end;
+        if (le > p) {
+            if (*p == '>') {
+                pf.off.push_back(pf.seq.size());
+                in_record = true;
+            } else if (in_record) {
+                pf.seq.insert(pf.seq.end(), (const uint8_t *)p, (const uint8_t *)le);
+            }
+        }
+        p = nl ? nl + 1 : end;
+    }
+    pf.nb_reads = pf.off.size();
+    pf.off.push_back(pf.seq.size());
+}
+
+inline void parse_fastq(const std::string &t, ParsedFile &pf)
+{
+    const char *p = t.data(), *end = p + t.size();
+    pf.seq.reserve(t.size() / 2);
+    // counting rule first: non-empty lines / 4
+    uint64_t non_empty = 0;
+    for (const char *q = p; q < end;) {
+        const char *nl = (const char *)memchr(q, '\n', (size_t)(end - q));
+        const char *le = nl ? nl : end;
+        if (le > q) non_empty++;
+        q = nl ? nl + 1 : end;
+    }
+    pf.nb_reads = non_empty / 4;
+    auto next_line = [&](const char *&b, const char *&e) -> bool {
+        if (p >= end) return false;
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+        b = p;
+        e = nl ? nl : end;
+        p = nl ? nl + 1 : end;
+        return true;
+    };
+    auto next_non_empty = [&](const char *&b, const char *&e) -> bool {
+        while (next_line(b, e))
+            if (e > b) return true;
+        return false;
+    };
+    for (uint64_t r = 0; r < pf.nb_reads; r++) {
+        const char *b, *e;
+        pf.off.push_back(pf.seq.size());
+        if (!next_non_empty(b, e)) continue;            // '@' line
+        if (!next_line(b, e)) continue;                 // sequence line, taken as is (may be empty)
+        pf.seq.insert(pf.seq.end(), (const uint8_t *)b, (const uint8_t *)e);
+        if (!next_non_empty(b, e)) continue;            // '+' line
+        if (b[0] != '+') std::cerr << "Error\n";        // fastq_file.h:158-160
+        next_non_empty(b, e);                           // quality line
+    }
+    pf.off.push_back(pf.seq.size());
+}
+
+inline bool parse_reads_file(const std::string &fname, ParsedFile &pf, const char *who)
+{
+    std::string text;
+    pf.fname = fname;
+    if (!load_text(fname, text, pf.format, pf.gz, who)) return false;
+    if (pf.format == Format::Fasta) parse_fasta(text, pf);
+    else parse_fastq(text, pf);
+    return true;
+}
+
+}  // namespace commet_host

@@ -1,0 +1,209 @@
+"""GPU: the drop-in executables (commet_b200/bin) against the golden outputs of the unmodified reference
+and, when oracle/_ref travelled with the snapshot, live against the reference binaries on fuzzed files."""
+import hashlib
+import json
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import commet_flow
+from tests import helpers as H
+from tests.golden import fixtures
+
+pytestmark = pytest.mark.gpu
+GOLDEN = json.loads((Path(__file__).parent / "golden" / "golden.json").read_text())
+
+
+@pytest.fixture(scope="module")
+def bin_dir():
+    from commet_b200 import build
+    build.build_all()
+    return build.BIN
+
+
+def sha(p):
+    return hashlib.sha256(Path(p).read_bytes()).hexdigest()
+
+
+def check_flow(work, res, g):
+    for n in ("plain", "percentage", "normalized"):
+        assert res[n] == g["csv"][n]
+        assert hashlib.sha256(res[n].encode()).hexdigest() == g["csv_sha256"][n]
+    got = {p.name: sha(p) for p in (work / "output_commet").glob("*.bv")}
+    assert got == g["bv"]
+
+
+@pytest.mark.parametrize("case,config,kw", [
+    ("abcde_3sets_k32", "ABCDE_bench/sets_config.txt", dict(k=32)),
+    ("abcde_5sets_k32", "ABCDE_bench/five_sets.txt", dict(k=32)),
+    ("dissymmetry_k33", "test_dissymmetry/fof.txt", dict(k=33)),
+    ("abcde_3sets_k21_filtered", "ABCDE_bench/sets_config.txt", dict(k=21, t=3, l=100, e=1.9, n=0, m=9000)),
+])
+def test_commet_flow_bit_exact(bin_dir, tmp_path, case, config, kw):
+    """Whole Commet.py flow (filter_reads -> N^2-1 index_and_search -> bvop -i matrices): every .bv file and the
+    three CSV matrices byte-identical to the reference's."""
+    fixtures.materialize(tmp_path)
+    res = commet_flow.run(config, bin_dir, tmp_path, **kw)
+    check_flow(tmp_path, res, GOLDEN[case])
+
+
+@pytest.mark.parametrize("k", [20, 22, 33])
+def test_chunk_boundary_known_answer(bin_dir, tmp_path, k):
+    fixtures.materialize(tmp_path)
+    (tmp_path / "a.txt").write_text("A:ABCDE_bench/A.fa\n")
+    out = tmp_path / "o"
+    r = subprocess.run([str(bin_dir / "index_and_search"), "-i", "a.txt", "-s", "a.txt", "-o", str(out), "-l", str(out),
+                        "-k", str(k), "-t", "2"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    g = GOLDEN["chunk_boundary_A_in_A"][str(k)]
+    assert sha(out / "A.fa_in_A.bv") == g["bv_sha256"]
+    m = re.search(r"indexed (\d+), searched (\d+), shared (\d+)", (out / "A_in_A.log").read_text())
+    assert [int(x) for x in m.groups()] == g["counters"]
+
+
+def test_full_mode(bin_dir, tmp_path):
+    fixtures.materialize(tmp_path)
+    (tmp_path / "fa.txt").write_text("set1:test_dissymmetry/A.fa\n")
+    (tmp_path / "fb.txt").write_text("set2:test_dissymmetry/B.fa\n")
+    out = tmp_path / "full"
+    r = subprocess.run([str(bin_dir / "index_and_search"), "-i", "fa.txt", "-s", "fb.txt", "-o", str(out), "-l", str(out),
+                        "-k", "25", "-f"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert {p.name: sha(p) for p in out.glob("*.bv")} == GOLDEN["full_mode_k25"]
+
+
+def test_bvop_known_answers(bin_dir, tmp_path):
+    fixtures.materialize(tmp_path)
+    commet_flow.run("ABCDE_bench/sets_config.txt", bin_dir, tmp_path, k=32)
+    for name, args in (("not", ["C.fa_in_set1.bv", "-n"]), ("and", ["A.fa_in_set2.bv", "-a", "A.fa_in_set3.bv"]),
+                       ("or", ["A.fa_in_set2.bv", "-o", "A.fa_in_set3.bv"]),
+                       ("andnot", ["A.fa_in_set2.bv", "-d", "A.fa_in_set3.bv"])):
+        a = ["output_commet/" + x if x.endswith(".bv") else x for x in args]
+        r = subprocess.run([str(bin_dir / "bvop"), *a, "-p", f"bvop_{name}.bv", "-i"], cwd=tmp_path, capture_output=True,
+                           text=True)
+        assert r.returncode == 0
+        assert r.stdout == GOLDEN["bvop"][name]["stdout"]
+        assert sha(tmp_path / f"bvop_{name}.bv") == GOLDEN["bvop"][name]["file_sha256"]
+    # size mismatch exits 1 (boolean_vector.h:420-423)
+    r = subprocess.run([str(bin_dir / "bvop"), "output_commet/A.fa_in_set2.bv", "-a", "output_commet/C.fa_in_set1.bv"],
+                       cwd=tmp_path, capture_output=True)
+    assert r.returncode == 1
+    # no -p: header + raw payload on stdout
+    r = subprocess.run([str(bin_dir / "bvop"), "output_commet/C.fa_in_set1.bv", "-n"], cwd=tmp_path, capture_output=True)
+    assert r.stdout.startswith(b"NOT output_commet/C.fa_in_set1.bv\n\n#10000\n") and len(r.stdout.split(b"#10000\n", 1)[1]) == 1251
+
+
+# ---- live against the reference binaries -------------------------------------------------------------
+needs_ref = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref did not travel")
+
+
+def _write_set(rng, tmp, name, reads_per_file, with_bv):
+    items = []
+    for fi, reads in enumerate(reads_per_file):
+        kind = int(rng.integers(0, 5))
+        base = tmp / f"{name}_{fi}"
+        if kind == 0:
+            path = H.write_fasta(base.with_suffix(".fa"), reads)
+        elif kind == 1:
+            path = H.write_fasta(base.with_suffix(".fa"), reads, width=int(rng.integers(7, 40)),
+                                 final_newline=bool(rng.integers(0, 2)), blank_every=int(rng.integers(0, 4)))
+        elif kind == 2:
+            path = H.write_fastq(base.with_suffix(".fq"), reads, final_newline=bool(rng.integers(0, 2)))
+        elif kind == 3:
+            path = H.write_fasta(base.with_suffix(".fa.gz"), reads, gz=True)
+        else:
+            path = H.write_fastq(base.with_suffix(".fq.gz"), reads, gz=True)
+        if with_bv:
+            n = len(reads)
+            valid = (rng.random(n) < 0.7).astype(np.uint8)
+            if valid.sum() == 0:
+                valid[int(rng.integers(0, n))] = 1
+            bvp = tmp / f"{name}_{fi}.in.bv"
+            oracle.write_bv_file(bvp, b"input", n, oracle.tags_to_bv(valid))
+            items.append(f"{path},{bvp}")
+        else:
+            items.append(str(path))
+    return items
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(30))
+def test_index_and_search_vs_reference_binary(bin_dir, tmp_path, seed):
+    rng = np.random.default_rng(3000 + seed)
+    k = int(rng.integers(8, 21))
+    t = int(rng.integers(0, 4))
+    L = int(rng.integers(k, 4 * k))
+    dirt = dict(p_N=float(rng.choice([0, 0.02])), p_lower=float(rng.choice([0, 0.3])), p_other=float(rng.choice([0, 0.01])))
+    maxk = oracle.max_kmer(k)
+    n_ref = int(min(400, max(20, 3 * maxk // max(1, (L - k + 1)) + 5)))
+    ref_files = [H.make_ref_set(rng, n_ref, max(1, L - 10), L + 10, **dirt) for _ in range(int(rng.integers(1, 3)))]
+    all_ref = [r for f in ref_files for r in f]
+    iitems = _write_set(rng, tmp_path, "idx", ref_files, with_bv=bool(rng.integers(0, 2)))
+    (tmp_path / "index.txt").write_text(" refset:" + " ; ".join(iitems) + "\n")      # name keeps its spaces, files do not
+    lines, names = [], []
+    for s in range(int(rng.integers(1, 4))):
+        files = [H.make_query_set(rng, all_ref, int(rng.integers(5, 120)), max(1, L - 10), L + 10, **dirt)
+                 for _ in range(int(rng.integers(1, 3)))]
+        lines.append(f"Q{s}:" + ";".join(_write_set(rng, tmp_path, f"q{s}", files, with_bv=bool(rng.integers(0, 2)))))
+        names.append(f"Q{s}")
+    (tmp_path / "query.txt").write_text("\n".join(lines) + "\n")
+    outs = {}
+    full = ["-f"] if seed % 5 == 4 else []
+    for who, tool in (("ref", oracle.REF_DIR / "index_and_search"), ("gpu", bin_dir / "index_and_search")):
+        out = tmp_path / who
+        r = subprocess.run([str(tool), "-i", str(tmp_path / "index.txt"), "-s", str(tmp_path / "query.txt"), "-o", str(out),
+                            "-l", str(out), "-k", str(k), "-t", str(t), *full], capture_output=True, text=True)
+        assert r.returncode == 0, (who, r.stderr)
+        outs[who] = out
+    ref_bvs = {p.name: p.read_bytes() for p in outs["ref"].glob("*.bv")}
+    gpu_bvs = {p.name: p.read_bytes() for p in outs["gpu"].glob("*.bv")}
+    assert ref_bvs.keys() == gpu_bvs.keys() and len(ref_bvs) > 0
+    for name in ref_bvs:
+        assert ref_bvs[name] == gpu_bvs[name], (seed, k, t, name)
+    pat = re.compile(r"\[indexed \d+, searched \d+, shared \d+\](\n[0-9.eE+-]+%)?")
+    for lg in outs["ref"].glob("*.log"):
+        a = pat.search(lg.read_text()).group(0)
+        b = pat.search((outs["gpu"] / lg.name).read_text()).group(0)
+        assert a == b, (seed, lg.name)
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(20))
+def test_filter_reads_vs_reference_binary(bin_dir, tmp_path, seed):
+    rng = np.random.default_rng(4000 + seed)
+    n = int(rng.integers(1, 3000))
+    reads = []
+    for _ in range(n):
+        L = int(rng.integers(1, 160))
+        kind = rng.random()
+        if kind < 0.15:
+            r = np.full(L, ord(rng.choice(list("ACGTacgtN"))), dtype=np.uint8)
+        elif kind < 0.3:
+            r = np.tile(np.frombuffer(bytes(rng.choice([b"AC", b"AT", b"ACGT", b"AAC"])), dtype=np.uint8), L)[:L]
+        else:
+            r = H.dirty(rng, H.random_read(rng, L), p_N=float(rng.choice([0, 0.05])), p_lower=float(rng.choice([0, 0.4])),
+                        p_other=float(rng.choice([0, 0.02])))
+        reads.append(r.tobytes())
+    kind = seed % 4
+    if kind == 0: path = H.write_fasta(tmp_path / "in.fa", reads)
+    elif kind == 1: path = H.write_fastq(tmp_path / "in.fq", reads)
+    elif kind == 2: path = H.write_fasta(tmp_path / "in.fa.gz", reads, gz=True, width=31)
+    else: path = H.write_fastq(tmp_path / "in.fq.gz", reads, gz=True)
+    args = []
+    if rng.random() < 0.8: args += ["-l", str(int(rng.integers(0, 120)))]
+    if rng.random() < 0.6: args += ["-n", str(int(rng.integers(0, 6)))]
+    if rng.random() < 0.8: args += ["-e", str(rng.choice(["1.0", "1.5", "2", "0.5", str(round(float(rng.uniform(0, 2.1)), 4))]))]
+    if rng.random() < 0.4: args += ["-m", str(float(int(rng.integers(0, n + 3))))]
+    if rng.random() < 0.3: args += ["-c", "my comment"]
+    res = {}
+    for who, tool in (("ref", oracle.REF_DIR / "filter_reads"), ("gpu", bin_dir / "filter_reads")):
+        outp = tmp_path / f"{who}.bv"
+        r = subprocess.run([str(tool), str(path), *args, "-o", str(outp)], capture_output=True, text=True)
+        assert r.returncode == 0, (who, r.stderr)
+        res[who] = (outp.read_bytes(), [ln for ln in r.stdout.split("\n") if not ln.startswith("Total  time")])
+    assert res["ref"][0] == res["gpu"][0], (seed, args)
+    assert res["ref"][1] == res["gpu"][1], (seed, args)
