@@ -267,7 +267,7 @@ def main():
             for p in range(world):
                 if p != rank:
                     ctx.index_or(gather_buf[p].data_ptr(), 0, fbytes)
-            counters = torch.zeros(2, dtype=torch.int64, device=dev)
+            counters = torch.zeros(4, dtype=torch.int64, device=dev)
             ext.wait_stream(torch.cuda.current_stream())
             ctx.search_reads_device(q, k, t, tags_d.data_ptr(), counters.data_ptr())
             ctx.sync()
@@ -312,6 +312,13 @@ def main():
     launches = (ctx.launches - launches0) // args.steps
     info = infos[-1]
     shared = info["shared"][0]
+    probes = None
+    if world == 1:
+        # untimed instrumented pass: the number of filter byte tests the REFERENCE semantics perform (N_probes)
+        ctx.count_probes(True)
+        probes = step_device()
+        ctx.count_probes(False)
+        assert probes["shared"][0] == shared
 
     # end-to-end leg (single GPU path of the public API; at N>1 every rank runs it on its own query set
     # against the full reference set -- no sharding of the host->device copies)
@@ -357,6 +364,10 @@ def main():
                             "ms_per_launch": idx_ms}
         line["kernels"] = {"index_ms": idx_ms, "search_ms": srch_ms, "kmers_per_s": kmers / (idx_ms / 1e3),
                            "key_inserts_per_s": 4 * kmers / (idx_ms / 1e3)}
+        if probes and srch_ms > 0:
+            line["kernels"].update({"n_probes": probes["tests"], "n_lookups": probes["lookups"],
+                                    "probes_per_s": probes["tests"] / (srch_ms / 1e3),
+                                    "probe_GBps_algorithmic": probes["tests"] * 32 / (srch_ms / 1e3) / 1e9})
     if not args.no_cpu and world == 1:
         line["cpu_baseline"] = cpu_baseline(ref_h.numpy(), qry_h.numpy(), L, k, t, min(args.cpu_sample, n))
     print(json.dumps(line))

@@ -37,6 +37,7 @@ _SIGS = {
     "commet_ctx_sync": (C.c_int, [C.c_void_p]),
     "commet_ctx_stream": (C.c_void_p, [C.c_void_p]),
     "commet_ctx_launches": (C.c_uint64, [C.c_void_p]),
+    "commet_ctx_count_probes": (C.c_int, [C.c_void_p, C.c_int]),
     "commet_host_alloc": (C.c_void_p, [C.c_size_t]),
     "commet_host_free": (None, [C.c_void_p]),
     "commet_filter_bytes": (C.c_uint64, [C.c_int]),
@@ -189,6 +190,10 @@ class Context:
     def stream(self) -> int:
         return int(self.lib.commet_ctx_stream(self.handle) or 0)
 
+    def count_probes(self, on: bool = True):
+        """instrumented search: info["tests"], info["lookups"] = the reference's probe counts"""
+        self._ck(self.lib.commet_ctx_count_probes(self.handle, int(on)))
+
     @property
     def launches(self) -> int:
         return int(self.lib.commet_ctx_launches(self.handle))
@@ -288,8 +293,8 @@ class Context:
                                                   C.cast(qb, C.c_void_p), C.cast(qo, C.c_void_p), _ptr(nq),
                                                   C.cast(tg, C.c_void_p), _ptr(searched), _ptr(shared), _ptr(stats)))
         info = dict(chunks=int(stats[0]), indexed=int(stats[1]), kmers=int(stats[2]), index_ns=int(stats[3]),
-                    search_ns=int(stats[4]), searched=[int(x) for x in searched[:ns]],
-                    shared=[int(x) for x in shared[:ns]])
+                    search_ns=int(stats[4]), tests=int(stats[5]), lookups=int(stats[6]),
+                    searched=[int(x) for x in searched[:ns]], shared=[int(x) for x in shared[:ns]])
         return tags, info
 
     def index_and_search_staged(self, k: int, t: int, index: ReadStream, queries, d_tags, maxk: int | None = None):
@@ -305,8 +310,8 @@ class Context:
                                                          C.cast(qh, C.c_void_p), C.cast(th, C.c_void_p),
                                                          _ptr(searched), _ptr(shared), _ptr(stats)))
         return dict(chunks=int(stats[0]), indexed=int(stats[1]), kmers=int(stats[2]), index_ns=int(stats[3]),
-                    search_ns=int(stats[4]), searched=[int(x) for x in searched[:ns]],
-                    shared=[int(x) for x in shared[:ns]])
+                    search_ns=int(stats[4]), tests=int(stats[5]), lookups=int(stats[6]),
+                    searched=[int(x) for x in searched[:ns]], shared=[int(x) for x in shared[:ns]])
 
     # -- stage 3 --------------------------------------------------------------
     def filter_reads(self, bases, offs, min_len=0, max_N=-1, min_shannon=0.0, max_reads=-1):

@@ -53,8 +53,9 @@ struct commet_ctx {
     uint64_t filter_cap = 0;          // allocated bytes
     uint64_t filter_bytes = 0;        // 2^(k-1)
     int k = 0;
-    unsigned long long *scratch = nullptr;   // 64 u64 of device counters
+    unsigned long long *scratch = nullptr;   // kScratch u64 of device counters
     uint64_t launches = 0;
+    bool count_probes = false;        // instrumented search kernel (reference-semantics probe counts)
 };
 
 struct commet_reads {
@@ -66,6 +67,9 @@ struct commet_reads {
 };
 
 namespace {
+
+constexpr int kScratch = 256;         // [0,128): 4 counters per query set; [128,256): misc
+constexpr int kMaxSets = 30;
 
 struct DevBuf {                       // scoped device allocation
     void *p = nullptr;
@@ -119,8 +123,8 @@ extern "C" int commet_ctx_create(int device, commet_ctx **out)
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CK(cudaMalloc(&c->scratch, 64 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(c->scratch, 0, 64 * sizeof(unsigned long long), c->stream));
+    CK(cudaMalloc(&c->scratch, kScratch * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(c->scratch, 0, kScratch * sizeof(unsigned long long), c->stream));
     *out = c;
     return 0;
 }
@@ -144,6 +148,7 @@ extern "C" int commet_ctx_sync(commet_ctx *c)
 }
 
 extern "C" void *commet_ctx_stream(commet_ctx *c) { return (void *)c->stream; }
+extern "C" int commet_ctx_count_probes(commet_ctx *c, int on) { c->count_probes = on != 0; return 0; }
 extern "C" uint64_t commet_ctx_launches(commet_ctx *c) { return c->launches; }
 
 extern "C" void *commet_host_alloc(size_t bytes)
@@ -283,9 +288,9 @@ extern "C" int commet_reads_kmer_counts(commet_ctx *c, commet_reads *r, int k, u
     if (r->n_reads == 0) return 0;
     DevBuf d;
     if (d.alloc(r->n_reads * sizeof(uint32_t)) != cudaSuccess) return fail("allocation of k-mer counts failed");
-    CK(cudaMemsetAsync(c->scratch, 0, sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->scratch + 150, 0, sizeof(unsigned long long), c->stream));
     k_kmer_counts<<<grid_for(c, r->n_reads, 256, 8), 256, 0, c->stream>>>(r->planes, r->offs, r->n_reads,
-                                                                         d.as<uint32_t>(), c->scratch);
+                                                                         d.as<uint32_t>(), c->scratch + 150);
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(counts, d.p, r->n_reads * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -305,12 +310,12 @@ static int chunk_plan(commet_ctx *c, commet_reads *r, int k, uint64_t max_kmer,
     CKR(prepare(c, r, k));
     DevBuf d;
     if (d.alloc(n * sizeof(uint32_t)) != cudaSuccess) return fail("allocation of k-mer counts failed");
-    CK(cudaMemsetAsync(c->scratch, 0, sizeof(unsigned long long), c->stream));
-    k_kmer_counts<<<grid_for(c, n, 256, 8), 256, 0, c->stream>>>(r->planes, r->offs, n, d.as<uint32_t>(), c->scratch);
+    CK(cudaMemsetAsync(c->scratch + 150, 0, sizeof(unsigned long long), c->stream));
+    k_kmer_counts<<<grid_for(c, n, 256, 8), 256, 0, c->stream>>>(r->planes, r->offs, n, d.as<uint32_t>(), c->scratch + 150);
     c->launches++;
     CK(cudaGetLastError());
     unsigned long long total = 0;
-    CK(cudaMemcpyAsync(&total, c->scratch, sizeof total, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&total, c->scratch + 150, sizeof total, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (n_kmers) *n_kmers = total;
     if (total < max_kmer) {            // the limit is never reached: one chunk, nothing dropped
@@ -435,8 +440,11 @@ static int search_launch(commet_ctx *c, commet_reads *r, int k, int t, uint32_t 
     if (c->k != k || !c->filter) return fail("commet_search: no filter for k=%d (current k=%d)", k, c->k);
     if (r->n_reads == 0) return 0;
     CKR(prepare(c, r, k));
-    k_search<<<grid_for(c, r->n_reads, 256, 8), 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t,
-                                                                    d_tags, d_counters);
+    unsigned g = grid_for(c, r->n_reads, 256, 8);
+    if (c->count_probes)
+        k_search<true><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters);
+    else
+        k_search<false><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -458,7 +466,7 @@ extern "C" int commet_search(commet_ctx *c, commet_reads *r, int k, int t, uint8
     if (d.alloc(nw * 4) != cudaSuccess) return fail("tag allocation failed");
     CK(cudaMemsetAsync(d.p, 0, nw * 4, c->stream));
     CK(cudaMemcpyAsync(d.p, tags, nb, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync(c->scratch, 0, 2 * sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->scratch, 0, 4 * sizeof(unsigned long long), c->stream));
     CKR(search_launch(c, r, k, t, d.as<uint32_t>(), c->scratch));
     unsigned long long cnt[2] = {0, 0};
     CK(cudaMemcpyAsync(tags, d.p, nb, cudaMemcpyDeviceToHost, c->stream));
@@ -475,14 +483,14 @@ extern "C" int commet_index_and_search_staged(commet_ctx *c, int k, int t, uint6
                                               uint64_t *searched, uint64_t *shared, uint64_t *stats)
 {
     CKR(set_device(c));
-    if (n_sets < 0 || n_sets > 30) return fail("n_sets=%d unsupported (0..30)", n_sets);
+    if (n_sets < 0 || n_sets > kMaxSets) return fail("n_sets=%d unsupported (0..%d)", n_sets, kMaxSets);
     std::vector<uint64_t> bounds;
     uint64_t n_indexed = 0, n_kmers = 0;
     CKR(chunk_plan(c, index, k, max_kmer, bounds, &n_indexed, &n_kmers));
     for (int s = 0; s < n_sets; s++) CKR(prepare(c, queries[s], k));
     uint64_t n_chunks = bounds.size() / 2;
-    // scratch: [2+2s] found total, [3+2s] searched in the last chunk
-    CK(cudaMemsetAsync(c->scratch, 0, 64 * sizeof(unsigned long long), c->stream));
+    // scratch[4s..4s+3]: found total, searched in the last chunk, filter tests, k-mer lookups
+    CK(cudaMemsetAsync(c->scratch, 0, 128 * sizeof(unsigned long long), c->stream));
     const bool timed = stats && n_chunks <= 64;
     std::vector<cudaEvent_t> ev;
     if (n_chunks) CKR(commet_index_begin(c, k));
@@ -497,17 +505,20 @@ extern "C" int commet_index_and_search_staged(commet_ctx *c, int k, int t, uint6
         CKR(index_range(c, index, bounds[2 * ch], bounds[2 * ch + 1] - bounds[2 * ch], nullptr));
         if (timed) CK(cudaEventRecord(e1, c->stream));
         for (int s = 0; s < n_sets; s++) {
-            CK(cudaMemsetAsync(c->scratch + 3 + 2 * s, 0, sizeof(unsigned long long), c->stream));
-            CKR(search_launch(c, queries[s], k, t, d_tags[s], c->scratch + 2 + 2 * s));
+            CK(cudaMemsetAsync(c->scratch + 4 * s + 1, 0, sizeof(unsigned long long), c->stream));
+            CKR(search_launch(c, queries[s], k, t, d_tags[s], c->scratch + 4 * s));
         }
         if (timed) CK(cudaEventRecord(e2, c->stream));
     }
-    unsigned long long h[64];
+    unsigned long long h[128];
     CK(cudaMemcpyAsync(h, c->scratch, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    uint64_t n_tests = 0, n_lookups = 0;
     for (int s = 0; s < n_sets; s++) {
-        if (shared) shared[s] = h[2 + 2 * s];
-        if (searched) searched[s] = h[3 + 2 * s];
+        if (shared) shared[s] = h[4 * s];
+        if (searched) searched[s] = h[4 * s + 1];
+        n_tests += h[4 * s + 2];
+        n_lookups += h[4 * s + 3];
     }
     if (stats) {
         double t_index = 0, t_search = 0;
@@ -518,7 +529,7 @@ extern "C" int commet_index_and_search_staged(commet_ctx *c, int k, int t, uint6
         }
         stats[0] = n_chunks; stats[1] = n_indexed; stats[2] = n_kmers;
         stats[3] = (uint64_t)(t_index * 1e6); stats[4] = (uint64_t)(t_search * 1e6);
-        stats[5] = stats[6] = stats[7] = 0;
+        stats[5] = n_tests; stats[6] = n_lookups; stats[7] = 0;
     }
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
     return 0;
@@ -531,7 +542,7 @@ extern "C" int commet_index_and_search(commet_ctx *c, int k, int t, uint64_t max
                                        uint64_t *shared, uint64_t *stats)
 {
     CKR(set_device(c));
-    if (n_sets < 0 || n_sets > 30) return fail("n_sets=%d unsupported (0..30)", n_sets);
+    if (n_sets < 0 || n_sets > kMaxSets) return fail("n_sets=%d unsupported (0..%d)", n_sets, kMaxSets);
     commet_reads *idx = nullptr;
     std::vector<commet_reads *> q(n_sets, nullptr);
     std::vector<uint32_t *> dt(n_sets, nullptr);
@@ -616,7 +627,7 @@ extern "C" int commet_filter_reads_staged(commet_ctx *c, commet_reads *r, int64_
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(c->stream));
     }
-    unsigned long long *out = c->scratch + 8;
+    unsigned long long *out = c->scratch + 128;
     k_filter_cutoff<<<1, 1024, 0, c->stream>>>(totals.as<unsigned int>(), n_blocks, classes.as<uint8_t>(), n,
                                                cut ? (long long)max_reads : -1LL, out);
     c->launches++;
@@ -677,7 +688,7 @@ extern "C" int commet_bv_popcount_dev(commet_ctx *c, const void *d_bv, uint64_t 
     CKR(set_device(c));
     uint64_t n_bytes = n_bits / 8 + 1;
     if ((uintptr_t)d_bv & 15) return fail("bv buffer must be 16-byte aligned");
-    unsigned long long *tot = c->scratch + 16;
+    unsigned long long *tot = c->scratch + 140;
     CK(cudaMemsetAsync(tot, 0, sizeof *tot, c->stream));
     uint64_t n_vec = n_bytes / 16;
     k_popcount<<<grid_for(c, std::max<uint64_t>(n_vec, 16), 256, 8), 256, 0, c->stream>>>(static_cast<const uint4 *>(d_bv),
@@ -731,8 +742,8 @@ extern "C" int commet_bench_random_sectors(commet_ctx *c, uint64_t bytes, uint64
     unsigned g = grid_for(c, n_ops / 4, 256, 8);
     for (int rep = 0; rep < 2; rep++) {          // first pass warms up, second is timed
         if (rep == 1) CK(cudaEventRecord(e0, c->stream));
-        if (atomic_or) k_random_sectors<true><<<g, 256, 0, c->stream>>>(buf.as<uint32_t>(), mask, n_ops, c->scratch + 20);
-        else k_random_sectors<false><<<g, 256, 0, c->stream>>>(buf.as<uint32_t>(), mask, n_ops, c->scratch + 20);
+        if (atomic_or) k_random_sectors<true><<<g, 256, 0, c->stream>>>(buf.as<uint32_t>(), mask, n_ops, c->scratch + 144);
+        else k_random_sectors<false><<<g, 256, 0, c->stream>>>(buf.as<uint32_t>(), mask, n_ops, c->scratch + 144);
         c->launches++;
     }
     CK(cudaEventRecord(e1, c->stream));

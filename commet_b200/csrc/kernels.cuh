@@ -207,10 +207,13 @@ k_index(uint32_t *__restrict__ filter, const uint4 *__restrict__ planes, uint64_
 // ------------------------------------------------------ stage 2: search ----
 // BloomFilter::is_found (bloom_filter.h:124-131): b, c, d after a passed,
 // short-circuit in the reference's order.
-__device__ __forceinline__ bool probe_bcd(const uint32_t *__restrict__ filter, const Keys &q)
+__device__ __forceinline__ bool probe_bcd(const uint32_t *__restrict__ filter, const Keys &q, unsigned int &tests)
 {
+    tests++;
     if (!(ld_nc_u32(filter + key_word(q.b)) & key_bit(q.b, 1))) return false;
+    tests++;
     if (!(ld_nc_u32(filter + key_word(q.c)) & key_bit(q.c, 2))) return false;
+    tests++;
     return (ld_nc_u32(filter + key_word(q.d)) & key_bit(q.d, 3)) != 0;
 }
 
@@ -218,9 +221,14 @@ __device__ __forceinline__ bool probe_bcd(const uint32_t *__restrict__ filter, c
 // left-to-right greedy scan; on a hit seen++ and, unless seen >= t, the next
 // candidate is k positions later (hash.clear()).  The lane keeps a 96-bit
 // register window of the H/L/W planes and issues kSearchBatch a-probes at once.
+// COUNT adds the number of filter byte tests (`tests`) and k-mer lookups the
+// REFERENCE performs on this strand: a-probes issued speculatively past a hit
+// are not counted, so the totals equal the oracle's (SURVEY 8d N_probes).
+template <bool COUNT>
 __device__ __forceinline__ bool scan_strand(const uint32_t *__restrict__ filter,
                                             const uint4 *__restrict__ planes, uint64_t o,
-                                            uint32_t npos, int k, int t, uint64_t mask, bool rev)
+                                            uint32_t npos, int k, int t, uint64_t mask, bool rev,
+                                            unsigned int &tests, unsigned int &lookups)
 {
     constexpr int U = kSearchBatch;
     uint64_t wi = o >> 5;
@@ -265,13 +273,17 @@ __device__ __forceinline__ bool scan_strand(const uint32_t *__restrict__ filter,
         bool hit = false;
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            if (!hit && ((m >> u) & 1u) && (av[u] & key_bit(ka[u], 0))) {
-                Keys q = make_keys(hv >> u, lv >> u, k, mask, rev);
-                if (probe_bcd(filter, q)) {
-                    hit = true;
-                    seen++;
-                    p += (uint32_t)u + (uint32_t)k;
+            if (!hit && ((m >> u) & 1u)) {
+                unsigned int tt = 1;
+                if (av[u] & key_bit(ka[u], 0)) {
+                    Keys q = make_keys(hv >> u, lv >> u, k, mask, rev);
+                    if (probe_bcd(filter, q, tt)) {
+                        hit = true;
+                        seen++;
+                        p += (uint32_t)u + (uint32_t)k;
+                    }
                 }
+                if (COUNT) { tests += tt; lookups++; }
             }
         }
         if (hit) {
@@ -284,7 +296,9 @@ __device__ __forceinline__ bool scan_strand(const uint32_t *__restrict__ filter,
 }
 
 // search_reads (search_reads.h:34-87): one lane per read, grid-stride.
-// counters[0] += newly found, counters[1] += reads scanned.
+// counters[0] += newly found, counters[1] += reads scanned; with COUNT also
+// counters[2] += filter byte tests, counters[3] += k-mer lookups (reference semantics).
+template <bool COUNT>
 __global__ void __launch_bounds__(256)
 k_search(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
          const uint64_t *__restrict__ offs, uint64_t n_reads, int k, int t,
@@ -292,7 +306,7 @@ k_search(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
 {
     const uint64_t mask = (1ull << k) - 1;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    unsigned int found = 0, searched = 0;
+    unsigned int found = 0, searched = 0, tests = 0, lookups = 0;
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += stride) {
         if ((tags[r >> 5] >> (r & 31)) & 1u) continue;        // file_manager.h:99
         searched++;
@@ -300,8 +314,8 @@ k_search(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
         uint64_t len = offs[r + 1] - o;
         if (len < (uint64_t)k) continue;
         uint32_t npos = (uint32_t)(len - k + 1);
-        bool f = scan_strand(filter, planes, o, npos, k, t, mask, false);
-        if (!f) f = scan_strand(filter, planes, o, npos, k, t, mask, true);
+        bool f = scan_strand<COUNT>(filter, planes, o, npos, k, t, mask, false, tests, lookups);
+        if (!f) f = scan_strand<COUNT>(filter, planes, o, npos, k, t, mask, true, tests, lookups);
         if (f) {
             atomicOr(&tags[r >> 5], 1u << (r & 31));
             found++;
@@ -314,6 +328,17 @@ k_search(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
     if ((threadIdx.x & 31) == 0) {
         if (found) atomicAdd(&counters[0], (unsigned long long)found);
         if (searched) atomicAdd(&counters[1], (unsigned long long)searched);
+    }
+    if (COUNT) {
+        unsigned long long t64 = tests, l64 = lookups;
+        for (int d = 16; d; d >>= 1) {
+            t64 += __shfl_xor_sync(0xffffffffu, t64, d);
+            l64 += __shfl_xor_sync(0xffffffffu, l64, d);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (t64) atomicAdd(&counters[2], t64);
+            if (l64) atomicAdd(&counters[3], l64);
+        }
     }
 }
 

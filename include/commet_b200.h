@@ -45,6 +45,9 @@ void commet_ctx_destroy(commet_ctx *ctx);
 int commet_ctx_sync(commet_ctx *ctx);
 /* CUDA stream of the context as a void* (cudaStream_t); for event timing by the host language. */
 void *commet_ctx_stream(commet_ctx *ctx);
+/* on != 0: search kernels also count the filter byte tests and k-mer lookups the REFERENCE would perform
+ * (stats[5], stats[6] of commet_index_and_search*); a slightly slower instrumented kernel. */
+int commet_ctx_count_probes(commet_ctx *ctx, int on);
 /* number of kernels launched by this context since creation */
 uint64_t commet_ctx_launches(commet_ctx *ctx);
 
@@ -112,7 +115,8 @@ int commet_index_or(commet_ctx *ctx, const void *d_other, uint64_t offset, uint6
  * tags: n_reads/8+1 bytes, read AND written.  *n_found = newly tagged reads
  * (search_reads' return value), *n_searched = reads scanned (:39,44).
  * _dev: tags live on the device as ceil(n/32) u32 words; counters[0]+=found,
- * counters[1]=searched (device u64[2]); nothing is copied to the host. */
+ * counters[1]=searched (device u64[4]; [2],[3] += tests, lookups when probe counting is on); nothing is
+ * copied to the host. */
 int commet_search(commet_ctx *ctx, commet_reads *r, int k, int t, uint8_t *tags,
                   uint64_t *n_found, uint64_t *n_searched);
 int commet_search_dev(commet_ctx *ctx, commet_reads *r, int k, int t, uint32_t *d_tags,
@@ -125,7 +129,8 @@ int commet_search_dev(commet_ctx *ctx, commet_reads *r, int k, int t, uint32_t *
  * searched[s] = last chunk's count, shared[s] = sum over chunks, exactly the
  * numbers of the "[indexed X, searched Y, shared Z]" log line (:286).
  * stats (optional, u64[8]): [0] chunks [1] indexed reads [2] indexed k-mers
- * [3] ns index kernels [4] ns search kernels (device time, CUDA events). */
+ * [3] ns index kernels [4] ns search kernels (device time, CUDA events)
+ * [5] filter byte tests [6] k-mer lookups (only with commet_ctx_count_probes). */
 int commet_index_and_search(commet_ctx *ctx, int k, int t, uint64_t max_kmer,
                             const uint8_t *ibases, const uint64_t *ioffs, uint64_t n_index,
                             int n_sets, const uint8_t *const *qbases,

@@ -109,6 +109,24 @@ def test_index_and_search_chunk_loop(ctx, seed):
     assert info["searched"] == exp["searched"] and info["shared"] == exp["shared"]
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_probe_counts_match_reference_semantics(ctx, seed):
+    """N_probes: the instrumented kernel counts exactly the byte tests / lookups the reference does."""
+    rng = np.random.default_rng(8100 + seed)
+    k = int(rng.integers(9, 16))            # small k: dense filter, many a/b/c passes
+    t = int(rng.integers(1, 4))
+    ref = H.make_ref_set(rng, 3000, 40, 90, **DIRT[seed % 3])
+    qry = H.make_query_set(rng, ref, 800, 40, 90, **DIRT[seed % 3])
+    exp_tags, exp = oracle.index_and_search(k, t, H.to_stream(ref), [H.to_stream(qry)])
+    ctx.count_probes(True)
+    try:
+        tags, info = ctx.index_and_search(k, t, H.to_stream(ref), [H.to_stream(qry)])
+    finally:
+        ctx.count_probes(False)
+    assert np.array_equal(tags[0], oracle.tags_to_bv(exp_tags[0]))
+    assert (info["tests"], info["lookups"]) == (exp["tests"], exp["lookups"])
+
+
 def test_chunk_plan_matches_oracle_walk(ctx):
     rng = np.random.default_rng(5)
     k = 14
