@@ -208,6 +208,7 @@ def main():
     ap.add_argument("-t", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=200_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--direct-index", action="store_true", help="disable the L2-blocked insert (A/B)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -233,6 +234,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     ctx = commet_b200.Context(local_rank)
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    if args.direct_index:
+        ctx.binned_index(False)
 
     n, L, k, t = args.reads, args.length, args.k, args.t
     ref_d, qry_d, offs_d = make_sets_torch(n, L, seed=0, device=dev, qseed=rank)

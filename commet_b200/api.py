@@ -38,6 +38,7 @@ _SIGS = {
     "commet_ctx_stream": (C.c_void_p, [C.c_void_p]),
     "commet_ctx_launches": (C.c_uint64, [C.c_void_p]),
     "commet_ctx_count_probes": (C.c_int, [C.c_void_p, C.c_int]),
+    "commet_ctx_binned_index": (C.c_int, [C.c_void_p, C.c_int]),
     "commet_host_alloc": (C.c_void_p, [C.c_size_t]),
     "commet_host_free": (None, [C.c_void_p]),
     "commet_filter_bytes": (C.c_uint64, [C.c_int]),
@@ -193,6 +194,10 @@ class Context:
     def count_probes(self, on: bool = True):
         """instrumented search: info["tests"], info["lookups"] = the reference's probe counts"""
         self._ck(self.lib.commet_ctx_count_probes(self.handle, int(on)))
+
+    def binned_index(self, on: bool = True):
+        """L2-blocked insert for filters larger than L2 (default on); off = direct RED.OR"""
+        self._ck(self.lib.commet_ctx_binned_index(self.handle, int(on)))
 
     @property
     def launches(self) -> int:

@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -56,6 +57,10 @@ struct commet_ctx {
     unsigned long long *scratch = nullptr;   // kScratch u64 of device counters
     uint64_t launches = 0;
     bool count_probes = false;        // instrumented search kernel (reference-semantics probe counts)
+    bool binned_index = true;         // L2-blocked insert for DRAM-resident filters
+    uint32_t *recs = nullptr;         // region-sorted key records of the L2-blocked insert
+    uint64_t recs_cap = 0;            // capacity in records
+    unsigned long long *bins = nullptr;   // hist[512] | base[513] | cursor[512] | tile counter
 };
 
 struct commet_reads {
@@ -136,6 +141,8 @@ extern "C" void commet_ctx_destroy(commet_ctx *c)
     cudaStreamSynchronize(c->stream);
     if (c->filter) cudaFree(c->filter);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->recs) cudaFree(c->recs);
+    if (c->bins) cudaFree(c->bins);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -149,6 +156,7 @@ extern "C" int commet_ctx_sync(commet_ctx *c)
 
 extern "C" void *commet_ctx_stream(commet_ctx *c) { return (void *)c->stream; }
 extern "C" int commet_ctx_count_probes(commet_ctx *c, int on) { c->count_probes = on != 0; return 0; }
+extern "C" int commet_ctx_binned_index(commet_ctx *c, int on) { c->binned_index = on != 0; return 0; }
 extern "C" uint64_t commet_ctx_launches(commet_ctx *c) { return c->launches; }
 
 extern "C" void *commet_host_alloc(size_t bytes)
@@ -300,9 +308,11 @@ extern "C" int commet_reads_kmer_counts(commet_ctx *c, commet_reads *r, int k, u
 
 // ------------------------------------------------------------- chunk plan ---
 static int chunk_plan(commet_ctx *c, commet_reads *r, int k, uint64_t max_kmer,
-                      std::vector<uint64_t> &bounds, uint64_t *n_indexed, uint64_t *n_kmers)
+                      std::vector<uint64_t> &bounds, uint64_t *n_indexed, uint64_t *n_kmers,
+                      std::vector<uint64_t> *chunk_kmers = nullptr)
 {
     bounds.clear();
+    if (chunk_kmers) chunk_kmers->clear();
     uint64_t n = r->n_reads;
     if (n_indexed) *n_indexed = 0;
     if (n_kmers) *n_kmers = 0;
@@ -321,6 +331,7 @@ static int chunk_plan(commet_ctx *c, commet_reads *r, int k, uint64_t max_kmer,
     if (total < max_kmer) {            // the limit is never reached: one chunk, nothing dropped
         bounds.push_back(0);
         bounds.push_back(n);
+        if (chunk_kmers) chunk_kmers->push_back(total);
         if (n_indexed) *n_indexed = n;
         return 0;
     }
@@ -335,6 +346,7 @@ static int chunk_plan(commet_ctx *c, commet_reads *r, int k, uint64_t max_kmer,
         bounds.push_back(i);
         indexed += i - start;
         kmers += cum;
+        if (chunk_kmers) chunk_kmers->push_back(cum);
         if (i < n && cum >= max_kmer) i++;     // fetched, then lost
     }
     if (n_indexed) *n_indexed = indexed;
@@ -375,7 +387,57 @@ extern "C" int commet_index_begin(commet_ctx *c, int k)
     return 0;
 }
 
-static int index_range(commet_ctx *c, commet_reads *r, uint64_t first, uint64_t count, unsigned long long *d_kmers)
+// L2-blocked insert of stream positions [b0, b1): see kernels.cuh.  kmers_hint = upper bound of the
+// k-mers in the range (0: unknown -> the number of positions).  Returns 1 if the direct path must be used.
+static int index_range_binned(commet_ctx *c, commet_reads *r, uint64_t b0, uint64_t b1, uint64_t kmers_hint)
+{
+    const int k = c->k;
+    const int n_bins = 1 << (k - kRecKeyBits);
+    if (!c->bins) CK(cudaMalloc(&c->bins, 2048 * sizeof(unsigned long long)));
+    unsigned long long *hist = c->bins, *base = c->bins + 512, *cursor = c->bins + 1100, *tile_counter = c->bins + 1700;
+    uint64_t positions = b1 - b0;
+    uint64_t kmers = kmers_hint ? std::min(kmers_hint, positions) : positions;
+    // scratch: 4 records of 4 bytes per k-mer; bounded by what the device has free, else sub-ranges
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    uint64_t budget = (uint64_t)((free_b + c->recs_cap * 4) * 0.6) / 4;       // records
+    if (const char *e = getenv("COMMET_B200_RECS_BUDGET")) {                   // tests: force sub-ranges
+        uint64_t v = strtoull(e, nullptr, 10);
+        if (v >= 4096) budget = std::min(budget, v);
+    }
+    uint64_t need = 4 * kmers + 64;
+    uint64_t parts = 1;
+    if (need > budget) {
+        need = 4 * positions + 64;                   // sub-ranges are cut by position: no per-part k-mer count
+        parts = (need + budget - 1) / budget;
+        need = 4 * ((positions + parts - 1) / parts + 32) + 64;
+    }
+    if (c->recs_cap < need) {
+        if (c->recs) { cudaFree(c->recs); c->recs = nullptr; c->recs_cap = 0; }
+        if (cudaMalloc(&c->recs, need * sizeof(uint32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;                                // no room for the record buffer: direct atomics
+        }
+        c->recs_cap = need;
+    }
+    for (uint64_t p = 0; p < parts; p++) {
+        uint64_t s0 = b0 + positions * p / parts, s1 = b0 + positions * (p + 1) / parts;
+        if (s1 <= s0) continue;
+        CK(cudaMemsetAsync(hist, 0, 512 * sizeof(unsigned long long), c->stream));
+        unsigned g = grid_for(c, s1 - s0 + 32, 256, 8);
+        k_bin_count<<<g, 256, 0, c->stream>>>(r->planes, s0, s1, k, n_bins, hist);
+        k_bin_scan<<<1, 32, 0, c->stream>>>(hist, n_bins, base, cursor, tile_counter);
+        uint64_t n_tiles = (((s1 + 31) >> 5) - (s0 >> 5) + kBinTileWords - 1) / kBinTileWords;
+        unsigned gs = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * 4);
+        k_bin_scatter<<<gs, 256, 0, c->stream>>>(r->planes, s0, s1, k, n_bins, cursor, c->recs);
+        k_bin_apply<<<c->sm_count * 8, 256, 0, c->stream>>>(c->filter, c->recs, base, n_bins, tile_counter);
+        c->launches += 4;
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+static int index_range(commet_ctx *c, commet_reads *r, uint64_t first, uint64_t count, uint64_t kmers_hint)
 {
     if (c->k == 0) return fail("commet_index_add before commet_index_begin");
     if (first + count > r->n_reads) return fail("index range out of bounds");
@@ -387,8 +449,13 @@ static int index_range(commet_ctx *c, commet_reads *r, uint64_t first, uint64_t 
     CK(cudaMemcpyAsync(&hb[1], r->offs + first + count, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (hb[1] <= hb[0]) return 0;
+    // filters larger than L2 (k >= 28: > 64 MiB) take the L2-blocked path
+    if (c->binned_index && c->k >= 28 && c->k - kRecKeyBits <= 9) {
+        int rc = index_range_binned(c, r, hb[0], hb[1], kmers_hint);
+        if (rc <= 0) return rc;
+    }
     uint64_t positions = hb[1] - hb[0] + 32;
-    k_index<<<grid_for(c, positions, 256, 8), 256, 0, c->stream>>>(c->filter, r->planes, hb[0], hb[1], c->k, d_kmers);
+    k_index<<<grid_for(c, positions, 256, 8), 256, 0, c->stream>>>(c->filter, r->planes, hb[0], hb[1], c->k, nullptr);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -397,7 +464,7 @@ static int index_range(commet_ctx *c, commet_reads *r, uint64_t first, uint64_t 
 extern "C" int commet_index_add(commet_ctx *c, commet_reads *r, uint64_t first, uint64_t count)
 {
     CKR(set_device(c));
-    return index_range(c, r, first, count, nullptr);
+    return index_range(c, r, first, count, 0);
 }
 
 extern "C" void *commet_index_filter_ptr(commet_ctx *c) { return c->filter; }
@@ -484,9 +551,9 @@ extern "C" int commet_index_and_search_staged(commet_ctx *c, int k, int t, uint6
 {
     CKR(set_device(c));
     if (n_sets < 0 || n_sets > kMaxSets) return fail("n_sets=%d unsupported (0..%d)", n_sets, kMaxSets);
-    std::vector<uint64_t> bounds;
+    std::vector<uint64_t> bounds, chunk_kmers;
     uint64_t n_indexed = 0, n_kmers = 0;
-    CKR(chunk_plan(c, index, k, max_kmer, bounds, &n_indexed, &n_kmers));
+    CKR(chunk_plan(c, index, k, max_kmer, bounds, &n_indexed, &n_kmers, &chunk_kmers));
     for (int s = 0; s < n_sets; s++) CKR(prepare(c, queries[s], k));
     uint64_t n_chunks = bounds.size() / 2;
     // scratch[4s..4s+3]: found total, searched in the last chunk, filter tests, k-mer lookups
@@ -502,7 +569,7 @@ extern "C" int commet_index_and_search_staged(commet_ctx *c, int k, int t, uint6
             ev.push_back(e0); ev.push_back(e1); ev.push_back(e2);
             CK(cudaEventRecord(e0, c->stream));
         }
-        CKR(index_range(c, index, bounds[2 * ch], bounds[2 * ch + 1] - bounds[2 * ch], nullptr));
+        CKR(index_range(c, index, bounds[2 * ch], bounds[2 * ch + 1] - bounds[2 * ch], chunk_kmers[ch]));
         if (timed) CK(cudaEventRecord(e1, c->stream));
         for (int s = 0; s < n_sets; s++) {
             CK(cudaMemsetAsync(c->scratch + 4 * s + 1, 0, sizeof(unsigned long long), c->stream));

@@ -204,6 +204,241 @@ k_index(uint32_t *__restrict__ filter, const uint4 *__restrict__ planes, uint64_
     if (lane == 0 && local && n_kmers) atomicAdd(n_kmers, local);
 }
 
+// ------------------------------------------- stage 1, L2-blocked variant ----
+// A DRAM-resident filter (k >= 28: 2^(k-1) bytes > L2) takes random RED.OR at
+// the DRAM random-sector rate (~20 G/s measured).  Instead the key stream is
+// first partitioned by filter REGION (2^kRegionLog2 bytes, L2-sized), then
+// applied region after region so that every RED.OR hits L2:
+//   k_bin_count   : per-region record counts            (streaming read)
+//   k_bin_scan    : exclusive prefix -> region offsets   (1 block)
+//   k_bin_scatter : 32-bit records, region-contiguous    (streaming write)
+//   k_bin_apply   : tiles consumed in region order, RED.OR into L2-resident words
+// record = low (kRegionLog2+1) key bits | j << (kRegionLog2+1); the region is
+// the remaining high key bits, i.e. a function of the k-mer's FIRST bases.
+constexpr int kRegionLog2 = 25;                 // 32 MiB regions
+constexpr int kRecKeyBits = kRegionLog2 + 1;    // byte offset in region + odd/even bit
+constexpr int kMaxBins = 512;
+constexpr int kBinTileWords = 64;               // 2048 stream positions per scatter tile
+constexpr int kBinTileRecs = kBinTileWords * 32 * 4;
+constexpr int kApplyTileRecs = 4096;
+
+__device__ __forceinline__ uint64_t ld_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p, uint64_t pol)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_stream_u32(uint32_t *p, uint32_t v, uint64_t pol)
+{
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+k_bin_count(const uint4 *__restrict__ planes, uint64_t b0, uint64_t b1, int k, int n_bins,
+            unsigned long long *__restrict__ hist)
+{
+    __shared__ unsigned int sh[kMaxBins];
+    for (int i = threadIdx.x; i < n_bins; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint64_t mask = (1ull << k) - 1;
+    uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    uint64_t w_first = b0 >> 5, w_end = (b1 + 31) >> 5;
+    for (uint64_t wi = w_first + warp; wi < w_end; wi += n_warps) {
+        uint4 q0 = planes[wi];
+        uint32_t W = q0.w;
+        uint64_t lo = wi << 5;
+        if (lo < b0) W &= ~0u << (b0 - lo);
+        if (lo + 32 > b1) W &= ~0u >> (lo + 32 - b1);
+        if (W == 0) continue;
+        uint4 q1 = planes[wi + 1], q2 = planes[wi + 2];
+        if ((W >> lane) & 1u) {
+            Keys q = make_keys(window64(q0.x, q1.x, q2.x, lane), window64(q0.y, q1.y, q2.y, lane), k, mask, false);
+            atomicAdd(&sh[q.a >> kRecKeyBits], 1u);
+            atomicAdd(&sh[q.b >> kRecKeyBits], 1u);
+            atomicAdd(&sh[q.c >> kRecKeyBits], 1u);
+            atomicAdd(&sh[q.d >> kRecKeyBits], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_bins; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
+// base[b] = exclusive prefix of hist, base[n_bins] = total; cursor[b] = base[b]; tile counter reset
+__global__ void k_bin_scan(const unsigned long long *__restrict__ hist, int n_bins,
+                           unsigned long long *__restrict__ base, unsigned long long *__restrict__ cursor,
+                           unsigned long long *__restrict__ tile_counter)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (int b = 0; b < n_bins; b++) {
+            base[b] = acc;
+            cursor[b] = acc;
+            acc += hist[b];
+        }
+        base[n_bins] = acc;
+        *tile_counter = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_bin_scatter(const uint4 *__restrict__ planes, uint64_t b0, uint64_t b1, int k, int n_bins,
+              unsigned long long *__restrict__ cursor, uint32_t *__restrict__ recs)
+{
+    __shared__ uint32_t stage[kBinTileRecs];            // 32 KB
+    __shared__ uint4 pl[kBinTileWords + 2];
+    __shared__ unsigned int cnt[kMaxBins], start[kMaxBins], fill[kMaxBins];
+    __shared__ unsigned long long gbase[kMaxBins];
+    const uint64_t mask = (1ull << k) - 1;
+    const uint32_t rec_mask = (1u << kRecKeyBits) - 1u;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t pol = ld_policy_evict_first();
+    uint64_t w_first = b0 >> 5, w_end = (b1 + 31) >> 5;
+    uint64_t n_tiles = (w_end - w_first + kBinTileWords - 1) / kBinTileWords;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint64_t tw0 = w_first + tile * kBinTileWords;
+        for (int i = threadIdx.x; i < kBinTileWords + 2; i += blockDim.x) {
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            if (tw0 + i < w_end + 2) q = planes[tw0 + i];     // planes has a zero tail of >= 4 words
+            uint64_t lo = (tw0 + i) << 5;
+            if (i >= kBinTileWords || tw0 + i >= w_end) q.w = 0;
+            else {
+                if (lo < b0) q.w &= ~0u << (b0 - lo);
+                if (lo + 32 > b1) q.w &= ~0u >> (lo + 32 - b1);
+            }
+            pl[i] = q;
+        }
+        for (int i = threadIdx.x; i < n_bins; i += blockDim.x) cnt[i] = 0;
+        __syncthreads();
+        // phase A: count records per region
+        for (int it = 0; it < kBinTileWords / 8; it++) {
+            int wl = warp * (kBinTileWords / 8) + it;
+            uint4 q0 = pl[wl];
+            if ((q0.w >> lane) & 1u) {
+                uint4 q1 = pl[wl + 1], q2 = pl[wl + 2];
+                Keys q = make_keys(window64(q0.x, q1.x, q2.x, lane), window64(q0.y, q1.y, q2.y, lane), k, mask, false);
+                atomicAdd(&cnt[q.a >> kRecKeyBits], 1u);
+                atomicAdd(&cnt[q.b >> kRecKeyBits], 1u);
+                atomicAdd(&cnt[q.c >> kRecKeyBits], 1u);
+                atomicAdd(&cnt[q.d >> kRecKeyBits], 1u);
+            }
+        }
+        __syncthreads();
+        // exclusive scan of cnt (n_bins <= 512, two entries per thread) + global reservation
+        {
+            unsigned int a0 = 0, a1 = 0;
+            int i0 = 2 * threadIdx.x, i1 = i0 + 1;
+            if (i0 < n_bins) a0 = cnt[i0];
+            if (i1 < n_bins) a1 = cnt[i1];
+            unsigned int s = a0 + a1, incl = s;
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += v;
+            }
+            __shared__ unsigned int wsum[8];
+            if (lane == 31) wsum[warp] = incl;
+            __syncthreads();
+            unsigned int off = 0;
+            for (uint32_t w = 0; w < warp; w++) off += wsum[w];
+            unsigned int excl = off + incl - s;
+            if (i0 < n_bins) { start[i0] = excl; fill[i0] = excl; }
+            if (i1 < n_bins) { start[i1] = excl + a0; fill[i1] = excl + a0; }
+            if (i0 < n_bins && a0) gbase[i0] = atomicAdd(&cursor[i0], (unsigned long long)a0);
+            if (i1 < n_bins && a1) gbase[i1] = atomicAdd(&cursor[i1], (unsigned long long)a1);
+        }
+        __syncthreads();
+        // phase B: place records, region-sorted, in shared memory
+        for (int it = 0; it < kBinTileWords / 8; it++) {
+            int wl = warp * (kBinTileWords / 8) + it;
+            uint4 q0 = pl[wl];
+            if ((q0.w >> lane) & 1u) {
+                uint4 q1 = pl[wl + 1], q2 = pl[wl + 2];
+                Keys q = make_keys(window64(q0.x, q1.x, q2.x, lane), window64(q0.y, q1.y, q2.y, lane), k, mask, false);
+                stage[atomicAdd(&fill[q.a >> kRecKeyBits], 1u)] = ((uint32_t)q.a & rec_mask);
+                stage[atomicAdd(&fill[q.b >> kRecKeyBits], 1u)] = ((uint32_t)q.b & rec_mask) | (1u << kRecKeyBits);
+                stage[atomicAdd(&fill[q.c >> kRecKeyBits], 1u)] = ((uint32_t)q.c & rec_mask) | (2u << kRecKeyBits);
+                stage[atomicAdd(&fill[q.d >> kRecKeyBits], 1u)] = ((uint32_t)q.d & rec_mask) | (3u << kRecKeyBits);
+            }
+        }
+        __syncthreads();
+        // phase C: one warp per region run, coalesced copy-out
+        for (int b = warp; b < n_bins; b += 8) {
+            unsigned int n = cnt[b];
+            if (n == 0) continue;
+            const uint32_t *src = stage + start[b];
+            uint32_t *dst = recs + gbase[b];
+            for (unsigned int i = lane; i < n; i += 32) st_stream_u32(dst + i, src[i], pol);
+        }
+        __syncthreads();
+    }
+}
+
+// Tiles of region-sorted records are taken in order from a global counter, so
+// at any time the running blocks touch one or two regions: the RED.OR hit L2.
+__global__ void __launch_bounds__(256)
+k_bin_apply(uint32_t *__restrict__ filter, const uint32_t *__restrict__ recs,
+            const unsigned long long *__restrict__ base, int n_bins,
+            unsigned long long *__restrict__ tile_counter)
+{
+    __shared__ unsigned long long sbase[kMaxBins + 1];
+    __shared__ unsigned long long s_tile;
+    __shared__ int s_bin;
+    for (int i = threadIdx.x; i <= n_bins; i += blockDim.x) sbase[i] = base[i];
+    __syncthreads();
+    const unsigned long long total = sbase[n_bins];
+    const unsigned long long n_tiles = (total + kApplyTileRecs - 1) / kApplyTileRecs;
+    const uint64_t pol = ld_policy_evict_first();
+    const uint32_t rec_mask = (1u << kRecKeyBits) - 1u;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            unsigned long long tl = atomicAdd(tile_counter, 1ull);
+            s_tile = tl;
+            if (tl < n_tiles) {
+                unsigned long long first = tl * kApplyTileRecs;
+                int lo = 0, hi = n_bins - 1;               // last bin with base <= first
+                while (lo < hi) {
+                    int mid = (lo + hi + 1) >> 1;
+                    if (sbase[mid] <= first) lo = mid; else hi = mid - 1;
+                }
+                s_bin = lo;
+            }
+        }
+        __syncthreads();
+        unsigned long long tl = s_tile;
+        int bin0 = s_bin;
+        __syncthreads();
+        if (tl >= n_tiles) break;
+        unsigned long long t0 = tl * kApplyTileRecs;
+#pragma unroll
+        for (int it = 0; it < kApplyTileRecs / (256 * 4); it++) {
+            unsigned long long i = t0 + ((unsigned long long)it * 256 + threadIdx.x) * 4;
+            if (i >= total) break;
+            uint4 v = ld_stream_u4(reinterpret_cast<const uint4 *>(recs + i), pol);
+            uint32_t r[4] = {v.x, v.y, v.z, v.w};
+            int bin = bin0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                unsigned long long idx = i + e;
+                if (idx >= total) break;
+                while (idx >= sbase[bin + 1]) bin++;
+                uint32_t key_low = r[e] & rec_mask;
+                int j = (int)(r[e] >> kRecKeyBits);
+                uint64_t word = ((uint64_t)bin << (kRegionLog2 - 2)) + (key_low >> 3);
+                atomicOr(filter + word, key_bit((uint64_t)key_low, j));
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------ stage 2: search ----
 // BloomFilter::is_found (bloom_filter.h:124-131): b, c, d after a passed,
 // short-circuit in the reference's order.

@@ -48,6 +48,9 @@ void *commet_ctx_stream(commet_ctx *ctx);
 /* on != 0: search kernels also count the filter byte tests and k-mer lookups the REFERENCE would perform
  * (stats[5], stats[6] of commet_index_and_search*); a slightly slower instrumented kernel. */
 int commet_ctx_count_probes(commet_ctx *ctx, int on);
+/* on == 0: always insert with direct RED.OR into the filter; default on: filters larger than L2 (k >= 28) are
+ * fed through the L2-blocked path (keys partitioned by 32 MiB filter region first).  Same filter bits. */
+int commet_ctx_binned_index(commet_ctx *ctx, int on);
 /* number of kernels launched by this context since creation */
 uint64_t commet_ctx_launches(commet_ctx *ctx);
 

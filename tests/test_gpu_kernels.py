@@ -49,6 +49,32 @@ def test_index_filter_bit_exact(ctx, k, dirt):
     assert np.array_equal(ctx.filter_download(k), oracle_filter(k, stream, 17, 101))
 
 
+@pytest.mark.parametrize("k,budget", [(28, None), (29, None), (31, None), (28, "5000"), (30, "100000")])
+def test_index_l2_blocked_path_bit_exact(ctx, k, budget, monkeypatch):
+    """Filters larger than L2 go through the region-partitioned insert: same bits as the oracle, also when the
+    record buffer forces several sub-ranges, and the same bits as the direct RED.OR path."""
+    if budget:
+        monkeypatch.setenv("COMMET_B200_RECS_BUDGET", budget)
+    rng = np.random.default_rng(k)
+    reads = H.make_ref_set(rng, 4000, 20, 150, **DIRT[k % 3])
+    reads += [b"A" * 200, b"T" * 90, b"ACGT" * 40, b"N" * 50, b"G" * (k - 1), b"C" * k]      # skewed regions
+    stream = H.to_stream(reads)
+    rs = ctx.stage(*stream)
+    exp = oracle_filter(k, stream)
+    ctx.binned_index(True)
+    ctx.index_reads(rs, k)
+    got = ctx.filter_download(k)
+    assert np.array_equal(got, exp)
+    ctx.binned_index(False)
+    try:
+        ctx.index_reads(rs, k, 5, 3000)
+        direct = ctx.filter_download(k)
+    finally:
+        ctx.binned_index(True)
+    ctx.index_reads(rs, k, 5, 3000)
+    assert np.array_equal(ctx.filter_download(k), direct)
+
+
 @pytest.mark.parametrize("k", [3, 9, 12, 17, 21])
 def test_kmer_counts(ctx, k):
     rng = np.random.default_rng(k)
