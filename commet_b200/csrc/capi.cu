@@ -76,10 +76,13 @@ namespace {
 constexpr int kScratch = 256;         // [0,128): 4 counters per query set; [128,256): misc
 constexpr int kMaxSets = 30;
 
-struct DevBuf {                       // scoped device allocation
+struct DevBuf {                       // scoped, stream-ordered device allocation (cudaMallocAsync pool)
     void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    cudaStream_t st;
+    explicit DevBuf(const commet_ctx *c) : st(c->stream) {}
+    DevBuf(const DevBuf &) = delete;
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 16, st); }
     template <class T> T *as() { return static_cast<T *>(p); }
 };
 
@@ -128,6 +131,12 @@ extern "C" int commet_ctx_create(int device, commet_ctx **out)
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {   // temporaries come from the stream-ordered pool and stay cached between calls
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     CK(cudaMalloc(&c->scratch, kScratch * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(c->scratch, 0, kScratch * sizeof(unsigned long long), c->stream));
     *out = c;
@@ -181,8 +190,8 @@ static int reads_alloc(commet_ctx *c, uint64_t n_reads, uint64_t n_bases, commet
     r->n_reads = n_reads;
     r->n_bases = n_bases;
     r->n_words = (n_bases + 31) / 32;
-    cudaError_t e = cudaMalloc(&r->planes, (r->n_words + 4) * sizeof(uint4));
-    if (e == cudaSuccess) e = cudaMalloc(&r->offs, (n_reads + 1) * sizeof(uint64_t));
+    cudaError_t e = cudaMallocAsync(&r->planes, (r->n_words + 4) * sizeof(uint4), c->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&r->offs, (n_reads + 1) * sizeof(uint64_t), c->stream);
     if (e != cudaSuccess) {
         commet_reads_free(r);
         return fail("device allocation for %llu bases failed: %s", (unsigned long long)n_bases,
@@ -212,7 +221,7 @@ extern "C" int commet_reads_upload(commet_ctx *c, const uint8_t *bases, const ui
     if (offs[0] != 0) return fail("commet_reads_upload: offs[0] must be 0");
     commet_reads *r = nullptr;
     CKR(reads_alloc(c, n_reads, n_bases, &r));
-    DevBuf ascii;
+    DevBuf ascii(c);
     uint64_t padded = r->n_words * 32;
     if (ascii.alloc(padded) != cudaSuccess) {
         commet_reads_free(r);
@@ -242,7 +251,7 @@ extern "C" int commet_reads_from_device(commet_ctx *c, const uint8_t *d_bases, c
         rc = launch_encode(c, d_bases, r);                 // already vector-aligned: encode in place
         if (rc == 0) CK(cudaStreamSynchronize(c->stream));
     } else {
-        DevBuf ascii;
+        DevBuf ascii(c);
         if (ascii.alloc(padded) != cudaSuccess) { commet_reads_free(r); return fail("staging allocation failed"); }
         CK(cudaMemsetAsync(ascii.as<uint8_t>() + n_bases, 0, padded - n_bases, c->stream));
         if (n_bases) CK(cudaMemcpyAsync(ascii.p, d_bases, n_bases, cudaMemcpyDeviceToDevice, c->stream));
@@ -258,8 +267,9 @@ extern "C" void commet_reads_free(commet_reads *r)
 {
     if (!r) return;
     if (r->ctx) cudaSetDevice(r->ctx->device);
-    if (r->planes) cudaFree(r->planes);
-    if (r->offs) cudaFree(r->offs);
+    cudaStream_t st = r->ctx ? r->ctx->stream : nullptr;
+    if (r->planes) cudaFreeAsync(r->planes, st);
+    if (r->offs) cudaFreeAsync(r->offs, st);
     delete r;
 }
 
@@ -272,18 +282,16 @@ static int prepare(commet_ctx *c, commet_reads *r, int k)
     if (k < 1 || k > kMaxK) return fail("k=%d unsupported (1..%d)", k, kMaxK);
     if (r->k_prepared == k) return 0;
     if (r->n_words) {
-        DevBuf S;
+        DevBuf S(c);
         if (S.alloc((r->n_words + 3) * sizeof(uint32_t)) != cudaSuccess) return fail("allocation of start marks failed");
         CK(cudaMemsetAsync(S.p, 0, (r->n_words + 3) * sizeof(uint32_t), c->stream));
         if (r->n_reads) {
             k_mark_starts<<<grid_for(c, r->n_reads, 256, 8), 256, 0, c->stream>>>(r->offs, r->n_reads, S.as<uint32_t>());
             c->launches++;
         }
-        k_windows<<<grid_for(c, r->n_words * 32, 256, 8), 256, 0, c->stream>>>(r->planes, S.as<uint32_t>(), r->n_words,
-                                                                                 r->n_bases, k);
+        k_windows<<<grid_for(c, r->n_words, 256, 8), 256, 0, c->stream>>>(r->planes, S.as<uint32_t>(), r->n_words, k);
         c->launches++;
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(c->stream));      // S is freed on return
+        CK(cudaGetLastError());                    // S is released in stream order
     }
     r->k_prepared = k;
     return 0;
@@ -294,7 +302,7 @@ extern "C" int commet_reads_kmer_counts(commet_ctx *c, commet_reads *r, int k, u
     CKR(set_device(c));
     CKR(prepare(c, r, k));
     if (r->n_reads == 0) return 0;
-    DevBuf d;
+    DevBuf d(c);
     if (d.alloc(r->n_reads * sizeof(uint32_t)) != cudaSuccess) return fail("allocation of k-mer counts failed");
     CK(cudaMemsetAsync(c->scratch + 150, 0, sizeof(unsigned long long), c->stream));
     k_kmer_counts<<<grid_for(c, r->n_reads, 256, 8), 256, 0, c->stream>>>(r->planes, r->offs, r->n_reads,
@@ -318,7 +326,7 @@ static int chunk_plan(commet_ctx *c, commet_reads *r, int k, uint64_t max_kmer,
     if (n_kmers) *n_kmers = 0;
     if (n == 0) return 0;
     CKR(prepare(c, r, k));
-    DevBuf d;
+    DevBuf d(c);
     if (d.alloc(n * sizeof(uint32_t)) != cudaSuccess) return fail("allocation of k-mer counts failed");
     CK(cudaMemsetAsync(c->scratch + 150, 0, sizeof(unsigned long long), c->stream));
     k_kmer_counts<<<grid_for(c, n, 256, 8), 256, 0, c->stream>>>(r->planes, r->offs, n, d.as<uint32_t>(), c->scratch + 150);
@@ -337,7 +345,8 @@ static int chunk_plan(commet_ctx *c, commet_reads *r, int k, uint64_t max_kmer,
     }
     // index_reads.h:48-49,60 + index_and_search.cpp:255: walk the per-read counts
     std::vector<uint32_t> cnt(n);
-    CK(cudaMemcpy(cnt.data(), d.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(cnt.data(), d.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     uint64_t i = 0, indexed = 0, kmers = 0;
     while (i < n) {
         uint64_t start = i, cum = 0;
@@ -443,11 +452,13 @@ static int index_range(commet_ctx *c, commet_reads *r, uint64_t first, uint64_t 
     if (first + count > r->n_reads) return fail("index range out of bounds");
     if (count == 0 || r->n_words == 0) return 0;
     CKR(prepare(c, r, c->k));
-    uint64_t hb[2];
-    // the two range offsets are read back so the grid can be sized; 16 bytes
-    CK(cudaMemcpyAsync(&hb[0], r->offs + first, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(&hb[1], r->offs + first + count, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    uint64_t hb[2] = {0, r->n_bases};
+    if (first != 0 || count != r->n_reads) {
+        // a sub-range: its two stream offsets are read back (16 bytes) so the work can be sized
+        CK(cudaMemcpyAsync(&hb[0], r->offs + first, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(&hb[1], r->offs + first + count, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
     if (hb[1] <= hb[0]) return 0;
     // filters larger than L2 (k >= 28: > 64 MiB) take the L2-blocked path
     if (c->binned_index && c->k >= 28 && c->k - kRecKeyBits <= 9) {
@@ -529,7 +540,7 @@ extern "C" int commet_search(commet_ctx *c, commet_reads *r, int k, int t, uint8
 {
     CKR(set_device(c));
     uint64_t nb = r->n_reads / 8 + 1, nw = tag_words(r->n_reads);
-    DevBuf d;
+    DevBuf d(c);
     if (d.alloc(nw * 4) != cudaSuccess) return fail("tag allocation failed");
     CK(cudaMemsetAsync(d.p, 0, nw * 4, c->stream));
     CK(cudaMemcpyAsync(d.p, tags, nb, cudaMemcpyHostToDevice, c->stream));
@@ -618,7 +629,7 @@ extern "C" int commet_index_and_search(commet_ctx *c, int k, int t, uint64_t max
         rc = commet_reads_upload(c, qbases[s], qoffs[s], n_query[s], &q[s]);
         if (rc == 0) {
             uint64_t nw = tag_words(n_query[s]);
-            if (cudaMalloc(&dt[s], nw * 4) != cudaSuccess) rc = fail("tag allocation failed");
+            if (cudaMallocAsync(&dt[s], nw * 4, c->stream) != cudaSuccess) rc = fail("tag allocation failed");
             else if (cudaMemsetAsync(dt[s], 0, nw * 4, c->stream) != cudaSuccess) rc = fail("tag memset failed");
         }
     }
@@ -628,7 +639,7 @@ extern "C" int commet_index_and_search(commet_ctx *c, int k, int t, uint64_t max
             rc = fail("tag download failed");
     if (rc == 0 && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail("stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
     commet_reads_free(idx);
-    for (int s = 0; s < n_sets; s++) { commet_reads_free(q[s]); if (dt[s]) cudaFree(dt[s]); }
+    for (int s = 0; s < n_sets; s++) { commet_reads_free(q[s]); if (dt[s]) cudaFreeAsync(dt[s], c->stream); }
     return rc;
 }
 
@@ -661,7 +672,7 @@ extern "C" int commet_filter_reads_staged(commet_ctx *c, commet_reads *r, int64_
     fp.margin = 2e-5f;
     if (max_reads < -1) max_reads = 0;          // `selected < max_reads` is false at once: nothing kept
     const bool cut = max_reads >= 0 && (uint64_t)max_reads < n;
-    DevBuf totals, classes, border, nb, patch;
+    DevBuf totals(c), classes(c), border(c), nb(c), patch(c);
     const unsigned int border_cap = 1u << 20;
     if (totals.alloc(n_blocks * 4 * sizeof(unsigned int)) != cudaSuccess ||
         border.alloc(border_cap * sizeof(BorderRec)) != cudaSuccess || nb.alloc(sizeof(unsigned int)) != cudaSuccess)
@@ -683,7 +694,8 @@ extern "C" int commet_filter_reads_staged(commet_ctx *c, commet_reads *r, int64_
     if (n_border) {
         std::vector<BorderRec> recs(n_border);
         std::vector<uint8_t> cls(n_border);
-        CK(cudaMemcpy(recs.data(), border.p, n_border * sizeof(BorderRec), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpyAsync(recs.data(), border.p, n_border * sizeof(BorderRec), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
         for (unsigned int i = 0; i < n_border; i++)
             cls[i] = shannon_from_counts(recs[i].cnt, recs[i].len) < min_shannon ? 3 : 0;
         if (patch.alloc(n_border) != cudaSuccess) return fail("patch allocation failed");
@@ -718,12 +730,13 @@ extern "C" int commet_filter_reads(commet_ctx *c, const uint8_t *bases, const ui
     CKR(set_device(c));
     commet_reads *r = nullptr;
     CKR(commet_reads_upload(c, bases, offs, n_reads, &r));
-    DevBuf d;
+    DevBuf d(c);
     uint64_t nw = tag_words(n_reads);
     int rc = 0;
     if (d.alloc(nw * 4) != cudaSuccess) rc = fail("bv allocation failed");
     if (rc == 0) rc = commet_filter_reads_staged(c, r, min_len, max_N, min_shannon, max_reads, d.as<uint32_t>(), counters);
-    if (rc == 0 && cudaMemcpy(bv, d.p, n_reads / 8 + 1, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("bv download failed");
+    if (rc == 0 && (cudaMemcpyAsync(bv, d.p, n_reads / 8 + 1, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                    cudaStreamSynchronize(c->stream) != cudaSuccess)) rc = fail("bv download failed");
     commet_reads_free(r);
     return rc;
 }
@@ -773,7 +786,7 @@ extern "C" int commet_bvop(commet_ctx *c, int op, const uint8_t *a, const uint8_
 {
     CKR(set_device(c));
     if (n_bytes == 0) return 0;
-    DevBuf da, db, dout;
+    DevBuf da(c), db(c), dout(c);
     if (da.alloc(n_bytes) != cudaSuccess || dout.alloc(n_bytes) != cudaSuccess || (op != 3 && db.alloc(n_bytes) != cudaSuccess))
         return fail("bvop allocation failed");
     CK(cudaMemcpyAsync(da.p, a, n_bytes, cudaMemcpyHostToDevice, c->stream));
@@ -788,7 +801,7 @@ extern "C" int commet_bv_popcount(commet_ctx *c, const uint8_t *bv, uint64_t n_b
 {
     CKR(set_device(c));
     uint64_t n_bytes = n_bits / 8 + 1;
-    DevBuf d;
+    DevBuf d(c);
     if (d.alloc(n_bytes) != cudaSuccess) return fail("popcount allocation failed");
     CK(cudaMemcpyAsync(d.p, bv, n_bytes, cudaMemcpyHostToDevice, c->stream));
     return commet_bv_popcount_dev(c, d.p, n_bits, ones);
@@ -799,7 +812,7 @@ extern "C" int commet_bench_random_sectors(commet_ctx *c, uint64_t bytes, uint64
 {
     CKR(set_device(c));
     if (bytes < 4096 || (bytes & (bytes - 1))) return fail("bytes must be a power of two >= 4096");
-    DevBuf buf;
+    DevBuf buf(c);
     if (buf.alloc(bytes) != cudaSuccess) return fail("allocation of %llu bytes failed", (unsigned long long)bytes);
     CK(cudaMemsetAsync(buf.p, 0, bytes, c->stream));
     uint64_t mask = bytes / 4 - 1;

@@ -120,25 +120,32 @@ k_mark_starts(const uint64_t *__restrict__ offs, uint64_t n_reads, uint32_t *__r
 
 // W plane: position b starts a k-mer iff V[b..b+k) are all set and no read
 // starts at b+1..b+k-1 (index_reads.h:52-58: hash.clear() per read and per
-// non-ACGT char; a k-mer is fed once hash_size >= k).  One warp per word.
+// non-ACGT char; a k-mer is fed once hash_size >= k).  One thread per 32
+// positions: with A = V & ~S on a 96-bit window, W = V & AND_{d=1..k-1} A[b+d]
+// is built from log2(k) shift-and-AND doublings instead of k tests.
 __global__ void __launch_bounds__(256)
-k_windows(uint4 *__restrict__ planes, const uint32_t *__restrict__ S, uint64_t n_words,
-          uint64_t n_bases, int k)
+k_windows(uint4 *__restrict__ planes, const uint32_t *__restrict__ S, uint64_t n_words, int k)
 {
-    const uint64_t mask = (k >= 64) ? ~0ull : ((1ull << k) - 1);
-    uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    uint32_t lane = threadIdx.x & 31;
-    const uint32_t *P = reinterpret_cast<const uint32_t *>(planes);
-    for (uint64_t wi = warp; wi < n_words; wi += n_warps) {
-        uint32_t v0 = P[4 * wi + 2], v1 = P[4 * (wi + 1) + 2], v2 = P[4 * (wi + 2) + 2];
-        uint32_t s0 = S[wi], s1 = S[wi + 1], s2 = S[wi + 2];
-        uint64_t vw = window64(v0, v1, v2, lane);
-        uint64_t sw = window64(s0, s1, s2, lane);
-        uint64_t b = 32 * wi + lane;
-        bool ok = ((vw & mask) == mask) && ((sw & mask & ~1ull) == 0) && (b + k <= n_bases);
-        uint32_t W = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) reinterpret_cast<uint32_t *>(planes)[4 * wi + 3] = W;
+    typedef unsigned __int128 u128;
+    const int m = k - 1;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t *P32 = reinterpret_cast<uint32_t *>(planes);
+    for (uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += stride) {
+        uint32_t v0 = P32[4 * wi + 2], v1 = P32[4 * (wi + 1) + 2], v2 = P32[4 * (wi + 2) + 2];
+        uint32_t a0 = v0 & ~S[wi], a1 = v1 & ~S[wi + 1], a2 = v2 & ~S[wi + 2];
+        u128 A = (u128)a0 | ((u128)a1 << 32) | ((u128)a2 << 64);
+        u128 P = A >> 1;                      // P[b] = A[b+1]
+        u128 acc = ~(u128)0;
+        int off = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            if (m & (1 << i)) {
+                acc &= P >> off;
+                off += 1 << i;
+            }
+            P &= P >> (1 << i);               // runs of 2^(i+1)
+        }
+        P32[4 * wi + 3] = v0 & (uint32_t)acc;  // V is 0 past the end of the stream: no k-mer crosses it
     }
 }
 
