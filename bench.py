@@ -206,7 +206,7 @@ def main():
     ap.add_argument("--len", type=int, default=100, dest="length")
     ap.add_argument("-k", type=int, default=33)
     ap.add_argument("-t", type=int, default=2)
-    ap.add_argument("--cpu-sample", type=int, default=200_000)
+    ap.add_argument("--cpu-sample", type=int, default=500_000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--direct-index", action="store_true", help="disable the L2-blocked insert (A/B)")
     args = ap.parse_args()
@@ -238,45 +238,47 @@ def main():
         ctx.binned_index(False)
 
     n, L, k, t = args.reads, args.length, args.k, args.t
+    k_arg = k
     ref_d, qry_d, offs_d = make_sets_torch(n, L, seed=0, device=dev, qseed=rank)
     torch.cuda.synchronize()
     n_tag_words = (n // 8 + 1 + 3) // 4
     tags_d = torch.zeros(n_tag_words, dtype=torch.int32, device=dev)
 
-    # reference-set shard of this rank (contiguous reads)
-    r0, r1 = rank * n // world, (rank + 1) * n // world
-    fbytes = 1 << (k - 1)
-    gather_buf = None
+    counters_d = torch.zeros(4, dtype=torch.int64, device=dev)
+    peers = None
     if world > 1:
-        gather_buf = torch.empty((world, fbytes), dtype=torch.uint8, device=dev)
+        # one-time: map every rank's filter into this process (CUDA IPC over NVLink peer memory)
+        from commet_b200 import multi
+        be0 = multi.DeviceBackend(ctx, None, [], [], [])
+
+        def all_gather_bytes(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        be0.connect(k_arg, world, rank, all_gather_bytes)
+        peers = be0.peers
 
     def step_device():
         """one pass with inputs resident in HBM; returns info dict"""
         tags_d.zero_()
         ext.wait_stream(torch.cuda.current_stream())
         q = ctx.stage_device(qry_d.data_ptr(), offs_d.data_ptr(), n, n * L)
+        idx = ctx.stage_device(ref_d.data_ptr(), offs_d.data_ptr(), n, n * L)
         if world == 1:
-            idx = ctx.stage_device(ref_d.data_ptr(), offs_d.data_ptr(), n, n * L)
             info = ctx.index_and_search_staged(k, t, idx, [q], [tags_d.data_ptr()])
-            idx.free()
         else:
-            sub = ref_d[r0 * L:r1 * L]
-            idx = ctx.stage_device(sub.data_ptr(), offs_d.data_ptr(), r1 - r0, (r1 - r0) * L)
-            ctx.index_reads(idx, k)
-            ctx.sync()
-            mine = torch.as_tensor(_FilterView(ctx.filter_ptr, fbytes, local_rank), device=dev)
-            dist.all_gather_into_tensor(gather_buf.view(-1), mine)
+            # every chunk of the reference set is sharded over the ranks, partial filters are merged by the
+            # one-kernel OR all-reduce over peer memory, every rank probes its own query set (commet_b200/multi.py)
+            counters_d.zero_()
             torch.cuda.current_stream().synchronize()
-            for p in range(world):
-                if p != rank:
-                    ctx.index_or(gather_buf[p].data_ptr(), 0, fbytes)
-            counters = torch.zeros(4, dtype=torch.int64, device=dev)
-            ext.wait_stream(torch.cuda.current_stream())
-            ctx.search_reads_device(q, k, t, tags_d.data_ptr(), counters.data_ptr())
+            be = multi.DeviceBackend(ctx, idx, [q], [tags_d.data_ptr()], [counters_d.data_ptr()])
+            be.peers, be.rank, be.k = peers, rank, k
+            r = multi.sharded_index_and_search(be, dist.barrier, world, rank, k, t)
             ctx.sync()
-            info = {"shared": [int(counters[0])], "searched": [int(counters[1])], "chunks": 1, "index_ns": 0, "search_ns": 0,
-                    "kmers": 0}
-            idx.free()
+            c = counters_d.tolist()
+            info = {"shared": [c[0]], "searched": [c[1]], "chunks": r["chunks"], "index_ns": 0, "search_ns": 0, "kmers": 0,
+                    "phases_ms": {key[:-2]: round(r[key] * 1e3, 3) for key in ("index_s", "merge_s", "barrier_s")}}
+        idx.free()
         q.free()
         return info
 
@@ -323,24 +325,44 @@ def main():
         ctx.count_probes(False)
         assert probes["shared"][0] == shared
 
-    # end-to-end leg (single GPU path of the public API; at N>1 every rank runs it on its own query set
-    # against the full reference set -- no sharding of the host->device copies)
-    def step_e2e():
-        tags, inf = ctx.index_and_search(k, t, (ref_h.numpy(), offs_h), [(qry_h.numpy(), offs_h)])
-        return int(np.unpackbits(tags[0]).sum())
+    # end-to-end leg: the same pass through the public API with HOST (pinned) buffers: H2D of both sets and D2H
+    # of the tag vector inside the timed region.  N=1: Context.index_and_search (= the C-ABI call the drop-in
+    # index_and_search tool makes).  N>1: every rank uploads the reference set and its own query set, then
+    # the sharded loop of commet_b200/multi.py; wall clock, max over ranks.
+    tags_h = torch.empty(n // 8 + 1, dtype=torch.uint8).pin_memory()
 
-    e2e = None
-    if world == 1:
-        step_e2e()
-        t0 = time.perf_counter()
-        e2e_steps = max(1, min(args.steps, 3))
-        for _ in range(e2e_steps):
-            ones = step_e2e()
-        torch.cuda.synchronize()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-        assert ones == shared, (ones, shared)
-        e2e = {"value": n / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": int(2 * n * L + 2 * 8 * (n + 1)),
-               "d2h_bytes_per_step": int(n // 8 + 1)}
+    def step_e2e():
+        if world == 1:
+            _, inf = ctx.index_and_search(k, t, (ref_h.numpy(), offs_h), [(qry_h.numpy(), offs_h)])
+            return inf["shared"][0]
+        tags_d.zero_()
+        counters_d.zero_()
+        torch.cuda.current_stream().synchronize()
+        idx = ctx.stage(ref_h.numpy(), offs_h)
+        q = ctx.stage(qry_h.numpy(), offs_h)
+        be = multi.DeviceBackend(ctx, idx, [q], [tags_d.data_ptr()], [counters_d.data_ptr()])
+        be.peers, be.rank, be.k = peers, rank, k
+        multi.sharded_index_and_search(be, dist.barrier, world, rank, k, t)
+        ctx.sync()
+        tags_h.copy_(tags_d.view(torch.uint8)[:n // 8 + 1])
+        idx.free(); q.free()
+        return int(counters_d[0])
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        ones = step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    assert ones == shared, (ones, shared)
+    if world > 1:
+        tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt)
+    e2e = {"value": n * world / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+           "h2d_bytes_per_step": int(world * (2 * n * L + 2 * 8 * (n + 1))), "d2h_bytes_per_step": int(world * (n // 8 + 1))}
 
     if rank != 0:
         if world > 1:
@@ -354,23 +376,30 @@ def main():
         "metric": METRIC, "value": n * world / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic", "config": config, "gpu_launches": int(launches),
-        "clocks": cs.summary(), "shared_reads": int(shared), "chunks": info["chunks"],
+        "clocks": cs.summary(), "shared_reads": int(shared), "chunks": info["chunks"], "e2e": e2e,
     }
-    if e2e:
-        line["e2e"] = e2e
-    if world == 1 and idx_ms > 0:
+    if "phases_ms" in info:
+        line["phases_ms_rank0"] = info["phases_ms"]
+    if world == 1 and srch_ms > 0 and probes:
+        # dominant kernel = k_search (one launch per query set and chunk).  Algorithmic bytes (SURVEY 8d,
+        # DESIGN.md 5): one Bloom bit test = one 32-byte sector, counted with the REFERENCE's semantics
+        # (short-circuit a,b,c,d; greedy k-jump; reverse strand only when the forward scan failed).
+        ncu = ncu_traffic("k_search", config)
+        ach = probes["tests"] * 32 / (srch_ms / 1e3) / 1e9
+        ceil = random_sector_ceiling()
+        line["roofline"] = {"bound": "hbm", "kernel": "k_search", "achieved": ach, "peak": peak, "unit": "GB/s",
+                            "frac": ach / peak, "traffic": ncu, "peak_source": peak_src,
+                            "algorithmic": f"{probes['tests']} filter bit tests x 32 B sector per launch",
+                            "ms_per_launch": srch_ms,
+                            "random_sector_ceiling_GBps": ceil, "frac_of_random_sector_ceiling": (ach / ceil) if ceil else None}
         ins_bytes = kmers * 4 * 64            # 64 B per key insert, 4 keys per k-mer
-        ach = ins_bytes / (idx_ms / 1e3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "k_index", "achieved": ach, "peak": peak, "unit": "GB/s",
-                            "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                            "algorithmic": f"{kmers} k-mers x 4 keys x 64 B (32 B sector read + 32 B write-back)",
-                            "ms_per_launch": idx_ms}
+        line["roofline_index"] = {"bound": "hbm", "kernel": "k_bin_count+k_bin_scatter+k_bin_apply", "achieved": ins_bytes / (idx_ms / 1e3) / 1e9,
+                                  "peak": peak, "unit": "GB/s", "frac": ins_bytes / (idx_ms / 1e3) / 1e9 / peak,
+                                  "algorithmic": f"{kmers} k-mers x 4 keys x 64 B (32 B sector read + 32 B write-back)",
+                                  "ms": idx_ms}
         line["kernels"] = {"index_ms": idx_ms, "search_ms": srch_ms, "kmers_per_s": kmers / (idx_ms / 1e3),
-                           "key_inserts_per_s": 4 * kmers / (idx_ms / 1e3)}
-        if probes and srch_ms > 0:
-            line["kernels"].update({"n_probes": probes["tests"], "n_lookups": probes["lookups"],
-                                    "probes_per_s": probes["tests"] / (srch_ms / 1e3),
-                                    "probe_GBps_algorithmic": probes["tests"] * 32 / (srch_ms / 1e3) / 1e9})
+                           "key_inserts_per_s": 4 * kmers / (idx_ms / 1e3), "n_probes": probes["tests"],
+                           "n_lookups": probes["lookups"], "probes_per_s": probes["tests"] / (srch_ms / 1e3)}
     if not args.no_cpu and world == 1:
         line["cpu_baseline"] = cpu_baseline(ref_h.numpy(), qry_h.numpy(), L, k, t, min(args.cpu_sample, n))
     print(json.dumps(line))
@@ -379,11 +408,27 @@ def main():
     return 0
 
 
-class _FilterView:
-    """the context's filter exposed to torch (zero-copy) through __cuda_array_interface__"""
+def ncu_traffic(kernel: str, config: dict):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full
+    capture of this workload (profiles/ncu_traffic.json); None when the workload differs."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        d = json.loads(p.read_text())
+        w = d["workload"]
+        if all(config.get(key) == w[key] for key in ("reads_per_set", "read_len", "k", "t")):
+            return d["kernels"][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
 
-    def __init__(self, ptr, nbytes, device):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+def random_sector_ceiling():
+    """measured random 32-byte-sector load ceiling over a 4 GiB buffer (profiles/r01_ceilings.json), in GB/s"""
+    try:
+        d = json.loads((ROOT / "profiles" / "r01_ceilings.json").read_text())
+        return d["dram_4GiB_load_Gsectors_s"] * 32
+    except Exception:
+        return None
 
 
 def _mem_procs(filter_bytes: int) -> int:

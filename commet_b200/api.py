@@ -57,6 +57,10 @@ _SIGS = {
     "commet_index_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "commet_index_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]),
     "commet_index_or": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "commet_index_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "commet_peer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "commet_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "commet_index_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "commet_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, _u64p, _u64p]),
     "commet_search_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "commet_index_and_search": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
@@ -265,6 +269,28 @@ class Context:
 
     def index_or(self, d_other: int, offset: int, nbytes: int):
         self._ck(self.lib.commet_index_or(self.handle, _ptr(d_other), offset, nbytes))
+
+    # -- multi-GPU merge --------------------------------------------------------
+    def index_export(self) -> bytes:
+        """CUDA IPC handle (64 bytes) of this context's filter"""
+        buf = (C.c_uint8 * 64)()
+        self._ck(self.lib.commet_index_export(self.handle, buf))
+        return bytes(buf)
+
+    def peer_open(self, handle: bytes) -> int:
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        out = C.c_void_p()
+        self._ck(self.lib.commet_peer_open(self.handle, buf, C.byref(out)))
+        return int(out.value)
+
+    def peer_close(self, d_filter: int):
+        self._ck(self.lib.commet_peer_close(self.handle, _ptr(d_filter)))
+
+    def index_merge(self, d_filters, rank: int):
+        """one-kernel OR all-reduce of the partial filters over peer memory (see commet_index_merge)"""
+        n = len(d_filters)
+        arr = (C.c_void_p * n)(*[C.c_void_p(p or 0) for p in d_filters])
+        self._ck(self.lib.commet_index_merge(self.handle, C.cast(arr, C.c_void_p), n, rank))
 
     # -- stage 2 --------------------------------------------------------------
     def search_reads(self, reads: ReadStream, k: int, t: int, tags: np.ndarray):

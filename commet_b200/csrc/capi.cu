@@ -49,7 +49,9 @@ static int fail(const char *fmt, ...)
 struct commet_ctx {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;    // compute stream: every kernel launch
+    cudaStream_t copy_stream = nullptr;   // H2D staging copies, overlapped with kernels on `stream`
+    std::vector<cudaEvent_t> ev_pool;     // recycled chunk-arrival events
     uint32_t *filter = nullptr;       // bloom_filter.h byte array, device
     uint64_t filter_cap = 0;          // allocated bytes
     uint64_t filter_bytes = 0;        // 2^(k-1)
@@ -69,6 +71,11 @@ struct commet_reads {
     uint4 *planes = nullptr;          // n_words + 4 (zero tail)
     uint64_t *offs = nullptr;         // n_reads + 1, device
     int k_prepared = 0;               // W plane valid for this k (0: none)
+    // upload in flight: ASCII chunks arrive on the copy stream, each followed by an event; the
+    // encode of a chunk is enqueued on the compute stream behind its event (flush_encode)
+    uint8_t *ascii = nullptr;         // device staging of the ASCII bases (pool allocation)
+    std::vector<cudaEvent_t> chunk_ev;
+    uint64_t chunk_words = 0;         // plane words per chunk
 };
 
 namespace {
@@ -130,7 +137,15 @@ extern "C" int commet_ctx_create(int device, commet_ctx **out)
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    // Bloom probes and inserts touch ONE 32-byte sector per key: ask L2 not to pull the neighbouring
+    // sectors of the 128-byte line from DRAM with it (ncu: 4x the algorithmic bytes otherwise)
+    {
+        size_t gran = 32;
+        if (const char *e = getenv("COMMET_B200_L2_FETCH")) gran = (size_t)atoi(e);
+        if (gran) { if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) cudaGetLastError(); }
+    }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     {   // temporaries come from the stream-ordered pool and stay cached between calls
         cudaMemPool_t pool;
         CK(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -152,6 +167,8 @@ extern "C" void commet_ctx_destroy(commet_ctx *c)
     if (c->scratch) cudaFree(c->scratch);
     if (c->recs) cudaFree(c->recs);
     if (c->bins) cudaFree(c->bins);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -202,13 +219,80 @@ static int reads_alloc(commet_ctx *c, uint64_t n_reads, uint64_t n_bases, commet
     return 0;
 }
 
-static int launch_encode(commet_ctx *c, const uint8_t *d_bases_padded, commet_reads *r)
+static int launch_encode(commet_ctx *c, const uint8_t *d_bases_padded, commet_reads *r, uint64_t w0, uint64_t w1)
 {
-    if (r->n_words == 0) return 0;
-    k_encode<<<grid_for(c, r->n_words, 256, 8), 256, 0, c->stream>>>(
-        reinterpret_cast<const uint4 *>(d_bases_padded), r->planes, r->n_words);
+    if (w1 <= w0) return 0;
+    k_encode<<<grid_for(c, w1 - w0, 256, 8), 256, 0, c->stream>>>(
+        reinterpret_cast<const uint4 *>(d_bases_padded) + 2 * w0, r->planes + w0, w1 - w0);
     c->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+static int take_event(commet_ctx *c, cudaEvent_t *e)
+{
+    if (!c->ev_pool.empty()) {
+        *e = c->ev_pool.back();
+        c->ev_pool.pop_back();
+        return 0;
+    }
+    CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    return 0;
+}
+
+constexpr uint64_t kUploadChunk = 32ull << 20;      // bytes of ASCII per H2D copy (multiple of 32)
+
+// Enqueue the H2D copies of a host read stream on the copy stream (one event per chunk); nothing is
+// encoded yet and the host does not wait.  flush_encode() later enqueues, on the compute stream, the
+// 2-bit encode of every chunk behind its arrival event -- so kernels already queued on the compute
+// stream (the index of the previous set) run while these bytes cross PCIe.
+static int reads_upload_async(commet_ctx *c, const uint8_t *bases, const uint64_t *offs, uint64_t n_reads,
+                              commet_reads **out)
+{
+    if (offs[0] != 0) return fail("commet_reads_upload: offs[0] must be 0");
+    uint64_t n_bases = offs[n_reads];
+    commet_reads *r = nullptr;
+    CKR(reads_alloc(c, n_reads, n_bases, &r));
+    uint64_t padded = r->n_words * 32;
+    if (cudaMallocAsync(&r->ascii, padded ? padded : 32, c->stream) != cudaSuccess) {
+        commet_reads_free(r);
+        return fail("device allocation of %llu staging bytes failed", (unsigned long long)padded);
+    }
+    if (padded > n_bases) CK(cudaMemsetAsync(r->ascii + n_bases, 0, padded - n_bases, c->stream));
+    // the copy stream may touch the fresh allocations only after the compute stream has made them
+    cudaEvent_t ready;
+    CKR(take_event(c, &ready));
+    CK(cudaEventRecord(ready, c->stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, ready, 0));
+    c->ev_pool.push_back(ready);
+    CK(cudaMemcpyAsync(r->offs, offs, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->copy_stream));
+    r->chunk_words = kUploadChunk / 32;
+    for (uint64_t b = 0; b < n_bases || b == 0; b += kUploadChunk) {
+        uint64_t len = std::min(kUploadChunk, n_bases - b);
+        if (len) CK(cudaMemcpyAsync(r->ascii + b, bases + b, len, cudaMemcpyHostToDevice, c->copy_stream));
+        cudaEvent_t e;
+        CKR(take_event(c, &e));
+        CK(cudaEventRecord(e, c->copy_stream));
+        r->chunk_ev.push_back(e);
+        if (len == 0) break;
+    }
+    *out = r;
+    return 0;
+}
+
+// compute stream: wait for each chunk, encode it; then release the ASCII staging (stream-ordered)
+static int flush_encode(commet_ctx *c, commet_reads *r)
+{
+    if (!r->ascii) return 0;
+    for (size_t i = 0; i < r->chunk_ev.size(); i++) {
+        CK(cudaStreamWaitEvent(c->stream, r->chunk_ev[i], 0));
+        uint64_t w0 = i * r->chunk_words, w1 = std::min(r->n_words, w0 + r->chunk_words);
+        CKR(launch_encode(c, r->ascii, r, w0, w1));
+        c->ev_pool.push_back(r->chunk_ev[i]);
+    }
+    r->chunk_ev.clear();
+    CK(cudaFreeAsync(r->ascii, c->stream));
+    r->ascii = nullptr;
     return 0;
 }
 
@@ -217,21 +301,11 @@ extern "C" int commet_reads_upload(commet_ctx *c, const uint8_t *bases, const ui
 {
     if (!c || !offs || !out) return fail("commet_reads_upload: null argument");
     CKR(set_device(c));
-    uint64_t n_bases = offs[n_reads] - offs[0];
-    if (offs[0] != 0) return fail("commet_reads_upload: offs[0] must be 0");
     commet_reads *r = nullptr;
-    CKR(reads_alloc(c, n_reads, n_bases, &r));
-    DevBuf ascii(c);
-    uint64_t padded = r->n_words * 32;
-    if (ascii.alloc(padded) != cudaSuccess) {
-        commet_reads_free(r);
-        return fail("device allocation of %llu staging bytes failed", (unsigned long long)padded);
-    }
-    if (padded > n_bases) CK(cudaMemsetAsync(ascii.as<uint8_t>() + n_bases, 0, padded - n_bases, c->stream));
-    if (n_bases) CK(cudaMemcpyAsync(ascii.p, bases, n_bases, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(r->offs, offs, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-    int rc = launch_encode(c, ascii.as<uint8_t>(), r);
-    if (rc == 0 && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail("encode failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CKR(reads_upload_async(c, bases, offs, n_reads, &r));
+    int rc = flush_encode(c, r);
+    if (rc == 0 && cudaStreamSynchronize(c->stream) != cudaSuccess)
+        rc = fail("encode failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (rc != 0) { commet_reads_free(r); return rc; }
     *out = r;
     return 0;
@@ -248,14 +322,14 @@ extern "C" int commet_reads_from_device(commet_ctx *c, const uint8_t *d_bases, c
     uint64_t padded = r->n_words * 32;
     int rc = 0;
     if (padded == n_bases && ((uintptr_t)d_bases & 15) == 0) {
-        rc = launch_encode(c, d_bases, r);                 // already vector-aligned: encode in place
+        rc = launch_encode(c, d_bases, r, 0, r->n_words);   // already vector-aligned: encode in place
         if (rc == 0) CK(cudaStreamSynchronize(c->stream));
     } else {
         DevBuf ascii(c);
         if (ascii.alloc(padded) != cudaSuccess) { commet_reads_free(r); return fail("staging allocation failed"); }
         CK(cudaMemsetAsync(ascii.as<uint8_t>() + n_bases, 0, padded - n_bases, c->stream));
         if (n_bases) CK(cudaMemcpyAsync(ascii.p, d_bases, n_bases, cudaMemcpyDeviceToDevice, c->stream));
-        rc = launch_encode(c, ascii.as<uint8_t>(), r);
+        rc = launch_encode(c, ascii.as<uint8_t>(), r, 0, r->n_words);
         if (rc == 0) CK(cudaStreamSynchronize(c->stream));
     }
     if (rc != 0) { commet_reads_free(r); return rc; }
@@ -268,6 +342,11 @@ extern "C" void commet_reads_free(commet_reads *r)
     if (!r) return;
     if (r->ctx) cudaSetDevice(r->ctx->device);
     cudaStream_t st = r->ctx ? r->ctx->stream : nullptr;
+    if (r->ascii || !r->chunk_ev.empty()) {         // an upload that was never consumed: let its copies land first
+        if (r->ctx) cudaStreamSynchronize(r->ctx->copy_stream);
+        for (cudaEvent_t e : r->chunk_ev) { if (r->ctx) r->ctx->ev_pool.push_back(e); else cudaEventDestroy(e); }
+        if (r->ascii) cudaFreeAsync(r->ascii, st);
+    }
     if (r->planes) cudaFreeAsync(r->planes, st);
     if (r->offs) cudaFreeAsync(r->offs, st);
     delete r;
@@ -280,6 +359,7 @@ extern "C" uint64_t commet_reads_bases(const commet_reads *r) { return r ? r->n_
 static int prepare(commet_ctx *c, commet_reads *r, int k)
 {
     if (k < 1 || k > kMaxK) return fail("k=%d unsupported (1..%d)", k, kMaxK);
+    CKR(flush_encode(c, r));
     if (r->k_prepared == k) return 0;
     if (r->n_words) {
         DevBuf S(c);
@@ -381,7 +461,10 @@ extern "C" int commet_index_begin(commet_ctx *c, int k)
     CKR(set_device(c));
     if (k < 1 || k > kMaxK) return fail("k=%d unsupported (1..%d)", k, kMaxK);
     uint64_t bytes = commet_filter_bytes(k);
-    uint64_t cap = std::max<uint64_t>((bytes + 255) & ~255ull, 256);
+    // at least one whole 2 MiB block of its own: smaller cudaMalloc allocations are sub-allocated by the
+    // driver, and a CUDA IPC handle (commet_index_export) always maps the enclosing block
+    const uint64_t blk = 2ull << 20;
+    uint64_t cap = std::max<uint64_t>((bytes + blk - 1) & ~(blk - 1), blk);
     if (c->filter_cap < cap) {
         if (c->filter) { cudaFree(c->filter); c->filter = nullptr; c->filter_cap = 0; }
         cudaError_t e = cudaMalloc(&c->filter, cap);
@@ -392,7 +475,7 @@ extern "C" int commet_index_begin(commet_ctx *c, int k)
     }
     c->filter_bytes = bytes;
     c->k = k;
-    CK(cudaMemsetAsync(c->filter, 0, cap, c->stream));
+    CK(cudaMemsetAsync(c->filter, 0, std::max<uint64_t>((bytes + 255) & ~255ull, 256), c->stream));
     return 0;
 }
 
@@ -512,6 +595,65 @@ extern "C" int commet_index_or(commet_ctx *c, const void *d_other, uint64_t offs
     return 0;
 }
 
+// ------------------------------------------------------- multi-GPU merge ----
+extern "C" int commet_index_export(commet_ctx *c, uint8_t handle[COMMET_IPC_HANDLE_BYTES])
+{
+    CKR(set_device(c));
+    if (!c->filter) return fail("commet_index_export before commet_index_begin");
+    static_assert(sizeof(cudaIpcMemHandle_t) == COMMET_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->filter));
+    memcpy(handle, &h, sizeof h);
+    return 0;
+}
+
+extern "C" int commet_peer_open(commet_ctx *c, const uint8_t handle[COMMET_IPC_HANDLE_BYTES], void **d_filter)
+{
+    CKR(set_device(c));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    CK(cudaIpcOpenMemHandle(d_filter, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+extern "C" int commet_peer_close(commet_ctx *c, void *d_filter)
+{
+    CKR(set_device(c));
+    if (d_filter) CK(cudaIpcCloseMemHandle(d_filter));
+    return 0;
+}
+
+extern "C" int commet_index_merge(commet_ctx *c, void *const *d_filters, int n_ranks, int rank)
+{
+    CKR(set_device(c));
+    if (n_ranks < 1 || n_ranks > kMaxPeers || rank < 0 || rank >= n_ranks)
+        return fail("commet_index_merge: %d ranks (rank %d) unsupported (1..%d)", n_ranks, rank, kMaxPeers);
+    if (!c->filter) return fail("commet_index_merge before commet_index_begin");
+    if (n_ranks == 1) return 0;
+    PeerFilters pf;
+    for (int p = 0; p < kMaxPeers; p++) pf.f[p] = nullptr;
+    for (int p = 0; p < n_ranks; p++) {
+        pf.f[p] = p == rank ? reinterpret_cast<uint4 *>(c->filter) : static_cast<uint4 *>(d_filters[p]);
+        if (!pf.f[p]) return fail("commet_index_merge: no filter mapped for rank %d", p);
+    }
+    uint64_t n_vec = std::max<uint64_t>(c->filter_bytes / 16, 1);      // filter_cap >= 256 bytes
+    uint64_t v0 = n_vec * rank / n_ranks, v1 = n_vec * (rank + 1) / n_ranks;
+    if (v1 <= v0) return 0;
+    unsigned g = grid_for(c, v1 - v0, 256, 8);
+    switch (n_ranks) {
+    case 2: k_merge_peers<2><<<g, 256, 0, c->stream>>>(pf, rank, v0, v1); break;
+    case 3: k_merge_peers<3><<<g, 256, 0, c->stream>>>(pf, rank, v0, v1); break;
+    case 4: k_merge_peers<4><<<g, 256, 0, c->stream>>>(pf, rank, v0, v1); break;
+    case 5: k_merge_peers<5><<<g, 256, 0, c->stream>>>(pf, rank, v0, v1); break;
+    case 6: k_merge_peers<6><<<g, 256, 0, c->stream>>>(pf, rank, v0, v1); break;
+    case 7: k_merge_peers<7><<<g, 256, 0, c->stream>>>(pf, rank, v0, v1); break;
+    default: k_merge_peers<8><<<g, 256, 0, c->stream>>>(pf, rank, v0, v1); break;
+    }
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // --------------------------------------------------------- stage 2: search --
 static int search_launch(commet_ctx *c, commet_reads *r, int k, int t, uint32_t *d_tags, unsigned long long *d_counters)
 {
@@ -565,7 +707,6 @@ extern "C" int commet_index_and_search_staged(commet_ctx *c, int k, int t, uint6
     std::vector<uint64_t> bounds, chunk_kmers;
     uint64_t n_indexed = 0, n_kmers = 0;
     CKR(chunk_plan(c, index, k, max_kmer, bounds, &n_indexed, &n_kmers, &chunk_kmers));
-    for (int s = 0; s < n_sets; s++) CKR(prepare(c, queries[s], k));
     uint64_t n_chunks = bounds.size() / 2;
     // scratch[4s..4s+3]: found total, searched in the last chunk, filter tests, k-mer lookups
     CK(cudaMemsetAsync(c->scratch, 0, 128 * sizeof(unsigned long long), c->stream));
@@ -573,7 +714,7 @@ extern "C" int commet_index_and_search_staged(commet_ctx *c, int k, int t, uint6
     std::vector<cudaEvent_t> ev;
     if (n_chunks) CKR(commet_index_begin(c, k));
     for (uint64_t ch = 0; ch < n_chunks; ch++) {
-        if (ch) CK(cudaMemsetAsync(c->filter, 0, c->filter_cap, c->stream));
+        if (ch) CK(cudaMemsetAsync(c->filter, 0, std::max<uint64_t>((c->filter_bytes + 255) & ~255ull, 256), c->stream));
         cudaEvent_t e0, e1, e2;
         if (timed) {
             CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
@@ -581,6 +722,8 @@ extern "C" int commet_index_and_search_staged(commet_ctx *c, int k, int t, uint6
             CK(cudaEventRecord(e0, c->stream));
         }
         CKR(index_range(c, index, bounds[2 * ch], bounds[2 * ch + 1] - bounds[2 * ch], chunk_kmers[ch]));
+        // query sets still crossing PCIe are encoded only now, behind the first chunk's index kernels
+        if (ch == 0) for (int s = 0; s < n_sets; s++) CKR(prepare(c, queries[s], k));
         if (timed) CK(cudaEventRecord(e1, c->stream));
         for (int s = 0; s < n_sets; s++) {
             CK(cudaMemsetAsync(c->scratch + 4 * s + 1, 0, sizeof(unsigned long long), c->stream));
@@ -624,9 +767,10 @@ extern "C" int commet_index_and_search(commet_ctx *c, int k, int t, uint64_t max
     commet_reads *idx = nullptr;
     std::vector<commet_reads *> q(n_sets, nullptr);
     std::vector<uint32_t *> dt(n_sets, nullptr);
-    int rc = commet_reads_upload(c, ibases, ioffs, n_index, &idx);
+    // every H2D copy is queued up front on the copy stream (index set first); the host never waits for one
+    int rc = reads_upload_async(c, ibases, ioffs, n_index, &idx);
     for (int s = 0; rc == 0 && s < n_sets; s++) {
-        rc = commet_reads_upload(c, qbases[s], qoffs[s], n_query[s], &q[s]);
+        rc = reads_upload_async(c, qbases[s], qoffs[s], n_query[s], &q[s]);
         if (rc == 0) {
             uint64_t nw = tag_words(n_query[s]);
             if (cudaMallocAsync(&dt[s], nw * 4, c->stream) != cudaSuccess) rc = fail("tag allocation failed");
@@ -661,6 +805,7 @@ extern "C" int commet_filter_reads_staged(commet_ctx *c, commet_reads *r, int64_
                                           float min_shannon, int64_t max_reads, uint32_t *d_bv, uint64_t *counters)
 {
     CKR(set_device(c));
+    CKR(flush_encode(c, r));
     uint64_t n = r->n_reads;
     uint64_t n_bv_words = tag_words(n);
     uint64_t n_blocks = std::max<uint64_t>((std::max(n, n_bv_words * 32) + kFilterBlock - 1) / kFilterBlock, 1);

@@ -873,6 +873,53 @@ k_or_into(uint4 *__restrict__ dst, const uint4 *__restrict__ src, uint64_t n_vec
     }
 }
 
+// ----------------------------------------- multi-GPU: one-kernel OR all-reduce ----
+// Every rank holds a partial filter (its shard of the chunk's reads).  Rank `me`
+// owns vectors [v0, v1) of the filter: it pulls that slice from every peer
+// through NVLink (P2P loads on IPC-mapped peer memory), ORs the partials with its
+// own, and pushes the merged slice back into EVERY rank's filter (P2P stores).
+// When all ranks have run this kernel every filter is the OR of all partials:
+// reduce-scatter + all-gather in one pass, (G-1)/G of the filter in each
+// direction per GPU, instead of NCCL all-gather (G-1 filters in) + local OR.
+constexpr int kMaxPeers = 8;
+struct PeerFilters { uint4 *f[kMaxPeers]; };
+
+// Peer accesses are plain (weak) 16-byte LDG/STG: the partials were completed before the kernel started and
+// the pushes are consumed after it ends (the caller brackets the launch with rank barriers), so no
+// system-scope ordering is needed inside the kernel -- .sys-scoped accesses cost NVLink round trips.
+__device__ __forceinline__ uint4 ld_peer_u4(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_peer_u4(uint4 *p, uint4 v)
+{
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+k_merge_peers(PeerFilters pf, int me, uint64_t v0, uint64_t v1)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < v1; i += stride) {
+        uint4 part[G];
+#pragma unroll
+        for (int p = 0; p < G; p++) part[p] = (p == me) ? pf.f[p][i] : ld_peer_u4(pf.f[p] + i);   // G loads in flight
+        uint4 acc = part[0];
+#pragma unroll
+        for (int p = 1; p < G; p++) { acc.x |= part[p].x; acc.y |= part[p].y; acc.z |= part[p].z; acc.w |= part[p].w; }
+#pragma unroll
+        for (int p = 0; p < G; p++) {
+            if (p == me) pf.f[p][i] = acc;
+            else st_peer_u4(pf.f[p] + i, acc);
+        }
+    }
+}
+
 // ------------------------------------------------- measurement kernels ----
 // random 32-byte-sector ceilings: every lane touches an independent random
 // sector (one u32 load, or one RED.OR) of a `n_words`-word buffer.

@@ -110,6 +110,19 @@ int commet_index_upload(commet_ctx *ctx, int k, const uint8_t *filter, uint64_t 
  * filter, n bytes from byte offset `offset`); d_other may be peer memory. */
 int commet_index_or(commet_ctx *ctx, const void *d_other, uint64_t offset, uint64_t bytes);
 
+/* ---- multi-GPU merge of partial filters (north_star; no reference equivalent) ---------
+ * One process per GPU.  Each rank indexes its shard of a chunk into its own filter, then:
+ *   export:  CUDA IPC handle of this context's filter (valid until the next index_begin with another k)
+ *   open:    map a peer rank's filter into this process (peer access over NVLink)
+ *   merge:   ONE kernel: pull slice `rank` of every peer's partial, OR, push the merged slice into every
+ *            rank's filter.  d_filters[n_ranks]: entry `rank` is ignored (own filter).  The caller brackets
+ *            the call with a barrier over all ranks on both sides (partials complete / pushes complete). */
+#define COMMET_IPC_HANDLE_BYTES 64
+int commet_index_export(commet_ctx *ctx, uint8_t handle[COMMET_IPC_HANDLE_BYTES]);
+int commet_peer_open(commet_ctx *ctx, const uint8_t handle[COMMET_IPC_HANDLE_BYTES], void **d_filter);
+int commet_peer_close(commet_ctx *ctx, void *d_filter);
+int commet_index_merge(commet_ctx *ctx, void *const *d_filters, int n_ranks, int rank);
+
 /* ---- stage 2: search_reads ------------------------------------------------
  * include/search_reads.h:34-87 against the context's current filter: for
  * every read whose bit in `tags` is 0 (FileManager skips tagged reads,

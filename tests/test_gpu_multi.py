@@ -1,0 +1,97 @@
+"""GPU, 2 ranks (needs >= 2 devices; run with `gpurun --gpus 2`): the sharded chunk loop with the one-kernel
+OR all-reduce over CUDA-IPC peer memory gives the single-process oracle's tags, chunk by chunk."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+from oracle import oracle  # noqa: E402
+from tests import helpers as H  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _worker(rank, world, port, k, t, maxk, seed, out_dir):
+    import faulthandler
+    faulthandler.enable()
+    import torch
+    import torch.distributed as dist
+    import commet_b200
+    from commet_b200 import multi
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(rank)
+        ctx = commet_b200.Context(rank)
+        rng = np.random.default_rng(seed)
+        ref = H.make_ref_set(rng, 3000, 40, 120, p_N=0.01)
+        queries = [H.make_query_set(rng, ref, 1500, 40, 120, p_N=0.01) for _ in range(world)]
+        idx = ctx.stage(*H.to_stream(ref))
+        q = ctx.stage(*H.to_stream(queries[rank]))
+        nq = len(queries[rank])
+        tags = torch.zeros((nq // 8 + 1 + 3) // 4, dtype=torch.int32, device=f"cuda:{rank}")
+        counters = torch.zeros(4, dtype=torch.int64, device=f"cuda:{rank}")
+        torch.cuda.synchronize()
+        be = multi.DeviceBackend(ctx, idx, [q], [tags.data_ptr()], [counters.data_ptr()])
+
+        def all_gather_bytes(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        be.connect(k, world, rank, all_gather_bytes)
+        info = multi.sharded_index_and_search(be, dist.barrier, world, rank, k, t, maxk)
+        ctx.sync()
+        filt = ctx.filter_download(k)           # the LAST chunk's merged filter: must be identical on every rank
+        dist.barrier()
+        be.disconnect()
+        np.save(Path(out_dir) / f"tags{rank}.npy", tags.cpu().numpy().view(np.uint8)[:nq // 8 + 1])
+        np.save(Path(out_dir) / f"meta{rank}.npy", np.array([info["chunks"], info["indexed_here"], int(counters[0]), int(counters[1])]))
+        np.save(Path(out_dir) / f"filt{rank}.npy", filt)
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("k,t,maxk,seed", [(16, 2, None, 1), (20, 2, 60000, 2), (29, 2, 90000, 3)])
+def test_sharded_index_merge_search_two_gpus(tmp_path, k, t, maxk, seed):
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), k, t, maxk, seed, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(seed)
+    ref = H.make_ref_set(rng, 3000, 40, 120, p_N=0.01)
+    queries = [H.make_query_set(rng, ref, 1500, 40, 120, p_N=0.01) for _ in range(world)]
+    e_tags, e = oracle.index_and_search(k, t, H.to_stream(ref), [H.to_stream(q) for q in queries], maxk)
+    indexed = 0
+    for r in range(world):
+        tags = np.load(tmp_path / f"tags{r}.npy")
+        chunks, indexed_here, shared, searched = np.load(tmp_path / f"meta{r}.npy").tolist()
+        assert np.array_equal(tags, oracle.tags_to_bv(e_tags[r])), f"rank {r}: tags differ from the oracle"
+        assert chunks == e["chunks"] and shared == e["shared"][r] and searched == e["searched"][r]
+        indexed += indexed_here
+    assert indexed == e["indexed"]
+    assert np.array_equal(np.load(tmp_path / "filt0.npy"), np.load(tmp_path / "filt1.npy"))
+    if maxk:
+        assert e["chunks"] > 2
