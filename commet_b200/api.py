@@ -14,6 +14,7 @@ is in commet_b200/csrc.  No function in this module falls back to the CPU.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from pathlib import Path
 
 import numpy as np
@@ -140,6 +141,7 @@ class ReadStream:
     def __init__(self, ctx: "Context", handle: int):
         self.ctx = ctx
         self.handle = handle
+        ctx._streams.add(self)
 
     @property
     def n_reads(self) -> int:
@@ -150,9 +152,9 @@ class ReadStream:
         return int(self.ctx.lib.commet_reads_bases(self.handle))
 
     def free(self):
-        if self.handle:
+        if self.handle and self.ctx.handle:       # a closed context has already released its streams
             self.ctx.lib.commet_reads_free(self.handle)
-            self.handle = None
+        self.handle = None
 
     def __del__(self):
         try:
@@ -171,9 +173,12 @@ class Context:
             raise CommetError(self.lib.commet_last_error().decode())
         self.handle = h.value
         self.device = device
+        self._streams = weakref.WeakSet()
 
     def close(self):
         if getattr(self, "handle", None):
+            for r in list(self._streams):         # commet_reads hold a pointer to their context
+                r.free()
             self.lib.commet_ctx_destroy(self.handle)
             self.handle = None
 
