@@ -286,7 +286,9 @@ def main():
     ref_h = torch.empty(n * L, dtype=torch.uint8).pin_memory()
     qry_h = torch.empty(n * L, dtype=torch.uint8).pin_memory()
     ref_h.copy_(ref_d); qry_h.copy_(qry_d)
-    offs_h = np.arange(n + 1, dtype=np.uint64) * L
+    offs_ht = torch.empty(n + 1, dtype=torch.int64).pin_memory()       # page-locked like the bases: H2D copies queue ahead
+    offs_ht.copy_(offs_d)
+    offs_h = offs_ht.numpy().view(np.uint64)
 
     def barrier():
         if world > 1:

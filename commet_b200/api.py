@@ -329,7 +329,7 @@ class Context:
                                                   C.cast(qb, C.c_void_p), C.cast(qo, C.c_void_p), _ptr(nq),
                                                   C.cast(tg, C.c_void_p), _ptr(searched), _ptr(shared), _ptr(stats)))
         info = dict(chunks=int(stats[0]), indexed=int(stats[1]), kmers=int(stats[2]), index_ns=int(stats[3]),
-                    search_ns=int(stats[4]), tests=int(stats[5]), lookups=int(stats[6]),
+                    search_ns=int(stats[4]), tests=int(stats[5]), lookups=int(stats[6]), parts=int(stats[7]),
                     searched=[int(x) for x in searched[:ns]], shared=[int(x) for x in shared[:ns]])
         return tags, info
 

@@ -76,6 +76,9 @@ struct commet_reads {
     uint8_t *ascii = nullptr;         // device staging of the ASCII bases (pool allocation)
     std::vector<cudaEvent_t> chunk_ev;
     uint64_t chunk_words = 0;         // plane words per chunk
+    uint64_t offs_base = 0;           // subtracted from the uploaded offsets on the device (flush_encode)
+    const uint8_t *h_bases = nullptr; // host source whose copies are not queued yet (pageable memory)
+    const uint64_t *h_offs = nullptr;
 };
 
 namespace {
@@ -242,33 +245,32 @@ static int take_event(commet_ctx *c, cudaEvent_t *e)
 
 constexpr uint64_t kUploadChunk = 32ull << 20;      // bytes of ASCII per H2D copy (multiple of 32)
 
-// Enqueue the H2D copies of a host read stream on the copy stream (one event per chunk); nothing is
-// encoded yet and the host does not wait.  flush_encode() later enqueues, on the compute stream, the
-// 2-bit encode of every chunk behind its arrival event -- so kernels already queued on the compute
-// stream (the index of the previous set) run while these bytes cross PCIe.
-static int reads_upload_async(commet_ctx *c, const uint8_t *bases, const uint64_t *offs, uint64_t n_reads,
-                              commet_reads **out)
+// cudaMemcpyAsync from pageable memory is staged by the driver and blocks the HOST until the stream gets to
+// it; only page-locked (or device/managed) sources can be queued ahead of time
+static bool queueable(const void *p)
 {
-    if (offs[0] != 0) return fail("commet_reads_upload: offs[0] must be 0");
-    uint64_t n_bases = offs[n_reads];
-    commet_reads *r = nullptr;
-    CKR(reads_alloc(c, n_reads, n_bases, &r));
-    uint64_t padded = r->n_words * 32;
-    if (cudaMallocAsync(&r->ascii, padded ? padded : 32, c->stream) != cudaSuccess) {
-        commet_reads_free(r);
-        return fail("device allocation of %llu staging bytes failed", (unsigned long long)padded);
-    }
-    if (padded > n_bases) CK(cudaMemsetAsync(r->ascii + n_bases, 0, padded - n_bases, c->stream));
-    // the copy stream may touch the fresh allocations only after the compute stream has made them
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type != cudaMemoryTypeUnregistered;
+}
+
+// copy stream: offsets, then the bases in chunks with one arrival event each
+static int enqueue_copies(commet_ctx *c, commet_reads *r)
+{
+    const uint8_t *bases = r->h_bases;
+    const uint64_t *offs = r->h_offs;
+    r->h_bases = nullptr;
+    r->h_offs = nullptr;
+    // the copy stream may touch the allocations only after the compute stream has made them
     cudaEvent_t ready;
     CKR(take_event(c, &ready));
     CK(cudaEventRecord(ready, c->stream));
     CK(cudaStreamWaitEvent(c->copy_stream, ready, 0));
     c->ev_pool.push_back(ready);
-    CK(cudaMemcpyAsync(r->offs, offs, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaMemcpyAsync(r->offs, offs, (r->n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->copy_stream));
     r->chunk_words = kUploadChunk / 32;
-    for (uint64_t b = 0; b < n_bases || b == 0; b += kUploadChunk) {
-        uint64_t len = std::min(kUploadChunk, n_bases - b);
+    for (uint64_t b = 0; b < r->n_bases || b == 0; b += kUploadChunk) {
+        uint64_t len = std::min(kUploadChunk, r->n_bases - b);
         if (len) CK(cudaMemcpyAsync(r->ascii + b, bases + b, len, cudaMemcpyHostToDevice, c->copy_stream));
         cudaEvent_t e;
         CKR(take_event(c, &e));
@@ -276,6 +278,31 @@ static int reads_upload_async(commet_ctx *c, const uint8_t *bases, const uint64_
         r->chunk_ev.push_back(e);
         if (len == 0) break;
     }
+    return 0;
+}
+
+// Queue the H2D copies of a host read stream on the copy stream; nothing is encoded yet and the host does
+// not wait.  flush_encode() later enqueues, on the compute stream, the 2-bit encode of every chunk behind
+// its arrival event -- so kernels already queued on the compute stream (the insert of the previous part)
+// run while these bytes cross PCIe.  Pageable sources cannot be queued ahead (see queueable): their copies
+// are issued by flush_encode, when the data is actually needed.
+static int reads_upload_async(commet_ctx *c, const uint8_t *bases, const uint64_t *offs, uint64_t n_reads,
+                              commet_reads **out)
+{
+    const uint64_t base = offs[0];              // a part of a larger stream: `bases` points at its first base
+    uint64_t n_bases = offs[n_reads] - base;
+    commet_reads *r = nullptr;
+    CKR(reads_alloc(c, n_reads, n_bases, &r));
+    r->offs_base = base;
+    uint64_t padded = r->n_words * 32;
+    if (cudaMallocAsync(&r->ascii, padded ? padded : 32, c->stream) != cudaSuccess) {
+        commet_reads_free(r);
+        return fail("device allocation of %llu staging bytes failed", (unsigned long long)padded);
+    }
+    if (padded > n_bases) CK(cudaMemsetAsync(r->ascii + n_bases, 0, padded - n_bases, c->stream));
+    r->h_bases = bases;
+    r->h_offs = offs;
+    if (queueable(offs) && (n_bases == 0 || queueable(bases))) CKR(enqueue_copies(c, r));
     *out = r;
     return 0;
 }
@@ -284,8 +311,14 @@ static int reads_upload_async(commet_ctx *c, const uint8_t *bases, const uint64_
 static int flush_encode(commet_ctx *c, commet_reads *r)
 {
     if (!r->ascii) return 0;
+    if (r->h_offs) CKR(enqueue_copies(c, r));       // pageable source: copied now
     for (size_t i = 0; i < r->chunk_ev.size(); i++) {
         CK(cudaStreamWaitEvent(c->stream, r->chunk_ev[i], 0));
+        if (i == 0 && r->offs_base) {           // the offsets travel before the first chunk of bases
+            k_rebase<<<grid_for(c, r->n_reads + 1, 256, 8), 256, 0, c->stream>>>(r->offs, r->n_reads + 1, r->offs_base);
+            c->launches++;
+            r->offs_base = 0;
+        }
         uint64_t w0 = i * r->chunk_words, w1 = std::min(r->n_words, w0 + r->chunk_words);
         CKR(launch_encode(c, r->ascii, r, w0, w1));
         c->ev_pool.push_back(r->chunk_ev[i]);
@@ -300,6 +333,7 @@ extern "C" int commet_reads_upload(commet_ctx *c, const uint8_t *bases, const ui
                                    uint64_t n_reads, commet_reads **out)
 {
     if (!c || !offs || !out) return fail("commet_reads_upload: null argument");
+    if (offs[0] != 0) return fail("commet_reads_upload: offs[0] must be 0");
     CKR(set_device(c));
     commet_reads *r = nullptr;
     CKR(reads_upload_async(c, bases, offs, n_reads, &r));
@@ -485,7 +519,10 @@ static int index_range_binned(commet_ctx *c, commet_reads *r, uint64_t b0, uint6
 {
     const int k = c->k;
     const int n_bins = 1 << (k - kRecKeyBits);
-    if (!c->bins) CK(cudaMalloc(&c->bins, 2048 * sizeof(unsigned long long)));
+    if (!c->bins) {
+        CK(cudaMalloc(&c->bins, 2048 * sizeof(unsigned long long)));
+        CK(cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+    }
     unsigned long long *hist = c->bins, *base = c->bins + 512, *cursor = c->bins + 1100, *tile_counter = c->bins + 1700;
     uint64_t positions = b1 - b0;
     uint64_t kmers = kmers_hint ? std::min(kmers_hint, positions) : positions;
@@ -519,9 +556,9 @@ static int index_range_binned(commet_ctx *c, commet_reads *r, uint64_t b0, uint6
         unsigned g = grid_for(c, s1 - s0 + 32, 256, 8);
         k_bin_count<<<g, 256, 0, c->stream>>>(r->planes, s0, s1, k, n_bins, hist);
         k_bin_scan<<<1, 32, 0, c->stream>>>(hist, n_bins, base, cursor, tile_counter);
-        uint64_t n_tiles = (((s1 + 31) >> 5) - (s0 >> 5) + kBinTileWords - 1) / kBinTileWords;
-        unsigned gs = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * 4);
-        k_bin_scatter<<<gs, 256, 0, c->stream>>>(r->planes, s0, s1, k, n_bins, cursor, c->recs);
+        uint64_t n_tiles = (((s1 + 31) >> 5) - (s0 >> 5) + kScatTileWords - 1) / kScatTileWords;
+        unsigned gs = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * 2);
+        k_bin_scatter<<<gs, kScatThreads, sizeof(ScatterSmem), c->stream>>>(r->planes, s0, s1, k, n_bins, cursor, c->recs);
         k_bin_apply<<<c->sm_count * 8, 256, 0, c->stream>>>(c->filter, c->recs, base, n_bins, tile_counter);
         c->launches += 4;
         CK(cudaGetLastError());
@@ -698,39 +735,153 @@ extern "C" int commet_search(commet_ctx *c, commet_reads *r, int k, int t, uint8
 }
 
 // ------------------------------------------------------------- chunk loop ---
-extern "C" int commet_index_and_search_staged(commet_ctx *c, int k, int t, uint64_t max_kmer, commet_reads *index,
-                                              int n_sets, commet_reads *const *queries, uint32_t *const *d_tags,
-                                              uint64_t *searched, uint64_t *shared, uint64_t *stats)
+namespace {
+
+// CUDA-event stopwatch over segments of the compute stream (index / search device time of the log lines)
+struct SegTimer {
+    std::vector<cudaEvent_t> ev;
+    bool on = true;
+    int begin(cudaStream_t st)
+    {
+        if (!on) return 0;
+        if (ev.size() >= 512) { on = false; return 0; }
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        ev.push_back(e0);
+        ev.push_back(e1);
+        CK(cudaEventRecord(e0, st));
+        return 0;
+    }
+    int end(cudaStream_t st)
+    {
+        if (!on || ev.empty()) return 0;
+        CK(cudaEventRecord(ev.back(), st));
+        return 0;
+    }
+    double total_ms()          // after a stream sync
+    {
+        double t = 0;
+        for (size_t i = 0; on && i + 1 < ev.size(); i += 2) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) t += ms;
+        }
+        return t;
+    }
+    ~SegTimer() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+};
+
+}  // namespace
+
+// per-read k-mer counts of a staged stream (device) and their sum (host; syncs the compute stream)
+static int count_kmers(commet_ctx *c, commet_reads *r, int k, DevBuf &counts, unsigned long long *total)
 {
-    CKR(set_device(c));
-    if (n_sets < 0 || n_sets > kMaxSets) return fail("n_sets=%d unsupported (0..%d)", n_sets, kMaxSets);
-    std::vector<uint64_t> bounds, chunk_kmers;
-    uint64_t n_indexed = 0, n_kmers = 0;
-    CKR(chunk_plan(c, index, k, max_kmer, bounds, &n_indexed, &n_kmers, &chunk_kmers));
-    uint64_t n_chunks = bounds.size() / 2;
+    *total = 0;
+    CKR(prepare(c, r, k));
+    if (r->n_reads == 0) return 0;
+    if (counts.alloc(r->n_reads * sizeof(uint32_t)) != cudaSuccess) return fail("allocation of k-mer counts failed");
+    CK(cudaMemsetAsync(c->scratch + 150, 0, sizeof(unsigned long long), c->stream));
+    k_kmer_counts<<<grid_for(c, r->n_reads, 256, 8), 256, 0, c->stream>>>(r->planes, r->offs, r->n_reads,
+                                                                         counts.as<uint32_t>(), c->scratch + 150);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(total, c->scratch + 150, sizeof *total, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// src/index_and_search.cpp:255-277 as ONE streaming pass over the index set, given as consecutive parts of
+// its valid-read stream (one part for device-resident sets; a few for host sets, so that part i+1 crosses
+// PCIe while part i is inserted).  The stop rule of index_reads (index_reads.h:48-49,60) is applied on the
+// running k-mer count: as long as a whole part stays below max_kmer it is inserted without looking at
+// per-read counts; only a part that contains a chunk boundary has its counts walked on the host.  A chunk
+// closes after the read that reaches max_kmer, every query set is searched against it, and the next read is
+// fetched-and-lost -- also when that read is the first one of the next part.
+static int chunk_loop(commet_ctx *c, int k, int t, uint64_t max_kmer, const std::vector<commet_reads *> &parts,
+                      int n_sets, commet_reads *const *queries, uint32_t *const *d_tags,
+                      uint64_t *searched, uint64_t *shared, uint64_t *stats)
+{
     // scratch[4s..4s+3]: found total, searched in the last chunk, filter tests, k-mer lookups
     CK(cudaMemsetAsync(c->scratch, 0, 128 * sizeof(unsigned long long), c->stream));
-    const bool timed = stats && n_chunks <= 64;
-    std::vector<cudaEvent_t> ev;
-    if (n_chunks) CKR(commet_index_begin(c, k));
-    for (uint64_t ch = 0; ch < n_chunks; ch++) {
-        if (ch) CK(cudaMemsetAsync(c->filter, 0, std::max<uint64_t>((c->filter_bytes + 255) & ~255ull, 256), c->stream));
-        cudaEvent_t e0, e1, e2;
-        if (timed) {
-            CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
-            ev.push_back(e0); ev.push_back(e1); ev.push_back(e2);
-            CK(cudaEventRecord(e0, c->stream));
+    uint64_t n_chunks = 0, n_indexed = 0, n_kmers = 0;
+    uint64_t cum = 0, open_reads = 0;
+    bool began = false, dirty = false, pending_drop = false, queries_ready = false;
+    SegTimer t_index, t_search;
+    const uint64_t clear_bytes = std::max<uint64_t>((commet_filter_bytes(k) + 255) & ~255ull, 256);
+
+    auto open_filter = [&]() -> int {
+        if (!began) { CKR(commet_index_begin(c, k)); began = true; }
+        else if (dirty) CK(cudaMemsetAsync(c->filter, 0, clear_bytes, c->stream));
+        dirty = false;
+        return 0;
+    };
+    auto insert = [&](commet_reads *r, uint64_t first, uint64_t count, uint64_t kmers) -> int {
+        CKR(open_filter());
+        CKR(t_index.begin(c->stream));
+        CKR(index_range(c, r, first, count, kmers));
+        CKR(t_index.end(c->stream));
+        n_indexed += count;
+        n_kmers += kmers;
+        open_reads += count;
+        return 0;
+    };
+    auto close_chunk = [&]() -> int {
+        CKR(open_filter());                 // a chunk without reads still owns an (empty) filter
+        if (!queries_ready) {               // query sets still crossing PCIe are encoded only now
+            for (int s = 0; s < n_sets; s++) CKR(prepare(c, queries[s], k));
+            queries_ready = true;
         }
-        CKR(index_range(c, index, bounds[2 * ch], bounds[2 * ch + 1] - bounds[2 * ch], chunk_kmers[ch]));
-        // query sets still crossing PCIe are encoded only now, behind the first chunk's index kernels
-        if (ch == 0) for (int s = 0; s < n_sets; s++) CKR(prepare(c, queries[s], k));
-        if (timed) CK(cudaEventRecord(e1, c->stream));
+        CKR(t_search.begin(c->stream));
         for (int s = 0; s < n_sets; s++) {
             CK(cudaMemsetAsync(c->scratch + 4 * s + 1, 0, sizeof(unsigned long long), c->stream));
             CKR(search_launch(c, queries[s], k, t, d_tags[s], c->scratch + 4 * s));
         }
-        if (timed) CK(cudaEventRecord(e2, c->stream));
+        CKR(t_search.end(c->stream));
+        n_chunks++;
+        cum = 0;
+        open_reads = 0;
+        dirty = true;
+        return 0;
+    };
+
+    for (commet_reads *r : parts) {
+        const uint64_t n = r->n_reads;
+        if (n == 0) continue;
+        DevBuf counts(c);
+        unsigned long long total = 0;
+        CKR(count_kmers(c, r, k, counts, &total));
+        std::vector<uint32_t> cnt;          // fetched only when a chunk boundary falls inside this part
+        uint64_t first = 0, rem = total;
+        if (pending_drop) {                 // the read fetched and lost by the previous chunk (index_reads.h:60)
+            uint32_t c0 = 0;
+            CK(cudaMemcpyAsync(&c0, counts.p, sizeof c0, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            rem -= c0;
+            first = 1;
+            pending_drop = false;
+        }
+        while (first < n) {
+            if (cum + rem < max_kmer) {     // the rest of the part fits in the open chunk
+                CKR(insert(r, first, n - first, rem));
+                cum += rem;
+                break;
+            }
+            if (cnt.empty()) {
+                cnt.resize(n);
+                CK(cudaMemcpyAsync(cnt.data(), counts.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+            }
+            uint64_t i = first, fed = 0;
+            while (i < n && cum < max_kmer) { cum += cnt[i]; fed += cnt[i]; i++; }
+            if (i > first) CKR(insert(r, first, i - first, fed));
+            rem -= fed;
+            CKR(close_chunk());             // cum >= max_kmer here, because cum + rem was
+            if (i < n) { rem -= cnt[i]; i++; } else pending_drop = true;
+            first = i;
+        }
     }
+    if (open_reads > 0) CKR(close_chunk());
+
     unsigned long long h[128];
     CK(cudaMemcpyAsync(h, c->scratch, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -742,18 +893,43 @@ extern "C" int commet_index_and_search_staged(commet_ctx *c, int k, int t, uint6
         n_lookups += h[4 * s + 3];
     }
     if (stats) {
-        double t_index = 0, t_search = 0;
-        for (size_t i = 0; i + 2 < ev.size(); i += 3) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); t_index += ms;
-            cudaEventElapsedTime(&ms, ev[i + 1], ev[i + 2]); t_search += ms;
-        }
         stats[0] = n_chunks; stats[1] = n_indexed; stats[2] = n_kmers;
-        stats[3] = (uint64_t)(t_index * 1e6); stats[4] = (uint64_t)(t_search * 1e6);
-        stats[5] = n_tests; stats[6] = n_lookups; stats[7] = 0;
+        stats[3] = (uint64_t)(t_index.total_ms() * 1e6); stats[4] = (uint64_t)(t_search.total_ms() * 1e6);
+        stats[5] = n_tests; stats[6] = n_lookups; stats[7] = parts.size();
     }
-    for (cudaEvent_t e : ev) cudaEventDestroy(e);
     return 0;
+}
+
+extern "C" int commet_index_and_search_staged(commet_ctx *c, int k, int t, uint64_t max_kmer, commet_reads *index,
+                                              int n_sets, commet_reads *const *queries, uint32_t *const *d_tags,
+                                              uint64_t *searched, uint64_t *shared, uint64_t *stats)
+{
+    CKR(set_device(c));
+    if (n_sets < 0 || n_sets > kMaxSets) return fail("n_sets=%d unsupported (0..%d)", n_sets, kMaxSets);
+    if (k < 1 || k > kMaxK) return fail("k=%d unsupported (1..%d)", k, kMaxK);
+    std::vector<commet_reads *> parts(1, index);
+    return chunk_loop(c, k, t, max_kmer, parts, n_sets, queries, d_tags, searched, shared, stats);
+}
+
+// Read ranges of the parts a host-resident index set is uploaded in: 20 % / 30 % / 50 % of the bases, cut at
+// read boundaries.  Growing parts keep the copy of part i+1 shorter than the insert of part i, so only the
+// first (small) part's copy is exposed; few parts keep the number of sweeps of the filter low.
+static std::vector<uint64_t> split_parts(const uint64_t *offs, uint64_t n_reads)
+{
+    std::vector<uint64_t> cuts(1, 0);
+    const uint64_t n_bases = offs[n_reads];
+    uint64_t min_part = 64ull << 20;
+    if (const char *e = getenv("COMMET_B200_PART_BYTES")) min_part = std::max<uint64_t>(strtoull(e, nullptr, 10), 1);   // tests
+    if (n_bases >= 4 * min_part) {
+        const double frac[2] = {0.2, 0.5};
+        for (double f : frac) {
+            uint64_t target = (uint64_t)(f * (double)n_bases);
+            uint64_t r = (uint64_t)(std::lower_bound(offs, offs + n_reads + 1, target) - offs);
+            if (r > cuts.back() && r < n_reads) cuts.push_back(r);
+        }
+    }
+    cuts.push_back(n_reads);
+    return cuts;
 }
 
 extern "C" int commet_index_and_search(commet_ctx *c, int k, int t, uint64_t max_kmer, const uint8_t *ibases,
@@ -764,12 +940,21 @@ extern "C" int commet_index_and_search(commet_ctx *c, int k, int t, uint64_t max
 {
     CKR(set_device(c));
     if (n_sets < 0 || n_sets > kMaxSets) return fail("n_sets=%d unsupported (0..%d)", n_sets, kMaxSets);
-    commet_reads *idx = nullptr;
+    if (k < 1 || k > kMaxK) return fail("k=%d unsupported (1..%d)", k, kMaxK);
+    if (ioffs[0] != 0) return fail("commet_index_and_search: ioffs[0] must be 0");
+    std::vector<commet_reads *> parts;
     std::vector<commet_reads *> q(n_sets, nullptr);
     std::vector<uint32_t *> dt(n_sets, nullptr);
-    // every H2D copy is queued up front on the copy stream (index set first); the host never waits for one
-    int rc = reads_upload_async(c, ibases, ioffs, n_index, &idx);
+    // every H2D copy is queued up front on the copy stream (index parts first); the host never waits for one
+    std::vector<uint64_t> cuts = split_parts(ioffs, n_index);
+    int rc = 0;
+    for (size_t p = 0; rc == 0 && p + 1 < cuts.size(); p++) {
+        commet_reads *r = nullptr;
+        rc = reads_upload_async(c, ibases + ioffs[cuts[p]], ioffs + cuts[p], cuts[p + 1] - cuts[p], &r);
+        if (rc == 0) parts.push_back(r);
+    }
     for (int s = 0; rc == 0 && s < n_sets; s++) {
+        if (qoffs[s][0] != 0) { rc = fail("commet_index_and_search: qoffs[%d][0] must be 0", s); break; }
         rc = reads_upload_async(c, qbases[s], qoffs[s], n_query[s], &q[s]);
         if (rc == 0) {
             uint64_t nw = tag_words(n_query[s]);
@@ -777,12 +962,12 @@ extern "C" int commet_index_and_search(commet_ctx *c, int k, int t, uint64_t max
             else if (cudaMemsetAsync(dt[s], 0, nw * 4, c->stream) != cudaSuccess) rc = fail("tag memset failed");
         }
     }
-    if (rc == 0) rc = commet_index_and_search_staged(c, k, t, max_kmer, idx, n_sets, q.data(), dt.data(), searched, shared, stats);
+    if (rc == 0) rc = chunk_loop(c, k, t, max_kmer, parts, n_sets, q.data(), dt.data(), searched, shared, stats);
     for (int s = 0; rc == 0 && s < n_sets; s++)
         if (cudaMemcpyAsync(tags[s], dt[s], n_query[s] / 8 + 1, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
             rc = fail("tag download failed");
     if (rc == 0 && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail("stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
-    commet_reads_free(idx);
+    for (commet_reads *r : parts) commet_reads_free(r);
     for (int s = 0; s < n_sets; s++) { commet_reads_free(q[s]); if (dt[s]) cudaFreeAsync(dt[s], c->stream); }
     return rc;
 }

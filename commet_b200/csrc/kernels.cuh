@@ -107,6 +107,14 @@ k_encode(const uint4 *__restrict__ bases16, uint4 *__restrict__ planes, uint64_t
     }
 }
 
+// offsets of a part of a larger stream -> offsets inside the part
+__global__ void __launch_bounds__(256)
+k_rebase(uint64_t *__restrict__ offs, uint64_t n, uint64_t base)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) offs[i] -= base;
+}
+
 // start-of-read marks: bit offs[r] of S for every read r
 __global__ void __launch_bounds__(256)
 k_mark_starts(const uint64_t *__restrict__ offs, uint64_t n_reads, uint32_t *__restrict__ S)
@@ -225,8 +233,11 @@ k_index(uint32_t *__restrict__ filter, const uint4 *__restrict__ planes, uint64_
 constexpr int kRegionLog2 = 25;                 // 32 MiB regions
 constexpr int kRecKeyBits = kRegionLog2 + 1;    // byte offset in region + odd/even bit
 constexpr int kMaxBins = 512;
-constexpr int kBinTileWords = 64;               // 2048 stream positions per scatter tile
-constexpr int kBinTileRecs = kBinTileWords * 32 * 4;
+constexpr uint32_t kRecMask = (1u << kRecKeyBits) - 1u;
+constexpr int kScatThreads = 512;
+constexpr int kScatIters = 4;                                      // 32-position words per warp per tile
+constexpr int kScatTileWords = (kScatThreads / 32) * kScatIters;   // 64 words = 2048 stream positions
+constexpr int kScatTileRecs = kScatTileWords * 32 * 4;             // <= 8192 records per tile
 constexpr int kApplyTileRecs = 4096;
 
 __device__ __forceinline__ uint64_t ld_policy_evict_first()
@@ -247,6 +258,45 @@ __device__ __forceinline__ void st_stream_u32(uint32_t *p, uint32_t v, uint64_t 
     asm volatile("st.global.L1::no_allocate.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory");
 }
 
+// Region and record of the forward keys without building the 64-bit keys: with hw/lw = 64 plane bits from
+// the k-mer's first base (bit 0), the TOP key bits are the first bases and the LOW key bits the last ones,
+// both bit-reversed; c = a^b and d = a|b commute with taking bit fields.
+//   bin  = key >> kRecKeyBits        = brev(first 32 bases) >> (32 - (k - kRecKeyBits))
+//   rec  = key & kRecMask            = brev(32 bases from base k - kRecKeyBits) >> (32 - kRecKeyBits)
+struct BinKeys { uint32_t bin[4], rec[4]; };
+
+__device__ __forceinline__ void bin_only(uint64_t hw, uint64_t lw, int k, uint32_t bin[4])
+{
+    const int top = 32 - (k - kRecKeyBits);
+    bin[0] = __brev((uint32_t)hw) >> top;
+    bin[1] = __brev((uint32_t)lw) >> top;
+    bin[2] = bin[0] ^ bin[1];
+    bin[3] = bin[0] | bin[1];
+}
+
+__device__ __forceinline__ BinKeys bin_keys(uint64_t hw, uint64_t lw, int k)
+{
+    BinKeys q;
+    bin_only(hw, lw, k, q.bin);
+    const int skip = k - kRecKeyBits;                       // bases above the record bits (2..9)
+    uint32_t ra = __brev((uint32_t)(hw >> skip)) >> (32 - kRecKeyBits);
+    uint32_t rb = __brev((uint32_t)(lw >> skip)) >> (32 - kRecKeyBits);
+    q.rec[0] = ra;
+    q.rec[1] = rb | (1u << kRecKeyBits);
+    q.rec[2] = (ra ^ rb) | (2u << kRecKeyBits);
+    q.rec[3] = (ra | rb) | (3u << kRecKeyBits);
+    return q;
+}
+
+// W word of stream word `wi`, restricted to positions [b0, b1)
+__device__ __forceinline__ uint32_t w_in_range(uint32_t W, uint64_t wi, uint64_t b0, uint64_t b1)
+{
+    uint64_t lo = wi << 5;
+    if (lo < b0) W &= ~0u << (b0 - lo);
+    if (lo + 32 > b1) W &= ~0u >> (lo + 32 - b1);
+    return W;
+}
+
 __global__ void __launch_bounds__(256)
 k_bin_count(const uint4 *__restrict__ planes, uint64_t b0, uint64_t b1, int k, int n_bins,
             unsigned long long *__restrict__ hist)
@@ -254,25 +304,22 @@ k_bin_count(const uint4 *__restrict__ planes, uint64_t b0, uint64_t b1, int k, i
     __shared__ unsigned int sh[kMaxBins];
     for (int i = threadIdx.x; i < n_bins; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    const uint64_t mask = (1ull << k) - 1;
     uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     uint32_t lane = threadIdx.x & 31;
     uint64_t w_first = b0 >> 5, w_end = (b1 + 31) >> 5;
     for (uint64_t wi = w_first + warp; wi < w_end; wi += n_warps) {
         uint4 q0 = planes[wi];
-        uint32_t W = q0.w;
-        uint64_t lo = wi << 5;
-        if (lo < b0) W &= ~0u << (b0 - lo);
-        if (lo + 32 > b1) W &= ~0u >> (lo + 32 - b1);
+        uint32_t W = w_in_range(q0.w, wi, b0, b1);
         if (W == 0) continue;
-        uint4 q1 = planes[wi + 1], q2 = planes[wi + 2];
+        uint4 q1 = planes[wi + 1];
         if ((W >> lane) & 1u) {
-            Keys q = make_keys(window64(q0.x, q1.x, q2.x, lane), window64(q0.y, q1.y, q2.y, lane), k, mask, false);
-            atomicAdd(&sh[q.a >> kRecKeyBits], 1u);
-            atomicAdd(&sh[q.b >> kRecKeyBits], 1u);
-            atomicAdd(&sh[q.c >> kRecKeyBits], 1u);
-            atomicAdd(&sh[q.d >> kRecKeyBits], 1u);
+            uint32_t bin[4];
+            bin_only(__funnelshift_r(q0.x, q1.x, lane), __funnelshift_r(q0.y, q1.y, lane), k, bin);
+            atomicAdd(&sh[bin[0]], 1u);
+            atomicAdd(&sh[bin[1]], 1u);
+            atomicAdd(&sh[bin[2]], 1u);
+            atomicAdd(&sh[bin[3]], 1u);
         }
     }
     __syncthreads();
@@ -297,152 +344,150 @@ __global__ void k_bin_scan(const unsigned long long *__restrict__ hist, int n_bi
     }
 }
 
-__global__ void __launch_bounds__(256)
+// One tile = 2048 stream positions.  Single pass over the keys: the shared-memory atomic that counts a
+// region also hands the record its rank inside the tile's run for that region; (region, rank) and the
+// record stay in registers across the block-wide scan, then records are placed region-sorted in shared
+// memory and copied out with one coalesced store per record slot.
+struct ScatterSmem {
+    uint32_t stage[kScatTileRecs];            // 32 KB region-sorted records
+    uint16_t sbin[kScatTileRecs];             // 16 KB region of every staged record
+    unsigned long long delta[kMaxBins];       // global slot of the region's run minus its offset in `stage`
+    uint32_t cnt[kMaxBins], start[kMaxBins];
+    uint32_t wsum[kScatThreads / 32];
+};
+
+__global__ void __launch_bounds__(kScatThreads, 2)
 k_bin_scatter(const uint4 *__restrict__ planes, uint64_t b0, uint64_t b1, int k, int n_bins,
               unsigned long long *__restrict__ cursor, uint32_t *__restrict__ recs)
 {
-    __shared__ uint32_t stage[kBinTileRecs];            // 32 KB
-    __shared__ uint4 pl[kBinTileWords + 2];
-    __shared__ unsigned int cnt[kMaxBins], start[kMaxBins], fill[kMaxBins];
-    __shared__ unsigned long long gbase[kMaxBins];
-    const uint64_t mask = (1ull << k) - 1;
-    const uint32_t rec_mask = (1u << kRecKeyBits) - 1u;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t pol = ld_policy_evict_first();
-    uint64_t w_first = b0 >> 5, w_end = (b1 + 31) >> 5;
-    uint64_t n_tiles = (w_end - w_first + kBinTileWords - 1) / kBinTileWords;
+    const uint64_t w_first = b0 >> 5, w_end = (b1 + 31) >> 5;
+    const uint64_t n_tiles = (w_end - w_first + kScatTileWords - 1) / kScatTileWords;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        uint64_t tw0 = w_first + tile * kBinTileWords;
-        for (int i = threadIdx.x; i < kBinTileWords + 2; i += blockDim.x) {
-            uint4 q = make_uint4(0u, 0u, 0u, 0u);
-            if (tw0 + i < w_end + 2) q = planes[tw0 + i];     // planes has a zero tail of >= 4 words
-            uint64_t lo = (tw0 + i) << 5;
-            if (i >= kBinTileWords || tw0 + i >= w_end) q.w = 0;
-            else {
-                if (lo < b0) q.w &= ~0u << (b0 - lo);
-                if (lo + 32 > b1) q.w &= ~0u >> (lo + 32 - b1);
-            }
-            pl[i] = q;
-        }
-        for (int i = threadIdx.x; i < n_bins; i += blockDim.x) cnt[i] = 0;
+        for (int i = tid; i < n_bins; i += kScatThreads) sm.cnt[i] = 0;
         __syncthreads();
-        // phase A: count records per region
-        for (int it = 0; it < kBinTileWords / 8; it++) {
-            int wl = warp * (kBinTileWords / 8) + it;
-            uint4 q0 = pl[wl];
-            if ((q0.w >> lane) & 1u) {
-                uint4 q1 = pl[wl + 1], q2 = pl[wl + 2];
-                Keys q = make_keys(window64(q0.x, q1.x, q2.x, lane), window64(q0.y, q1.y, q2.y, lane), k, mask, false);
-                atomicAdd(&cnt[q.a >> kRecKeyBits], 1u);
-                atomicAdd(&cnt[q.b >> kRecKeyBits], 1u);
-                atomicAdd(&cnt[q.c >> kRecKeyBits], 1u);
-                atomicAdd(&cnt[q.d >> kRecKeyBits], 1u);
+        uint32_t rec[4 * kScatIters], br[4 * kScatIters];      // record, region << 16 | rank (~0: none)
+#pragma unroll
+        for (int it = 0; it < kScatIters; it++) {
+            uint64_t wi = w_first + tile * kScatTileWords + (uint64_t)it * (kScatThreads / 32) + warp;
+            uint32_t W = 0;
+            uint4 q0 = make_uint4(0u, 0u, 0u, 0u);
+            if (wi < w_end) {                                   // warp-uniform
+                q0 = planes[wi];
+                W = w_in_range(q0.w, wi, b0, b1);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) br[4 * it + j] = ~0u;
+            if (W != 0) {                                       // warp-uniform
+                uint4 q1 = planes[wi + 1], q2 = planes[wi + 2];
+                if ((W >> lane) & 1u) {
+                    BinKeys q = bin_keys(window64(q0.x, q1.x, q2.x, lane), window64(q0.y, q1.y, q2.y, lane), k);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        rec[4 * it + j] = q.rec[j];
+                        br[4 * it + j] = (q.bin[j] << 16) | atomicAdd(&sm.cnt[q.bin[j]], 1u);
+                    }
+                }
             }
         }
         __syncthreads();
-        // exclusive scan of cnt (n_bins <= 512, two entries per thread) + global reservation
+        // exclusive scan of cnt over the regions (n_bins <= 512 = one per thread) + global reservation
         {
-            unsigned int a0 = 0, a1 = 0;
-            int i0 = 2 * threadIdx.x, i1 = i0 + 1;
-            if (i0 < n_bins) a0 = cnt[i0];
-            if (i1 < n_bins) a1 = cnt[i1];
-            unsigned int s = a0 + a1, incl = s;
+            uint32_t c = (int)tid < n_bins ? sm.cnt[tid] : 0u;
+            uint32_t incl = c;
+#pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                unsigned int v = __shfl_up_sync(0xffffffffu, incl, d);
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= (uint32_t)d) incl += v;
             }
-            __shared__ unsigned int wsum[8];
-            if (lane == 31) wsum[warp] = incl;
+            if (lane == 31) sm.wsum[warp] = incl;
             __syncthreads();
-            unsigned int off = 0;
-            for (uint32_t w = 0; w < warp; w++) off += wsum[w];
-            unsigned int excl = off + incl - s;
-            if (i0 < n_bins) { start[i0] = excl; fill[i0] = excl; }
-            if (i1 < n_bins) { start[i1] = excl + a0; fill[i1] = excl + a0; }
-            if (i0 < n_bins && a0) gbase[i0] = atomicAdd(&cursor[i0], (unsigned long long)a0);
-            if (i1 < n_bins && a1) gbase[i1] = atomicAdd(&cursor[i1], (unsigned long long)a1);
-        }
-        __syncthreads();
-        // phase B: place records, region-sorted, in shared memory
-        for (int it = 0; it < kBinTileWords / 8; it++) {
-            int wl = warp * (kBinTileWords / 8) + it;
-            uint4 q0 = pl[wl];
-            if ((q0.w >> lane) & 1u) {
-                uint4 q1 = pl[wl + 1], q2 = pl[wl + 2];
-                Keys q = make_keys(window64(q0.x, q1.x, q2.x, lane), window64(q0.y, q1.y, q2.y, lane), k, mask, false);
-                stage[atomicAdd(&fill[q.a >> kRecKeyBits], 1u)] = ((uint32_t)q.a & rec_mask);
-                stage[atomicAdd(&fill[q.b >> kRecKeyBits], 1u)] = ((uint32_t)q.b & rec_mask) | (1u << kRecKeyBits);
-                stage[atomicAdd(&fill[q.c >> kRecKeyBits], 1u)] = ((uint32_t)q.c & rec_mask) | (2u << kRecKeyBits);
-                stage[atomicAdd(&fill[q.d >> kRecKeyBits], 1u)] = ((uint32_t)q.d & rec_mask) | (3u << kRecKeyBits);
+            uint32_t off = 0;
+            for (uint32_t w = 0; w < warp; w++) off += sm.wsum[w];
+            uint32_t excl = off + incl - c;
+            if ((int)tid < n_bins) {
+                sm.start[tid] = excl;
+                if (c) sm.delta[tid] = atomicAdd(&cursor[tid], (unsigned long long)c) - excl;
             }
         }
         __syncthreads();
-        // phase C: one warp per region run, coalesced copy-out
-        for (int b = warp; b < n_bins; b += 8) {
-            unsigned int n = cnt[b];
-            if (n == 0) continue;
-            const uint32_t *src = stage + start[b];
-            uint32_t *dst = recs + gbase[b];
-            for (unsigned int i = lane; i < n; i += 32) st_stream_u32(dst + i, src[i], pol);
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < kScatThreads / 32; w++) total += sm.wsum[w];
+#pragma unroll
+        for (int i = 0; i < 4 * kScatIters; i++) {
+            if (br[i] != ~0u) {
+                uint32_t bin = br[i] >> 16;
+                uint32_t pos = sm.start[bin] + (br[i] & 0xFFFFu);
+                sm.stage[pos] = rec[i];
+                sm.sbin[pos] = (uint16_t)bin;
+            }
         }
         __syncthreads();
+        for (uint32_t j = tid; j < total; j += kScatThreads)
+            st_stream_u32(recs + (sm.delta[sm.sbin[j]] + j), sm.stage[j], pol);
+        // no barrier here: the next tile's first barrier (after zeroing cnt) orders these reads of
+        // stage/sbin/delta before any of its writes to them
     }
 }
 
-// Tiles of region-sorted records are taken in order from a global counter, so
-// at any time the running blocks touch one or two regions: the RED.OR hit L2.
+// Tiles of region-sorted records are taken in order from a global counter, so at any time the running
+// blocks touch one or two regions: the RED.OR hit L2.  The next tile is claimed while the current one is
+// processed, and every thread has its four 16-byte record loads in flight before the first RED.
 __global__ void __launch_bounds__(256)
 k_bin_apply(uint32_t *__restrict__ filter, const uint32_t *__restrict__ recs,
             const unsigned long long *__restrict__ base, int n_bins,
             unsigned long long *__restrict__ tile_counter)
 {
     __shared__ unsigned long long sbase[kMaxBins + 1];
-    __shared__ unsigned long long s_tile;
-    __shared__ int s_bin;
+    __shared__ unsigned long long s_next;
     for (int i = threadIdx.x; i <= n_bins; i += blockDim.x) sbase[i] = base[i];
+    if (threadIdx.x == 0) s_next = atomicAdd(tile_counter, 1ull);
     __syncthreads();
     const unsigned long long total = sbase[n_bins];
     const unsigned long long n_tiles = (total + kApplyTileRecs - 1) / kApplyTileRecs;
     const uint64_t pol = ld_policy_evict_first();
-    const uint32_t rec_mask = (1u << kRecKeyBits) - 1u;
-    for (;;) {
-        if (threadIdx.x == 0) {
-            unsigned long long tl = atomicAdd(tile_counter, 1ull);
-            s_tile = tl;
-            if (tl < n_tiles) {
-                unsigned long long first = tl * kApplyTileRecs;
-                int lo = 0, hi = n_bins - 1;               // last bin with base <= first
-                while (lo < hi) {
-                    int mid = (lo + hi + 1) >> 1;
-                    if (sbase[mid] <= first) lo = mid; else hi = mid - 1;
-                }
-                s_bin = lo;
-            }
-        }
-        __syncthreads();
-        unsigned long long tl = s_tile;
-        int bin0 = s_bin;
-        __syncthreads();
-        if (tl >= n_tiles) break;
-        unsigned long long t0 = tl * kApplyTileRecs;
+    unsigned long long tl = s_next;
+    while (tl < n_tiles) {
+        __syncthreads();                                   // everybody holds `tl`: s_next may be overwritten
+        unsigned long long nxt = 0;
+        if (threadIdx.x == 0) nxt = atomicAdd(tile_counter, 1ull);      // consumed after this tile
+        const unsigned long long t0 = tl * kApplyTileRecs;
+        uint4 v[kApplyTileRecs / (256 * 4)];
+        unsigned long long idx[kApplyTileRecs / (256 * 4)];
 #pragma unroll
         for (int it = 0; it < kApplyTileRecs / (256 * 4); it++) {
-            unsigned long long i = t0 + ((unsigned long long)it * 256 + threadIdx.x) * 4;
-            if (i >= total) break;
-            uint4 v = ld_stream_u4(reinterpret_cast<const uint4 *>(recs + i), pol);
-            uint32_t r[4] = {v.x, v.y, v.z, v.w};
-            int bin = bin0;
+            idx[it] = t0 + ((unsigned long long)it * 256 + threadIdx.x) * 4;
+            v[it] = make_uint4(0u, 0u, 0u, 0u);
+            if (idx[it] < total) v[it] = ld_stream_u4(reinterpret_cast<const uint4 *>(recs + idx[it]), pol);   // recs is padded to 16 B
+        }
+#pragma unroll
+        for (int it = 0; it < kApplyTileRecs / (256 * 4); it++) {
+            if (idx[it] >= total) continue;
+            int lo = 0, hi = n_bins - 1;                   // last region with base <= idx
+            while (lo < hi) {
+                int mid = (lo + hi + 1) >> 1;
+                if (sbase[mid] <= idx[it]) lo = mid; else hi = mid - 1;
+            }
+            int bin = lo;
+            unsigned long long lim = sbase[bin + 1];
+            uint32_t r[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                unsigned long long idx = i + e;
-                if (idx >= total) break;
-                while (idx >= sbase[bin + 1]) bin++;
-                uint32_t key_low = r[e] & rec_mask;
-                int j = (int)(r[e] >> kRecKeyBits);
+                unsigned long long i = idx[it] + e;
+                if (i >= total) break;
+                while (i >= lim) lim = sbase[++bin + 1];
+                uint32_t key_low = r[e] & kRecMask;
                 uint64_t word = ((uint64_t)bin << (kRegionLog2 - 2)) + (key_low >> 3);
-                atomicOr(filter + word, key_bit((uint64_t)key_low, j));
+                atomicOr(filter + word, key_bit((uint64_t)key_low, (int)(r[e] >> kRecKeyBits)));
             }
         }
+        if (threadIdx.x == 0) s_next = nxt;
+        __syncthreads();
+        tl = s_next;
     }
 }
 

@@ -146,7 +146,8 @@ int commet_search_dev(commet_ctx *ctx, commet_reads *r, int k, int t, uint32_t *
  * numbers of the "[indexed X, searched Y, shared Z]" log line (:286).
  * stats (optional, u64[8]): [0] chunks [1] indexed reads [2] indexed k-mers
  * [3] ns index kernels [4] ns search kernels (device time, CUDA events)
- * [5] filter byte tests [6] k-mer lookups (only with commet_ctx_count_probes). */
+ * [5] filter byte tests [6] k-mer lookups (only with commet_ctx_count_probes)
+ * [7] parts the index set was uploaded in (host entry point: part i+1 crosses PCIe while part i is inserted). */
 int commet_index_and_search(commet_ctx *ctx, int k, int t, uint64_t max_kmer,
                             const uint8_t *ibases, const uint64_t *ioffs, uint64_t n_index,
                             int n_sets, const uint8_t *const *qbases,

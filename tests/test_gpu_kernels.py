@@ -135,6 +135,31 @@ def test_index_and_search_chunk_loop(ctx, seed):
     assert info["searched"] == exp["searched"] and info["shared"] == exp["shared"]
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_chunk_loop_over_uploaded_parts(ctx, seed, monkeypatch):
+    """Host index sets are uploaded in three parts (20/30/50 % of the bases) that are inserted while the next
+    one crosses PCIe: chunk boundaries and the fetched-and-lost read must come out the same wherever they fall
+    relative to the part boundaries (inside a part, on its last read, on the first read of the next part)."""
+    monkeypatch.setenv("COMMET_B200_PART_BYTES", str(int(np.random.default_rng(seed).integers(50, 3000))))
+    rng = np.random.default_rng(9000 + seed)
+    k = int(rng.integers(8, 19))
+    t = int(rng.integers(1, 3))
+    L = int(rng.integers(k, 4 * k))
+    n_ref = int(rng.integers(30, 1500))
+    ref = H.make_ref_set(rng, n_ref, max(1, L - 10), L + 10, **DIRT[seed % 3])
+    total_kmers = sum(max(0, len(r) - k + 1) for r in ref)
+    # from "never reached" to dozens of chunks, including limits that land exactly on a read's last k-mer
+    maxk = [None, max(1, total_kmers // 2), max(1, total_kmers // 7), max(1, total_kmers // 40), 1][seed % 5]
+    queries = [H.make_query_set(rng, ref, int(rng.integers(1, 300)), max(1, L - 10), L + 10, **DIRT[seed % 3])
+               for _ in range(2)]
+    exp_tags, exp = oracle.index_and_search(k, t, H.to_stream(ref), [H.to_stream(q) for q in queries], maxk)
+    tags, info = ctx.index_and_search(k, t, H.to_stream(ref), [H.to_stream(q) for q in queries], maxk)
+    assert info["chunks"] == exp["chunks"] and info["indexed"] == exp["indexed"] and info["kmers"] == exp["kmers"]
+    for s in range(len(queries)):
+        assert np.array_equal(tags[s], oracle.tags_to_bv(exp_tags[s])), (seed, k, t, s)
+    assert info["searched"] == exp["searched"] and info["shared"] == exp["shared"]
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_probe_counts_match_reference_semantics(ctx, seed):
     """N_probes: the instrumented kernel counts exactly the byte tests / lookups the reference does."""
