@@ -209,6 +209,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=500_000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--direct-index", action="store_true", help="disable the L2-blocked insert (A/B)")
+    ap.add_argument("--index-mode", type=int, default=None, help="commet_ctx_binned_index mode (A/B): 0 direct, 1 "
+                    "sorted records (default), 16..30 region passes with 2^mode-byte regions")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -235,7 +237,9 @@ def main():
     ctx = commet_b200.Context(local_rank)
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
     if args.direct_index:
-        ctx.binned_index(False)
+        ctx.binned_index(0)
+    if args.index_mode is not None:
+        ctx.binned_index(args.index_mode)
 
     n, L, k, t = args.reads, args.length, args.k, args.t
     k_arg = k

@@ -204,9 +204,10 @@ class Context:
         """instrumented search: info["tests"], info["lookups"] = the reference's probe counts"""
         self._ck(self.lib.commet_ctx_count_probes(self.handle, int(on)))
 
-    def binned_index(self, on: bool = True):
-        """L2-blocked insert for filters larger than L2 (default on); off = direct RED.OR"""
-        self._ck(self.lib.commet_ctx_binned_index(self.handle, int(on)))
+    def binned_index(self, mode=1):
+        """how filters larger than L2 are fed: 0 direct RED.OR, 1 keys sorted by region first (default), 16..30 region
+        passes with 2^mode-byte regions (commet_ctx_binned_index)"""
+        self._ck(self.lib.commet_ctx_binned_index(self.handle, int(mode)))
 
     @property
     def launches(self) -> int:

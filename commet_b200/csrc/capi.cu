@@ -60,6 +60,8 @@ struct commet_ctx {
     uint64_t launches = 0;
     bool count_probes = false;        // instrumented search kernel (reference-semantics probe counts)
     bool binned_index = true;         // L2-blocked insert for DRAM-resident filters
+    bool region_passes = false;       // ... by region passes over the stream (false, default: sort keys by region first)
+    int region_log2 = 26;             // bytes of filter one pass covers
     uint32_t *recs = nullptr;         // region-sorted key records of the L2-blocked insert
     uint64_t recs_cap = 0;            // capacity in records
     unsigned long long *bins = nullptr;   // hist[512] | base[513] | cursor[512] | tile counter
@@ -185,7 +187,14 @@ extern "C" int commet_ctx_sync(commet_ctx *c)
 
 extern "C" void *commet_ctx_stream(commet_ctx *c) { return (void *)c->stream; }
 extern "C" int commet_ctx_count_probes(commet_ctx *c, int on) { c->count_probes = on != 0; return 0; }
-extern "C" int commet_ctx_binned_index(commet_ctx *c, int on) { c->binned_index = on != 0; return 0; }
+extern "C" int commet_ctx_binned_index(commet_ctx *c, int on)
+{
+    // 0: direct RED.OR; 1: keys sorted by region first (default); 16..30: region passes with 2^on-byte regions
+    c->binned_index = on != 0;
+    c->region_passes = on >= 16 && on <= 30;
+    if (c->region_passes) c->region_log2 = on;
+    return 0;
+}
 extern "C" uint64_t commet_ctx_launches(commet_ctx *c) { return c->launches; }
 
 extern "C" void *commet_host_alloc(size_t bytes)
@@ -559,7 +568,14 @@ static int index_range_binned(commet_ctx *c, commet_reads *r, uint64_t b0, uint6
         uint64_t n_tiles = (((s1 + 31) >> 5) - (s0 >> 5) + kScatTileWords - 1) / kScatTileWords;
         unsigned gs = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * 2);
         k_bin_scatter<<<gs, kScatThreads, sizeof(ScatterSmem), c->stream>>>(r->planes, s0, s1, k, n_bins, cursor, c->recs);
-        k_bin_apply<<<c->sm_count * 8, 256, 0, c->stream>>>(c->filter, c->recs, base, n_bins, tile_counter);
+        {
+            int tile = 4096, bps = 8;
+            if (const char *e = getenv("COMMET_B200_APPLY_TILE")) tile = atoi(e);
+            if (const char *e = getenv("COMMET_B200_APPLY_BPS")) bps = atoi(e);
+            if (tile == 8192) k_bin_apply<8192><<<c->sm_count * bps, 256, 0, c->stream>>>(c->filter, c->recs, base, n_bins, tile_counter);
+            else if (tile == 2048) k_bin_apply<2048><<<c->sm_count * bps, 256, 0, c->stream>>>(c->filter, c->recs, base, n_bins, tile_counter);
+            else k_bin_apply<4096><<<c->sm_count * bps, 256, 0, c->stream>>>(c->filter, c->recs, base, n_bins, tile_counter);
+        }
         c->launches += 4;
         CK(cudaGetLastError());
     }
@@ -580,7 +596,14 @@ static int index_range(commet_ctx *c, commet_reads *r, uint64_t first, uint64_t 
         CK(cudaStreamSynchronize(c->stream));
     }
     if (hb[1] <= hb[0]) return 0;
-    // filters larger than L2 (k >= 28: > 64 MiB) take the L2-blocked path
+    // filters larger than L2 (k >= 28: > 64 MiB): region passes (default) or the sort-based L2-blocked path
+    if (c->binned_index && c->region_passes && c->k >= 28 && c->k - 1 - c->region_log2 >= 1 && c->k - 1 - c->region_log2 <= 10) {
+        const int R = c->k - 1 - c->region_log2;            // region = 2^region_log2 bytes = top R key bits
+        k_index_regions<<<c->sm_count * 8, 256, 0, c->stream>>>(c->filter, r->planes, hb[0], hb[1], c->k, R);
+        c->launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
     if (c->binned_index && c->k >= 28 && c->k - kRecKeyBits <= 9) {
         int rc = index_range_binned(c, r, hb[0], hb[1], kmers_hint);
         if (rc <= 0) return rc;

@@ -238,7 +238,6 @@ constexpr int kScatThreads = 512;
 constexpr int kScatIters = 4;                                      // 32-position words per warp per tile
 constexpr int kScatTileWords = (kScatThreads / 32) * kScatIters;   // 64 words = 2048 stream positions
 constexpr int kScatTileRecs = kScatTileWords * 32 * 4;             // <= 8192 records per tile
-constexpr int kApplyTileRecs = 4096;
 
 __device__ __forceinline__ uint64_t ld_policy_evict_first()
 {
@@ -436,58 +435,154 @@ k_bin_scatter(const uint4 *__restrict__ planes, uint64_t b0, uint64_t b1, int k,
 
 // Tiles of region-sorted records are taken in order from a global counter, so at any time the running
 // blocks touch one or two regions: the RED.OR hit L2.  The next tile is claimed while the current one is
-// processed, and every thread has its four 16-byte record loads in flight before the first RED.
+// processed (the claimer also looks up the region of the tile's first record, once per tile instead of a
+// binary search per thread), and every thread has its 16-byte record loads in flight before the first RED.
+template <int TILE>
 __global__ void __launch_bounds__(256)
 k_bin_apply(uint32_t *__restrict__ filter, const uint32_t *__restrict__ recs,
             const unsigned long long *__restrict__ base, int n_bins,
             unsigned long long *__restrict__ tile_counter)
 {
+    constexpr int U = TILE / (256 * 4);                    // 16-byte loads per thread per tile
     __shared__ unsigned long long sbase[kMaxBins + 1];
     __shared__ unsigned long long s_next;
+    __shared__ int s_bin;
     for (int i = threadIdx.x; i <= n_bins; i += blockDim.x) sbase[i] = base[i];
-    if (threadIdx.x == 0) s_next = atomicAdd(tile_counter, 1ull);
     __syncthreads();
     const unsigned long long total = sbase[n_bins];
-    const unsigned long long n_tiles = (total + kApplyTileRecs - 1) / kApplyTileRecs;
+    const unsigned long long n_tiles = (total + TILE - 1) / TILE;
     const uint64_t pol = ld_policy_evict_first();
+    auto bin_of = [&](unsigned long long first) {           // last region with base <= first
+        int lo = 0, hi = n_bins - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (sbase[mid] <= first) lo = mid; else hi = mid - 1;
+        }
+        return lo;
+    };
+    if (threadIdx.x == 0) {
+        unsigned long long tl = atomicAdd(tile_counter, 1ull);
+        s_next = tl;
+        s_bin = tl < n_tiles ? bin_of(tl * TILE) : 0;
+    }
+    __syncthreads();
     unsigned long long tl = s_next;
+    int bin0 = s_bin;
     while (tl < n_tiles) {
-        __syncthreads();                                   // everybody holds `tl`: s_next may be overwritten
+        __syncthreads();                                   // everybody holds tl/bin0: the slots may be overwritten
         unsigned long long nxt = 0;
         if (threadIdx.x == 0) nxt = atomicAdd(tile_counter, 1ull);      // consumed after this tile
-        const unsigned long long t0 = tl * kApplyTileRecs;
-        uint4 v[kApplyTileRecs / (256 * 4)];
-        unsigned long long idx[kApplyTileRecs / (256 * 4)];
+        const unsigned long long t0 = tl * TILE;
+        uint4 v[U];
 #pragma unroll
-        for (int it = 0; it < kApplyTileRecs / (256 * 4); it++) {
-            idx[it] = t0 + ((unsigned long long)it * 256 + threadIdx.x) * 4;
+        for (int it = 0; it < U; it++) {
+            unsigned long long idx = t0 + ((unsigned long long)it * 256 + threadIdx.x) * 4;
             v[it] = make_uint4(0u, 0u, 0u, 0u);
-            if (idx[it] < total) v[it] = ld_stream_u4(reinterpret_cast<const uint4 *>(recs + idx[it]), pol);   // recs is padded to 16 B
+            if (idx < total) v[it] = ld_stream_u4(reinterpret_cast<const uint4 *>(recs + idx), pol);   // recs is padded to 16 B
         }
+        int bin = bin0;
+        unsigned long long lim = sbase[bin + 1];
 #pragma unroll
-        for (int it = 0; it < kApplyTileRecs / (256 * 4); it++) {
-            if (idx[it] >= total) continue;
-            int lo = 0, hi = n_bins - 1;                   // last region with base <= idx
-            while (lo < hi) {
-                int mid = (lo + hi + 1) >> 1;
-                if (sbase[mid] <= idx[it]) lo = mid; else hi = mid - 1;
-            }
-            int bin = lo;
-            unsigned long long lim = sbase[bin + 1];
+        for (int it = 0; it < U; it++) {
+            unsigned long long idx = t0 + ((unsigned long long)it * 256 + threadIdx.x) * 4;
             uint32_t r[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                unsigned long long i = idx[it] + e;
+                unsigned long long i = idx + e;
                 if (i >= total) break;
-                while (i >= lim) lim = sbase[++bin + 1];
+                while (i >= lim) lim = sbase[++bin + 1];   // a tile rarely spans more than two regions
                 uint32_t key_low = r[e] & kRecMask;
                 uint64_t word = ((uint64_t)bin << (kRegionLog2 - 2)) + (key_low >> 3);
                 atomicOr(filter + word, key_bit((uint64_t)key_low, (int)(r[e] >> kRecKeyBits)));
             }
         }
-        if (threadIdx.x == 0) s_next = nxt;
+        if (threadIdx.x == 0) {
+            s_next = nxt;
+            s_bin = nxt < n_tiles ? bin_of(nxt * TILE) : 0;
+        }
         __syncthreads();
         tl = s_next;
+        bin0 = s_bin;
+    }
+}
+
+// --------------------------------- stage 1, region-pass variant (no sort) ----
+// The region of a key is its TOP bits = the k-mer's FIRST R bases, so "which k-mers of this 32-position
+// word fall into region r" is a bit-parallel pattern match on the plane words: R funnel-shift + LOP3 pairs
+// per key type, no key is built for the (2^R - 1)/2^R positions that miss.  The insert is then a sequence
+// of 2^R passes over the stream, pass r inserting only the keys of region r (2^(k-1-R) bytes, L2-sized):
+// every RED.OR hits L2, each key is still inserted exactly once, and there is no record buffer, no
+// histogram and no scatter.  Work items are (region, tile) pairs taken region-major, so the blocks running
+// at any time touch one or two regions.  Plane words are streamed with an evict-first policy so they do
+// not push the region out of L2.
+// MEASURED (profiles/r01_region_pass_diag.txt, C2): not the default.  The scan alone costs 0.53 ms per pass
+// (35 ms for the 64 passes of k=33), and blocks drift by more than one pass, so two or three regions are
+// live at once and the RED.OR fall back to DRAM rate: 104 ms against 32 ms for the sorted path.
+constexpr int kPassTileWords = 256;                 // one 32-position word per thread per item
+
+__device__ __forceinline__ uint4 ld_planes_stream(const uint4 *p, uint64_t pol)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+
+// positions s (bit s of the result) of this word whose first R bases spell region r in plane x:
+// base s+i must equal bit R-1-i of r (first base most significant, hash_key.h:65-91)
+__device__ __forceinline__ uint32_t match_region(uint32_t x0, uint32_t x1, uint32_t r, int R, uint32_t m)
+{
+    for (int i = 0; i < R; i++) {
+        uint32_t inv = ((r >> (R - 1 - i)) & 1u) ? 0u : ~0u;
+        m &= __funnelshift_r(x0, x1, i) ^ inv;
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(256)
+k_index_regions(uint32_t *__restrict__ filter, const uint4 *__restrict__ planes, uint64_t b0, uint64_t b1,
+                int k, int R)
+{
+    const uint64_t pol = ld_policy_evict_first();
+    const uint64_t w_first = b0 >> 5, w_end = (b1 + 31) >> 5;
+    const uint64_t n_tiles = (w_end - w_first + kPassTileWords - 1) / kPassTileWords;
+    const int low_bits = k - R;                              // key bits below the region bits (<= 32)
+    const uint32_t low_mask = low_bits >= 32 ? ~0u : ((1u << low_bits) - 1u);
+    // items (region r, tile) are taken region-major by block index: item = r * n_tiles + tile
+    uint32_t r = (uint32_t)(blockIdx.x / n_tiles);
+    uint64_t tile = blockIdx.x % n_tiles;
+    for (; r < (1u << R); ) {
+        const uint64_t wi = w_first + tile * kPassTileWords + threadIdx.x;
+        tile += gridDim.x;
+        const uint32_t r_now = r;
+        while (tile >= n_tiles) { tile -= n_tiles; r++; }
+        if (wi >= w_end) continue;
+        uint4 q0 = ld_planes_stream(planes + wi, pol);
+        uint32_t W = w_in_range(q0.w, wi, b0, b1);
+        if (W == 0) continue;
+        uint4 q1 = ld_planes_stream(planes + wi + 1, pol);
+        // key types a, b, c, d = planes H, L, H^L, H|L
+        uint32_t x0[4] = {q0.x, q0.y, q0.x ^ q0.y, q0.x | q0.y};
+        uint32_t x1[4] = {q1.x, q1.y, q1.x ^ q1.y, q1.x | q1.y};
+        uint32_t M[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) M[j] = match_region(x0[j], x1[j], r_now, R, W);
+        if ((M[0] | M[1] | M[2] | M[3]) == 0) continue;
+        uint4 q2 = ld_planes_stream(planes + wi + 2, pol);
+        uint32_t x2[4] = {q2.x, q2.y, q2.x ^ q2.y, q2.x | q2.y};
+        uint32_t *region = filter + ((uint64_t)r_now << (low_bits - 3));
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t m = M[j];
+            while (m) {
+                uint32_t sbit = __ffs(m) - 1;
+                m &= m - 1;
+                // low key bits = bases s+R .. s+k-1, last base least significant
+                uint64_t w64 = window64(x0[j], x1[j], x2[j], sbit);
+                uint32_t low = (__brev((uint32_t)(w64 >> R)) >> (32 - low_bits)) & low_mask;
+                atomicOr(region + (low >> 3), key_bit((uint64_t)low, j));
+            }
+        }
     }
 }
 

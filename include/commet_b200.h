@@ -48,8 +48,12 @@ void *commet_ctx_stream(commet_ctx *ctx);
 /* on != 0: search kernels also count the filter byte tests and k-mer lookups the REFERENCE would perform
  * (stats[5], stats[6] of commet_index_and_search*); a slightly slower instrumented kernel. */
 int commet_ctx_count_probes(commet_ctx *ctx, int on);
-/* on == 0: always insert with direct RED.OR into the filter; default on: filters larger than L2 (k >= 28) are
- * fed through the L2-blocked path (keys partitioned by 32 MiB filter region first).  Same filter bits. */
+/* How filters larger than L2 (k >= 28) are fed; the filter bits are the same in every mode.
+ *   0: direct RED.OR into the DRAM-resident filter
+ *   1: (default) keys partitioned (sorted) by 32 MiB filter region into a record buffer, then applied region by
+ *      region so that every RED.OR hits L2
+ *   16..30: region passes: 2^R passes over the stream, pass r inserting only the keys of the r-th 2^mode-byte
+ *      region (region membership = bit-parallel match on the first R bases); measured slower, kept for A/B */
 int commet_ctx_binned_index(commet_ctx *ctx, int on);
 /* number of kernels launched by this context since creation */
 uint64_t commet_ctx_launches(commet_ctx *ctx);

@@ -50,10 +50,14 @@ def test_index_filter_bit_exact(ctx, k, dirt):
 
 
 @pytest.mark.parametrize("k,budget", [(28, None), (29, None), (31, None), (28, "5000"), (30, "100000")])
-def test_index_l2_blocked_path_bit_exact(ctx, k, budget, monkeypatch):
-    """Filters larger than L2 go through the region-partitioned insert: same bits as the oracle, also when the
-    record buffer forces several sub-ranges, and the same bits as the direct RED.OR path."""
+@pytest.mark.parametrize("mode", [1, 26, 22])
+def test_index_l2_blocked_path_bit_exact(ctx, k, budget, mode, monkeypatch):
+    """Filters larger than L2 are fed region by region -- by sorting key records by region first (mode 1, also
+    when the record buffer forces several sub-ranges) or by region passes over the stream (modes 26 and 22 = 64 MiB
+    and 4 MiB regions, i.e. few and many passes): same bits as the oracle and as the direct RED.OR path."""
     if budget:
+        if mode != 1:
+            pytest.skip("the record budget only concerns the sorted path")
         monkeypatch.setenv("COMMET_B200_RECS_BUDGET", budget)
     rng = np.random.default_rng(k)
     reads = H.make_ref_set(rng, 4000, 20, 150, **DIRT[k % 3])
@@ -61,18 +65,19 @@ def test_index_l2_blocked_path_bit_exact(ctx, k, budget, monkeypatch):
     stream = H.to_stream(reads)
     rs = ctx.stage(*stream)
     exp = oracle_filter(k, stream)
-    ctx.binned_index(True)
-    ctx.index_reads(rs, k)
-    got = ctx.filter_download(k)
-    assert np.array_equal(got, exp)
-    ctx.binned_index(False)
     try:
+        ctx.binned_index(mode)
+        ctx.index_reads(rs, k)
+        got = ctx.filter_download(k)
+        assert np.array_equal(got, exp)
+        ctx.binned_index(0)
         ctx.index_reads(rs, k, 5, 3000)
         direct = ctx.filter_download(k)
+        ctx.binned_index(mode)
+        ctx.index_reads(rs, k, 5, 3000)
+        assert np.array_equal(ctx.filter_download(k), direct)
     finally:
-        ctx.binned_index(True)
-    ctx.index_reads(rs, k, 5, 3000)
-    assert np.array_equal(ctx.filter_download(k), direct)
+        ctx.binned_index(1)
 
 
 @pytest.mark.parametrize("k", [3, 9, 12, 17, 21])
