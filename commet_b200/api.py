@@ -73,6 +73,8 @@ _SIGS = {
                                       C.c_int64, C.c_void_p, C.c_void_p]),
     "commet_filter_reads_staged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_int64,
                                              C.c_void_p, C.c_void_p]),
+    "commet_filter_reads_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_float,
+                                          C.c_int64, C.c_void_p, C.c_void_p]),
     "commet_bvop": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "commet_bv_popcount": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, _u64p]),
     "commet_bvop_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -365,6 +367,14 @@ class Context:
         cnt = np.zeros(4, dtype=np.uint64)
         self._ck(self.lib.commet_filter_reads_staged(self.handle, reads.handle, min_len, max_N, C.c_float(min_shannon),
                                                      max_reads, _ptr(d_bv), _ptr(cnt)))
+        return dict(rm_length=int(cnt[0]), rm_N=int(cnt[1]), rm_shannon=int(cnt[2]), selected=int(cnt[3]))
+
+    def filter_reads_device(self, d_bases: int, d_offs: int, n_reads: int, d_bv: int, min_len=0, max_N=-1, min_shannon=0.0,
+                            max_reads=-1):
+        """the selection fused into the staging pass, on ASCII bases already resident on the device"""
+        cnt = np.zeros(4, dtype=np.uint64)
+        self._ck(self.lib.commet_filter_reads_dev(self.handle, _ptr(d_bases), _ptr(d_offs), n_reads, min_len, max_N,
+                                                  C.c_float(min_shannon), max_reads, _ptr(d_bv), _ptr(cnt)))
         return dict(rm_length=int(cnt[0]), rm_N=int(cnt[1]), rm_shannon=int(cnt[2]), selected=int(cnt[3]))
 
     # -- stage 4 --------------------------------------------------------------

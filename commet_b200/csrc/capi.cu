@@ -362,12 +362,24 @@ extern "C" int commet_reads_from_device(commet_ctx *c, const uint8_t *d_bases, c
     commet_reads *r = nullptr;
     CKR(reads_alloc(c, n_reads, n_bases, &r));
     CK(cudaMemcpyAsync(r->offs, d_offs, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
-    uint64_t padded = r->n_words * 32;
     int rc = 0;
-    if (padded == n_bases && ((uintptr_t)d_bases & 15) == 0) {
-        rc = launch_encode(c, d_bases, r, 0, r->n_words);   // already vector-aligned: encode in place
+    if (((uintptr_t)d_bases & 15) == 0) {
+        // vector-aligned: whole 32-base words are encoded where they lie; a ragged last word goes through a
+        // zero-padded 32-byte scratch
+        const uint64_t full = n_bases / 32;
+        rc = launch_encode(c, d_bases, r, 0, full);
+        if (rc == 0 && full < r->n_words) {
+            DevBuf tail(c);
+            if (tail.alloc(32) != cudaSuccess) { commet_reads_free(r); return fail("staging allocation failed"); }
+            CK(cudaMemsetAsync(tail.p, 0, 32, c->stream));
+            CK(cudaMemcpyAsync(tail.p, d_bases + full * 32, n_bases - full * 32, cudaMemcpyDeviceToDevice, c->stream));
+            k_encode<<<1, 32, 0, c->stream>>>(tail.as<uint4>(), r->planes + full, 1);
+            c->launches++;
+            CK(cudaGetLastError());
+        }
         if (rc == 0) CK(cudaStreamSynchronize(c->stream));
     } else {
+        uint64_t padded = r->n_words * 32;
         DevBuf ascii(c);
         if (ascii.alloc(padded) != cudaSuccess) { commet_reads_free(r); return fail("staging allocation failed"); }
         CK(cudaMemsetAsync(ascii.as<uint8_t>() + n_bases, 0, padded - n_bases, c->stream));
@@ -1009,12 +1021,12 @@ static float shannon_from_counts(const unsigned int cnt[5], unsigned int len)
     return fabsf(index);
 }
 
-extern "C" int commet_filter_reads_staged(commet_ctx *c, commet_reads *r, int64_t min_len, int64_t max_N,
-                                          float min_shannon, int64_t max_reads, uint32_t *d_bv, uint64_t *counters)
+// Shared tail of the two filter kernels: `launch` runs k_filter (bit-planes) or k_filter_ascii (fused with the
+// staging pass); then the undecided reads are settled, the -m cutoff located and the counters fetched.
+template <class Launch>
+static int filter_run(commet_ctx *c, uint64_t n, int64_t min_len, int64_t max_N, float min_shannon, int64_t max_reads,
+                      uint32_t *d_bv, uint64_t *counters, Launch launch)
 {
-    CKR(set_device(c));
-    CKR(flush_encode(c, r));
-    uint64_t n = r->n_reads;
     uint64_t n_bv_words = tag_words(n);
     uint64_t n_blocks = std::max<uint64_t>((std::max(n, n_bv_words * 32) + kFilterBlock - 1) / kFilterBlock, 1);
     if (n_blocks > 0x7fffffffull) return fail("too many reads for one filter call");
@@ -1033,9 +1045,8 @@ extern "C" int commet_filter_reads_staged(commet_ctx *c, commet_reads *r, int64_
     // class bytes are needed to locate a -m cutoff and to patch undecided reads' totals
     if (classes.alloc(n ? n : 1) != cudaSuccess) return fail("filter class allocation failed");
     CK(cudaMemsetAsync(nb.p, 0, sizeof(unsigned int), c->stream));
-    k_filter<<<(unsigned)n_blocks, kFilterBlock, 0, c->stream>>>(r->planes, r->offs, n, fp, d_bv, n_bv_words,
-                                                                 classes.as<uint8_t>(), totals.as<unsigned int>(),
-                                                                 border.as<BorderRec>(), border_cap, nb.as<unsigned int>());
+    launch((unsigned)n_blocks, fp, n_bv_words, classes.as<uint8_t>(), totals.as<unsigned int>(), border.as<BorderRec>(),
+           border_cap, nb.as<unsigned int>());
     c->launches++;
     CK(cudaGetLastError());
     unsigned int n_border = 0;
@@ -1076,22 +1087,55 @@ extern "C" int commet_filter_reads_staged(commet_ctx *c, commet_reads *r, int64_
     return 0;
 }
 
+extern "C" int commet_filter_reads_staged(commet_ctx *c, commet_reads *r, int64_t min_len, int64_t max_N,
+                                          float min_shannon, int64_t max_reads, uint32_t *d_bv, uint64_t *counters)
+{
+    CKR(set_device(c));
+    CKR(flush_encode(c, r));
+    const uint64_t n = r->n_reads;
+    return filter_run(c, n, min_len, max_N, min_shannon, max_reads, d_bv, counters,
+                      [&](unsigned n_blocks, const FilterParams &fp, uint64_t n_bv_words, uint8_t *classes, unsigned int *totals,
+                          BorderRec *border, unsigned int border_cap, unsigned int *nb) {
+                          k_filter<<<n_blocks, kFilterBlock, 0, c->stream>>>(r->planes, r->offs, n, fp, d_bv, n_bv_words, classes,
+                                                                             totals, border, border_cap, nb);
+                      });
+}
+
+extern "C" int commet_filter_reads_dev(commet_ctx *c, const uint8_t *d_bases, const uint64_t *d_offs, uint64_t n_reads,
+                                       int64_t min_len, int64_t max_N, float min_shannon, int64_t max_reads,
+                                       uint32_t *d_bv, uint64_t *counters)
+{
+    CKR(set_device(c));
+    if ((uintptr_t)d_bases & 15) return fail("commet_filter_reads_dev: d_bases must be 16-byte aligned");
+    return filter_run(c, n_reads, min_len, max_N, min_shannon, max_reads, d_bv, counters,
+                      [&](unsigned n_blocks, const FilterParams &fp, uint64_t n_bv_words, uint8_t *classes, unsigned int *totals,
+                          BorderRec *border, unsigned int border_cap, unsigned int *nb) {
+                          k_filter_ascii<<<n_blocks, 256, 0, c->stream>>>(d_bases, d_offs, n_reads, fp, d_bv, n_bv_words, classes,
+                                                                          totals, border, border_cap, nb);
+                      });
+}
+
+// host entry: the bases go H2D and through the fused kernel; no bit-planes are built
 extern "C" int commet_filter_reads(commet_ctx *c, const uint8_t *bases, const uint64_t *offs, uint64_t n_reads,
                                    int64_t min_len, int64_t max_N, float min_shannon, int64_t max_reads, uint8_t *bv,
                                    uint64_t *counters)
 {
     CKR(set_device(c));
-    commet_reads *r = nullptr;
-    CKR(commet_reads_upload(c, bases, offs, n_reads, &r));
-    DevBuf d(c);
+    if (offs[0] != 0) return fail("commet_filter_reads: offs[0] must be 0");
+    const uint64_t n_bases = offs[n_reads], padded = (n_bases + 15) / 16 * 16 + 16;
+    DevBuf d_bases(c), d_offs(c), d(c);
     uint64_t nw = tag_words(n_reads);
-    int rc = 0;
-    if (d.alloc(nw * 4) != cudaSuccess) rc = fail("bv allocation failed");
-    if (rc == 0) rc = commet_filter_reads_staged(c, r, min_len, max_N, min_shannon, max_reads, d.as<uint32_t>(), counters);
-    if (rc == 0 && (cudaMemcpyAsync(bv, d.p, n_reads / 8 + 1, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-                    cudaStreamSynchronize(c->stream) != cudaSuccess)) rc = fail("bv download failed");
-    commet_reads_free(r);
-    return rc;
+    if (d_bases.alloc(padded) != cudaSuccess || d_offs.alloc((n_reads + 1) * sizeof(uint64_t)) != cudaSuccess ||
+        d.alloc(nw * 4) != cudaSuccess)
+        return fail("filter_reads: device allocation for %llu bases failed", (unsigned long long)n_bases);
+    CK(cudaMemsetAsync(d_bases.as<uint8_t>() + (padded - 32), 0, 32, c->stream));
+    if (n_bases) CK(cudaMemcpyAsync(d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_offs.p, offs, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    CKR(commet_filter_reads_dev(c, d_bases.as<uint8_t>(), d_offs.as<uint64_t>(), n_reads, min_len, max_N, min_shannon,
+                                max_reads, d.as<uint32_t>(), counters));
+    CK(cudaMemcpyAsync(bv, d.p, n_reads / 8 + 1, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
 // ----------------------------------------------------------- stage 4: bvop --

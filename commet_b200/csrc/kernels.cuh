@@ -771,19 +771,41 @@ __device__ __forceinline__ float shannon_dev(const unsigned int cnt[5], unsigned
     return fabsf(idx);
 }
 
+// single-precision estimate of the same index (MUFU.LG2): within 1e-5 of the reference's value, used to
+// settle the reads that are nowhere near the threshold without the five double-precision logarithms
+__device__ __forceinline__ float shannon_fast(const unsigned int cnt[5], unsigned int len)
+{
+    float idx = 0.f;
+    const float inv = __frcp_rn((float)len);
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        float f = (float)cnt[j] * inv;
+        if (cnt[j]) idx = fmaf(f, __log2f(f), idx);
+    }
+    return fabsf(idx);
+}
+
+// the N and Shannon tests on a read's base counts (the length test comes first, filter_reads.cpp:189)
+__device__ __forceinline__ int classify_counts(long long len, const unsigned int cnt[5], const FilterParams &fp)
+{
+    if ((long long)cnt[4] > fp.max_N) return 2;           // :192
+    if (fp.min_shannon > 0.f) {                           // fabs() >= 0: e <= 0 never drops
+        float hf = shannon_fast(cnt, (unsigned int)len);
+        if (fabsf(hf - fp.min_shannon) > 1e-3f) return hf < fp.min_shannon ? 3 : 0;      // :195, decided 100x outside the error
+        float h = shannon_dev(cnt, (unsigned int)len);
+        if (fabsf(h - fp.min_shannon) <= fp.margin) return 4;
+        if (h < fp.min_shannon) return 3;                 // :195
+    }
+    return 0;
+}
+
 __device__ __forceinline__ int classify_read(const uint4 *__restrict__ planes, uint64_t o, uint64_t e,
                                              const FilterParams &fp, unsigned int cnt[5])
 {
     long long len = (long long)(e - o);
     if (len < fp.min_len) return 1;                       // filter_reads.cpp:189
     base_counts(planes, o, e, cnt);
-    if ((long long)cnt[4] > fp.max_N) return 2;           // :192
-    if (fp.min_shannon > 0.f) {                           // fabs() >= 0: e <= 0 never drops
-        float h = shannon_dev(cnt, (unsigned int)len);
-        if (fabsf(h - fp.min_shannon) <= fp.margin) return 4;
-        if (h < fp.min_shannon) return 3;                 // :195
-    }
-    return 0;
+    return classify_counts(len, cnt, fp);
 }
 
 // One block = 1024 consecutive reads.  Writes the selection bits (ballot,
@@ -827,6 +849,139 @@ k_filter(const uint4 *__restrict__ planes, const uint64_t *__restrict__ offs, ui
         uint32_t mc = __ballot_sync(0xffffffffu, cls == (c == 3 ? 0 : c + 1));
         if ((threadIdx.x & 31) == 0 && mc) atomicAdd(&tot[c], __popc(mc));
     }
+    __syncthreads();
+    if (threadIdx.x < 4) block_totals[4 * (uint64_t)blockIdx.x + threadIdx.x] = tot[threadIdx.x];
+}
+
+// The same selection FUSED INTO THE READ-STAGING PASS (north_star stage 3): the ASCII bases are read once
+// with 16-byte vector loads and nothing but the selection bits is written -- no bit-planes.  A group of 8
+// lanes owns one read (8 x 16 B = 128 B per step, the common read length), so a warp works on 4 reads at a
+// time and on 128 consecutive reads (4 words of the bit vector) in all; a block covers the same 1024 reads
+// as k_filter and produces the same outputs (bits, class bytes, block totals, undecided records).
+// `bases` must be 16-byte aligned and readable up to the next multiple of 16 bytes.
+__device__ __forceinline__ unsigned long long count_acgt16(uint4 v, uint32_t valid)   // valid: bit i = byte i counts
+{
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t m = (valid >> (4 * i)) & 0xFu;
+        uint32_t bm = (m & 1u) | ((m & 2u) << 7) | ((m & 4u) << 14) | ((m & 8u) << 21);     // 0x01 per valid byte
+        uint32_t x = w[i] | 0x20202020u;                                                    // fold case
+        acc += (unsigned long long)__popc(__vcmpeq4(x, 0x61616161u) & bm)
+             | ((unsigned long long)__popc(__vcmpeq4(x, 0x63636363u) & bm) << 16)
+             | ((unsigned long long)__popc(__vcmpeq4(x, 0x67676767u) & bm) << 32)
+             | ((unsigned long long)__popc(__vcmpeq4(x, 0x74747474u) & bm) << 48);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(256, 4)
+k_filter_ascii(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offs, uint64_t n_reads,
+               FilterParams fp, uint32_t *__restrict__ bv, uint64_t n_bv_words, uint8_t *__restrict__ classes,
+               unsigned int *__restrict__ block_totals, BorderRec *__restrict__ border,
+               unsigned int border_cap, unsigned int *__restrict__ n_border)
+{
+    __shared__ unsigned int tot[4];
+    if (threadIdx.x < 4) tot[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, gl = lane & 7;
+    const uint32_t gmask = 0xFFu << (8 * grp);
+    const uint64_t r0 = (uint64_t)blockIdx.x * kFilterBlock + (uint64_t)warp * 128;
+    unsigned int wtot[4] = {0, 0, 0, 0};                      // rm_len, rm_N, rm_shannon, selected (lane 0)
+    // lane i owns read rbase + i: its offsets (coalesced, fetched one word of the bit vector ahead), its class, its bit
+    uint64_t nx_o = 0, nx_e = 0;
+    if (r0 + lane < n_reads) { nx_o = offs[r0 + lane]; nx_e = offs[r0 + lane + 1]; }
+    for (int j = 0; j < 4; j++) {
+        const uint64_t my_r = r0 + 32 * j + lane;
+        const uint64_t my_o = nx_o, my_e = nx_e;
+        nx_o = nx_e = 0;
+        if (j < 3 && my_r + 32 < n_reads) { nx_o = offs[my_r + 32]; nx_e = offs[my_r + 33]; }
+        unsigned int mine[4] = {0, 0, 0, 0};
+        // counting: 4 double steps; in each a group of 8 lanes sweeps two reads, 128 bytes at a time, with the first
+        // 16-byte load of both reads in flight before either is counted
+        for (int it2 = 0; it2 < 4; it2++) {
+            uint64_t o[2], e[2], c0[2];
+            bool act[2];
+            uint4 v[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int src = 8 * it2 + 4 * u + grp;
+                o[u] = __shfl_sync(0xffffffffu, my_o, src);
+                e[u] = __shfl_sync(0xffffffffu, my_e, src);
+                act[u] = (long long)(e[u] - o[u]) >= fp.min_len && e[u] > o[u];      // uniform inside the group only
+                c0[u] = (o[u] & ~15ull) + 16 * gl;
+                v[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (act[u] && c0[u] < e[u]) v[u] = ld_nc_u4(reinterpret_cast<const uint4 *>(bases + c0[u]));
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                unsigned int cnt[4] = {0, 0, 0, 0};
+                if (act[u]) {
+                    unsigned long long acc = 0;                      // four 16-bit counters, flushed before overflow
+                    int pending = 0;
+                    for (uint64_t c = c0[u]; c < e[u]; c += 128) {
+                        uint4 x = c == c0[u] ? v[u] : ld_nc_u4(reinterpret_cast<const uint4 *>(bases + c));
+                        uint32_t valid = 0xFFFFu;
+                        if (c < o[u]) valid &= 0xFFFFu << (o[u] - c);
+                        if (c + 16 > e[u]) valid &= 0xFFFFu >> (c + 16 - e[u]);
+                        acc += count_acgt16(x, valid);
+                        if (++pending == 4000) {
+                            for (int q = 0; q < 4; q++) cnt[q] += (unsigned int)((acc >> (16 * q)) & 0xFFFFu);
+                            acc = 0;
+                            pending = 0;
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {                    // the reduction names the group's own lanes only
+                        cnt[q] += (unsigned int)((acc >> (16 * q)) & 0xFFFFu);
+                        cnt[q] += __shfl_xor_sync(gmask, cnt[q], 1);
+                        cnt[q] += __shfl_xor_sync(gmask, cnt[q], 2);
+                        cnt[q] += __shfl_xor_sync(gmask, cnt[q], 4);
+                    }
+                }
+                __syncwarp();
+                // hand the counts of read 8*it2 + 4*u + g to its owner lane
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    unsigned int t = __shfl_sync(0xffffffffu, cnt[q], 8 * (lane & 3));
+                    if ((int)(lane >> 2) == 2 * it2 + u) mine[q] = t;
+                }
+            }
+        }
+        // classification: one read per lane (the Shannon term is the expensive part; all 32 lanes work)
+        int cls = -1;
+        if (my_r < n_reads) {
+            const long long len = (long long)(my_e - my_o);
+            if (len < fp.min_len) cls = 1;
+            else {
+                unsigned int cnt[5] = {mine[0], mine[1], mine[2], mine[3], 0};
+                cnt[4] = (unsigned int)len - (cnt[0] + cnt[1] + cnt[2] + cnt[3]);
+                cls = classify_counts(len, cnt, fp);
+                if (cls == 4) {
+                    unsigned int slot = atomicAdd(n_border, 1u);
+                    if (slot < border_cap) {
+                        BorderRec br;
+                        br.read = my_r;
+                        for (int q = 0; q < 5; q++) br.cnt[q] = cnt[q];
+                        br.len = (unsigned int)len;
+                        border[slot] = br;
+                    }
+                    cls = 0;    // provisional; the host patches classes/bits/totals
+                }
+            }
+            if (classes) classes[my_r] = (uint8_t)cls;
+        }
+        __syncwarp();
+        const uint32_t sel = __ballot_sync(0xffffffffu, cls == 0);
+        const uint64_t word = (r0 >> 5) + j;
+        if (lane == 0 && word < n_bv_words) bv[word] = sel;         // padding bits stay 0
+        wtot[3] += __popc(sel);
+#pragma unroll
+        for (int q = 1; q <= 3; q++) wtot[q - 1] += __popc(__ballot_sync(0xffffffffu, cls == q));
+    }
+    if (lane == 0)
+        for (int q = 0; q < 4; q++) if (wtot[q]) atomicAdd(&tot[q], wtot[q]);
     __syncthreads();
     if (threadIdx.x < 4) block_totals[4 * (uint64_t)blockIdx.x + threadIdx.x] = tot[threadIdx.x];
 }

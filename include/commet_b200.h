@@ -179,6 +179,12 @@ int commet_filter_reads(commet_ctx *ctx, const uint8_t *bases, const uint64_t *o
 int commet_filter_reads_staged(commet_ctx *ctx, commet_reads *r, int64_t min_len, int64_t max_N,
                                float min_shannon, int64_t max_reads, uint32_t *d_bv,
                                uint64_t *counters);
+/* the selection fused into the staging pass: ASCII bases already on the device are read once (16-byte vector
+ * loads) and only the selection bits are written.  d_bases: 16-byte aligned, readable up to the next multiple of
+ * 16 bytes; d_bv: ceil((n_reads/8+1)/4) u32 words.  commet_filter_reads is this after an H2D copy. */
+int commet_filter_reads_dev(commet_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offs, uint64_t n_reads,
+                            int64_t min_len, int64_t max_N, float min_shannon, int64_t max_reads,
+                            uint32_t *d_bv, uint64_t *counters);
 
 /* ---- stage 4: bvop ------------------------------------------------------------
  * BooleanVector::full_and/or/and_not/not (include/boolean_vector.h:418-462)

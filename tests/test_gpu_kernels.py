@@ -245,9 +245,29 @@ def test_filter_reads(ctx, seed):
     if rng.random() < 0.5: kw["max_reads"] = int(rng.choice([0, 1, n // 3, n, n + 5, 1024, 1023, 1025]))
     stream = H.to_stream(reads)
     exp_bv, exp_cnt = oracle.filter_reads(*stream, **kw)
-    bv, cnt = ctx.filter_reads(*stream, **kw)
+    bv, cnt = ctx.filter_reads(*stream, **kw)               # fused with the staging pass (k_filter_ascii)
     assert cnt == exp_cnt, (seed, kw)
     assert np.array_equal(bv, exp_bv), (seed, kw)
+    import torch                                             # the same selection on an already staged stream (k_filter)
+    rs = ctx.stage(*stream)
+    d_bv = torch.zeros((n // 8 + 1 + 3) // 4, dtype=torch.int32, device="cuda:0")
+    torch.cuda.synchronize()
+    cnt2 = ctx.filter_reads_staged(rs, d_bv.data_ptr(), **kw)
+    assert cnt2 == exp_cnt, (seed, kw)
+    assert np.array_equal(d_bv.cpu().numpy().view(np.uint8)[:n // 8 + 1], exp_bv), (seed, kw)
+    rs.free()
+
+
+def test_filter_reads_long_reads(ctx):
+    """reads far longer than a warp step and than the 16-bit partial counters of the fused kernel"""
+    rng = np.random.default_rng(77)
+    reads = [H.dirty(rng, H.random_read(rng, L), p_N=0.01).tobytes() for L in (70000, 1, 600000, 129, 128, 127, 5000)]
+    reads.append(b"A" * 300000)
+    stream = H.to_stream(reads)
+    for kw in (dict(min_len=100, max_N=800, min_shannon=1.5), dict(max_N=6000), dict(min_shannon=0.5)):
+        exp_bv, exp_cnt = oracle.filter_reads(*stream, **kw)
+        bv, cnt = ctx.filter_reads(*stream, **kw)
+        assert cnt == exp_cnt and np.array_equal(bv, exp_bv), kw
 
 
 @pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 127, 128, 129, 4099, 1_000_003])
