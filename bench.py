@@ -77,26 +77,68 @@ def make_sets_torch(n_reads: int, length: int, seed: int, device, qseed: int | N
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clocks and throttle reasons during the timed region (B200_PROFILING.md), sampled in-process through
+    NVML every 20 ms -- spawning nvidia-smi takes ~100 ms per sample and holds driver locks the timed CUDA calls
+    wait on; nvidia-smi is only the fallback when NVML cannot be loaded."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.rows = []          # (sm_mhz, max_mhz, [active reason names])
+        self.source = "nvml"
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remaps indices: find the device through its PCI bus id
+            import torch
+            bus = getattr(torch.cuda.get_device_properties(index), "pci_bus_id", None)
+            h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if int(pynvml.nvmlDeviceGetPciInfo(hi).bus) == int(bus):
+                        h = hi
+                        break
+            self._h = h if h is not None else pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml = pynvml
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+            self.source = "nvidia-smi"
+
+    def _sample_nvml(self):
+        nv = self._nvml
+        sm = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+        self.rows.append((sm, self._max, [nm for nm, b in zip(self.NAMES, bits) if mask & b]))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        r = [x.strip() for x in out.strip().split(",")]
+        self.rows.append((float(r[0]), float(r[1]), [nm for nm, v in zip(self.NAMES, r[3:7]) if v.lower().startswith("active")]))
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02 if self._nvml is not None else 0.1)
 
     def __enter__(self):
         self._t.start()
@@ -107,18 +149,11 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = [r[0] for r in self.rows]
+        mx = max([r[1] for r in self.rows], default=0)
+        reasons = sorted({nm for r in self.rows for nm in r[2]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
+                "samples": len(sm), "source": self.source}
 
 
 def measured_peaks():

@@ -45,6 +45,86 @@ static int fail(const char *fmt, ...)
         if (rc_ != 0) return rc_;     \
     } while (0)
 
+// ------------------------------------------------------------------ trace ---
+// COMMET_B200_TRACE=1: host wall-clock of the phases of the chunk loop on stderr (where does the HOST spend its
+// time between the launches -- driver calls that block, allocations, syncs)
+#include <chrono>
+namespace {
+struct HostTrace {
+    bool on;
+    std::chrono::steady_clock::time_point t0, last;
+    HostTrace() : on(getenv("COMMET_B200_TRACE") != nullptr) { t0 = last = std::chrono::steady_clock::now(); }
+    void mark(const char *what)
+    {
+        if (!on) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[commet trace] +%8.3f ms (%8.3f) %s\n", std::chrono::duration<double, std::milli>(now - t0).count(),
+                std::chrono::duration<double, std::milli>(now - last).count(), what);
+        last = now;
+    }
+};
+thread_local HostTrace *g_trace = nullptr;
+inline void trace(const char *what) { if (g_trace) g_trace->mark(what); }
+}  // namespace
+
+// ------------------------------------------------------------------ arena ---
+// Device temporaries (ASCII staging, bit-planes, offsets, tags, counts) come from a context-owned cache of
+// cudaMalloc blocks.  Every user of a block touches it on the context's compute stream, or on the copy stream
+// behind an event recorded on the compute stream after the allocation, so handing a freed block to the next
+// owner needs no device synchronisation: stream order already separates the two uses.  Steady-state calls
+// therefore never enter the driver's allocator (cudaMallocAsync was measured to stall the host for 10-60 ms,
+// sometimes 500 ms, when a call re-allocates its gigabyte-sized staging buffers).
+namespace {
+struct Arena {
+    struct Block { void *p; size_t cap; bool used; };
+    std::vector<Block> blocks;
+    static size_t round_up(size_t bytes)
+    {
+        const size_t g = bytes >= (64u << 20) ? (2u << 20) : bytes >= (1u << 20) ? (256u << 10) : 4096;
+        return (std::max<size_t>(bytes, 16) + g - 1) / g * g;
+    }
+    cudaError_t alloc(void **out, size_t bytes)
+    {
+        const size_t want = round_up(bytes);
+        int best = -1;
+        for (size_t i = 0; i < blocks.size(); i++)          // best fit, but never waste more than half a block
+            if (!blocks[i].used && blocks[i].cap >= want && blocks[i].cap <= 2 * want + (1u << 20) &&
+                (best < 0 || blocks[i].cap < blocks[best].cap))
+                best = (int)i;
+        if (best >= 0) {
+            blocks[best].used = true;
+            *out = blocks[best].p;
+            return cudaSuccess;
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {                              // give the cached free blocks back and retry
+            cudaGetLastError();
+            trim();
+            e = cudaMalloc(&p, want);
+            if (e != cudaSuccess) { cudaGetLastError(); return e; }
+        }
+        blocks.push_back({p, want, true});
+        *out = p;
+        return cudaSuccess;
+    }
+    void free(void *p)
+    {
+        for (Block &b : blocks)
+            if (b.p == p) { b.used = false; return; }
+    }
+    void trim()                                              // cudaFree synchronises the device: no block is in flight after it
+    {
+        size_t j = 0;
+        for (size_t i = 0; i < blocks.size(); i++) {
+            if (blocks[i].used) blocks[j++] = blocks[i];
+            else cudaFree(blocks[i].p);
+        }
+        blocks.resize(j);
+    }
+};
+}  // namespace
+
 // ------------------------------------------------------------------ types ---
 struct commet_ctx {
     int device = 0;
@@ -65,6 +145,7 @@ struct commet_ctx {
     uint32_t *recs = nullptr;         // region-sorted key records of the L2-blocked insert
     uint64_t recs_cap = 0;            // capacity in records
     unsigned long long *bins = nullptr;   // hist[512] | base[513] | cursor[512] | tile counter
+    Arena arena;                      // cached device temporaries (see Arena)
 };
 
 struct commet_reads {
@@ -88,13 +169,13 @@ namespace {
 constexpr int kScratch = 256;         // [0,128): 4 counters per query set; [128,256): misc
 constexpr int kMaxSets = 30;
 
-struct DevBuf {                       // scoped, stream-ordered device allocation (cudaMallocAsync pool)
+struct DevBuf {                       // scoped, stream-ordered device temporary from the context's arena
     void *p = nullptr;
-    cudaStream_t st;
-    explicit DevBuf(const commet_ctx *c) : st(c->stream) {}
+    commet_ctx *ctx;
+    explicit DevBuf(commet_ctx *c) : ctx(c) {}
     DevBuf(const DevBuf &) = delete;
-    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
-    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 16, st); }
+    ~DevBuf() { if (p) ctx->arena.free(p); }
+    cudaError_t alloc(size_t bytes) { return ctx->arena.alloc(&p, bytes); }
     template <class T> T *as() { return static_cast<T *>(p); }
 };
 
@@ -151,12 +232,6 @@ extern "C" int commet_ctx_create(int device, commet_ctx **out)
     }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    {   // temporaries come from the stream-ordered pool and stay cached between calls
-        cudaMemPool_t pool;
-        CK(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t keep = UINT64_MAX;
-        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    }
     CK(cudaMalloc(&c->scratch, kScratch * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(c->scratch, 0, kScratch * sizeof(unsigned long long), c->stream));
     *out = c;
@@ -172,6 +247,7 @@ extern "C" void commet_ctx_destroy(commet_ctx *c)
     if (c->scratch) cudaFree(c->scratch);
     if (c->recs) cudaFree(c->recs);
     if (c->bins) cudaFree(c->bins);
+    for (Arena::Block &b : c->arena.blocks) cudaFree(b.p);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
@@ -219,8 +295,8 @@ static int reads_alloc(commet_ctx *c, uint64_t n_reads, uint64_t n_bases, commet
     r->n_reads = n_reads;
     r->n_bases = n_bases;
     r->n_words = (n_bases + 31) / 32;
-    cudaError_t e = cudaMallocAsync(&r->planes, (r->n_words + 4) * sizeof(uint4), c->stream);
-    if (e == cudaSuccess) e = cudaMallocAsync(&r->offs, (n_reads + 1) * sizeof(uint64_t), c->stream);
+    cudaError_t e = c->arena.alloc((void **)&r->planes, (r->n_words + 4) * sizeof(uint4));
+    if (e == cudaSuccess) e = c->arena.alloc((void **)&r->offs, (n_reads + 1) * sizeof(uint64_t));
     if (e != cudaSuccess) {
         commet_reads_free(r);
         return fail("device allocation for %llu bases failed: %s", (unsigned long long)n_bases,
@@ -304,7 +380,7 @@ static int reads_upload_async(commet_ctx *c, const uint8_t *bases, const uint64_
     CKR(reads_alloc(c, n_reads, n_bases, &r));
     r->offs_base = base;
     uint64_t padded = r->n_words * 32;
-    if (cudaMallocAsync(&r->ascii, padded ? padded : 32, c->stream) != cudaSuccess) {
+    if (c->arena.alloc((void **)&r->ascii, padded ? padded : 32) != cudaSuccess) {
         commet_reads_free(r);
         return fail("device allocation of %llu staging bytes failed", (unsigned long long)padded);
     }
@@ -333,7 +409,7 @@ static int flush_encode(commet_ctx *c, commet_reads *r)
         c->ev_pool.push_back(r->chunk_ev[i]);
     }
     r->chunk_ev.clear();
-    CK(cudaFreeAsync(r->ascii, c->stream));
+    c->arena.free(r->ascii);           // the next owner's work is ordered behind the encodes just queued
     r->ascii = nullptr;
     return 0;
 }
@@ -396,14 +472,17 @@ extern "C" void commet_reads_free(commet_reads *r)
 {
     if (!r) return;
     if (r->ctx) cudaSetDevice(r->ctx->device);
-    cudaStream_t st = r->ctx ? r->ctx->stream : nullptr;
     if (r->ascii || !r->chunk_ev.empty()) {         // an upload that was never consumed: let its copies land first
         if (r->ctx) cudaStreamSynchronize(r->ctx->copy_stream);
         for (cudaEvent_t e : r->chunk_ev) { if (r->ctx) r->ctx->ev_pool.push_back(e); else cudaEventDestroy(e); }
-        if (r->ascii) cudaFreeAsync(r->ascii, st);
+        if (r->ascii) {
+            if (r->ctx) r->ctx->arena.free(r->ascii); else cudaFree(r->ascii);
+        }
     }
-    if (r->planes) cudaFreeAsync(r->planes, st);
-    if (r->offs) cudaFreeAsync(r->offs, st);
+    if (r->ctx) {
+        if (r->planes) r->ctx->arena.free(r->planes);
+        if (r->offs) r->ctx->arena.free(r->offs);
+    }
     delete r;
 }
 
@@ -543,20 +622,27 @@ static int index_range_binned(commet_ctx *c, commet_reads *r, uint64_t b0, uint6
     if (!c->bins) {
         CK(cudaMalloc(&c->bins, 2048 * sizeof(unsigned long long)));
         CK(cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+        CK(cudaFuncSetAttribute(k_bin_count<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * 128 + 128) * 4));
     }
     unsigned long long *hist = c->bins, *base = c->bins + 512, *cursor = c->bins + 1100, *tile_counter = c->bins + 1700;
     uint64_t positions = b1 - b0;
     uint64_t kmers = kmers_hint ? std::min(kmers_hint, positions) : positions;
-    // scratch: 4 records of 4 bytes per k-mer; bounded by what the device has free, else sub-ranges
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
-    uint64_t budget = (uint64_t)((free_b + c->recs_cap * 4) * 0.6) / 4;       // records
-    if (const char *e = getenv("COMMET_B200_RECS_BUDGET")) {                   // tests: force sub-ranges
-        uint64_t v = strtoull(e, nullptr, 10);
-        if (v >= 4096) budget = std::min(budget, v);
-    }
+    // scratch: 4 records of 4 bytes per k-mer; bounded by what the device has free, else sub-ranges.  The
+    // driver is only asked for the free memory when the buffer has to grow: cudaMemGetInfo takes device-wide
+    // locks and was measured to block the host for tens of milliseconds between two launches.
     uint64_t need = 4 * kmers + 64;
     uint64_t parts = 1;
+    uint64_t budget = c->recs_cap;
+    if (const char *e = getenv("COMMET_B200_RECS_BUDGET")) {                   // tests: force sub-ranges
+        uint64_t v = strtoull(e, nullptr, 10);
+        if (v >= 4096) budget = v;
+        else if (need > budget) budget = 0;
+    } else if (need > budget) budget = 0;
+    if (budget == 0) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        budget = (uint64_t)((free_b + c->recs_cap * 4) * 0.6) / 4;             // records
+    }
     if (need > budget) {
         need = 4 * positions + 64;                   // sub-ranges are cut by position: no per-part k-mer count
         parts = (need + budget - 1) / budget;
@@ -575,18 +661,27 @@ static int index_range_binned(commet_ctx *c, commet_reads *r, uint64_t b0, uint6
         if (s1 <= s0) continue;
         CK(cudaMemsetAsync(hist, 0, 512 * sizeof(unsigned long long), c->stream));
         unsigned g = grid_for(c, s1 - s0 + 32, 256, 8);
-        k_bin_count<<<g, 256, 0, c->stream>>>(r->planes, s0, s1, k, n_bins, hist);
+        if (n_bins <= 128) {     // pair table: n_bins^2 + n_bins counters of dynamic shared memory
+            const size_t sh = ((size_t)n_bins * n_bins + n_bins) * sizeof(unsigned int);
+            k_bin_count<true><<<std::min(g, (unsigned)c->sm_count * 3), 256, sh, c->stream>>>(r->planes, s0, s1, k, n_bins, hist);
+        } else
+            k_bin_count<false><<<g, 256, n_bins * sizeof(unsigned int), c->stream>>>(r->planes, s0, s1, k, n_bins, hist);
         k_bin_scan<<<1, 32, 0, c->stream>>>(hist, n_bins, base, cursor, tile_counter);
         uint64_t n_tiles = (((s1 + 31) >> 5) - (s0 >> 5) + kScatTileWords - 1) / kScatTileWords;
         unsigned gs = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * 2);
         k_bin_scatter<<<gs, kScatThreads, sizeof(ScatterSmem), c->stream>>>(r->planes, s0, s1, k, n_bins, cursor, c->recs);
         {
-            int tile = 4096, bps = 8;
+            int tile = 2048, bps = 8, pf = 1;
             if (const char *e = getenv("COMMET_B200_APPLY_TILE")) tile = atoi(e);
             if (const char *e = getenv("COMMET_B200_APPLY_BPS")) bps = atoi(e);
-            if (tile == 8192) k_bin_apply<8192><<<c->sm_count * bps, 256, 0, c->stream>>>(c->filter, c->recs, base, n_bins, tile_counter);
-            else if (tile == 2048) k_bin_apply<2048><<<c->sm_count * bps, 256, 0, c->stream>>>(c->filter, c->recs, base, n_bins, tile_counter);
-            else k_bin_apply<4096><<<c->sm_count * bps, 256, 0, c->stream>>>(c->filter, c->recs, base, n_bins, tile_counter);
+            if (const char *e = getenv("COMMET_B200_APPLY_PREFETCH")) pf = atoi(e);
+            const unsigned ga = c->sm_count * bps;
+            if (tile == 8192 && pf) k_bin_apply<8192, true><<<ga, 256, 0, c->stream>>>(c->filter, c->recs, base, n_bins, tile_counter);
+            else if (tile == 8192) k_bin_apply<8192, false><<<ga, 256, 0, c->stream>>>(c->filter, c->recs, base, n_bins, tile_counter);
+            else if (tile == 2048 && pf) k_bin_apply<2048, true><<<ga, 256, 0, c->stream>>>(c->filter, c->recs, base, n_bins, tile_counter);
+            else if (tile == 2048) k_bin_apply<2048, false><<<ga, 256, 0, c->stream>>>(c->filter, c->recs, base, n_bins, tile_counter);
+            else if (pf) k_bin_apply<4096, true><<<ga, 256, 0, c->stream>>>(c->filter, c->recs, base, n_bins, tile_counter);
+            else k_bin_apply<4096, false><<<ga, 256, 0, c->stream>>>(c->filter, c->recs, base, n_bins, tile_counter);
         }
         c->launches += 4;
         CK(cudaGetLastError());
@@ -885,6 +980,7 @@ static int chunk_loop(commet_ctx *c, int k, int t, uint64_t max_kmer, const std:
         DevBuf counts(c);
         unsigned long long total = 0;
         CKR(count_kmers(c, r, k, counts, &total));
+        trace("part: encode + W plane + k-mer counts queued, total read back (sync)");
         std::vector<uint32_t> cnt;          // fetched only when a chunk boundary falls inside this part
         uint64_t first = 0, rem = total;
         if (pending_drop) {                 // the read fetched and lost by the previous chunk (index_reads.h:60)
@@ -898,6 +994,7 @@ static int chunk_loop(commet_ctx *c, int k, int t, uint64_t max_kmer, const std:
         while (first < n) {
             if (cum + rem < max_kmer) {     // the rest of the part fits in the open chunk
                 CKR(insert(r, first, n - first, rem));
+                trace("part: insert queued");
                 cum += rem;
                 break;
             }
@@ -916,10 +1013,12 @@ static int chunk_loop(commet_ctx *c, int k, int t, uint64_t max_kmer, const std:
         }
     }
     if (open_reads > 0) CKR(close_chunk());
+    trace("last chunk: searches queued");
 
     unsigned long long h[128];
     CK(cudaMemcpyAsync(h, c->scratch, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    trace("counters read back (sync)");
     uint64_t n_tests = 0, n_lookups = 0;
     for (int s = 0; s < n_sets; s++) {
         if (shared) shared[s] = h[4 * s];
@@ -983,27 +1082,35 @@ extern "C" int commet_index_and_search(commet_ctx *c, int k, int t, uint64_t max
     // every H2D copy is queued up front on the copy stream (index parts first); the host never waits for one
     std::vector<uint64_t> cuts = split_parts(ioffs, n_index);
     int rc = 0;
+    HostTrace tr;
+    g_trace = tr.on ? &tr : nullptr;
+    trace("enter");
     for (size_t p = 0; rc == 0 && p + 1 < cuts.size(); p++) {
         commet_reads *r = nullptr;
         rc = reads_upload_async(c, ibases + ioffs[cuts[p]], ioffs + cuts[p], cuts[p + 1] - cuts[p], &r);
         if (rc == 0) parts.push_back(r);
+        trace("index part: allocations + copies queued");
     }
     for (int s = 0; rc == 0 && s < n_sets; s++) {
         if (qoffs[s][0] != 0) { rc = fail("commet_index_and_search: qoffs[%d][0] must be 0", s); break; }
         rc = reads_upload_async(c, qbases[s], qoffs[s], n_query[s], &q[s]);
         if (rc == 0) {
             uint64_t nw = tag_words(n_query[s]);
-            if (cudaMallocAsync(&dt[s], nw * 4, c->stream) != cudaSuccess) rc = fail("tag allocation failed");
+            if (c->arena.alloc((void **)&dt[s], nw * 4) != cudaSuccess) rc = fail("tag allocation failed");
             else if (cudaMemsetAsync(dt[s], 0, nw * 4, c->stream) != cudaSuccess) rc = fail("tag memset failed");
         }
     }
+    trace("query sets: allocations + copies queued");
     if (rc == 0) rc = chunk_loop(c, k, t, max_kmer, parts, n_sets, q.data(), dt.data(), searched, shared, stats);
     for (int s = 0; rc == 0 && s < n_sets; s++)
         if (cudaMemcpyAsync(tags[s], dt[s], n_query[s] / 8 + 1, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
             rc = fail("tag download failed");
     if (rc == 0 && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail("stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
     for (commet_reads *r : parts) commet_reads_free(r);
-    for (int s = 0; s < n_sets; s++) { commet_reads_free(q[s]); if (dt[s]) cudaFreeAsync(dt[s], c->stream); }
+    trace("tags downloaded (sync)");
+    for (int s = 0; s < n_sets; s++) { commet_reads_free(q[s]); if (dt[s]) c->arena.free(dt[s]); }
+    trace("freed");
+    g_trace = nullptr;
     return rc;
 }
 

@@ -27,6 +27,16 @@ __device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t *p)
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+// Filter probes: one random word per DRAM row activation.  The L2 fill of a probe miss is limited to 64 bytes
+// (the smallest prefetch-size qualifier): same probe rate -- random probes are bound by DRAM row activations,
+// 37.9 G lines/s measured, not by bytes -- but half the DRAM traffic of the default 128-byte fill
+// (profiles/r01_ubench_sectors.txt: 63 B instead of 125 B per probe).
+__device__ __forceinline__ uint32_t ld_probe_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ uint4 ld_nc_u4(const uint4 *p)
 {
     uint4 v;
@@ -296,34 +306,71 @@ __device__ __forceinline__ uint32_t w_in_range(uint32_t W, uint64_t wi, uint64_t
     return W;
 }
 
+// Histogram of the four keys' regions.  c = a^b and d = a|b are functions of (a, b), so the block counts the
+// PAIR (region of a, region of b) -- one shared-memory atomic per k-mer instead of four, spread over n_bins^2
+// counters instead of n_bins -- and folds the pair table into the four marginals at the end.  JOINT needs
+// n_bins^2 counters of dynamic shared memory (n_bins <= 128: 64 KB); larger bin counts use four atomics.
+template <bool JOINT>
 __global__ void __launch_bounds__(256)
 k_bin_count(const uint4 *__restrict__ planes, uint64_t b0, uint64_t b1, int k, int n_bins,
             unsigned long long *__restrict__ hist)
 {
-    __shared__ unsigned int sh[kMaxBins];
-    for (int i = threadIdx.x; i < n_bins; i += blockDim.x) sh[i] = 0;
+    extern __shared__ unsigned int sh_cnt[];          // JOINT: n_bins^2 pair counters, then n_bins marginals
+    const int n_cnt = JOINT ? n_bins * n_bins : n_bins;
+    unsigned int *marg = JOINT ? sh_cnt + n_cnt : sh_cnt;
+    for (int i = threadIdx.x; i < n_cnt + (JOINT ? n_bins : 0); i += blockDim.x) sh_cnt[i] = 0;
     __syncthreads();
-    uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    uint32_t lane = threadIdx.x & 31;
-    uint64_t w_first = b0 >> 5, w_end = (b1 + 31) >> 5;
-    for (uint64_t wi = w_first + warp; wi < w_end; wi += n_warps) {
-        uint4 q0 = planes[wi];
-        uint32_t W = w_in_range(q0.w, wi, b0, b1);
-        if (W == 0) continue;
-        uint4 q1 = planes[wi + 1];
-        if ((W >> lane) & 1u) {
-            uint32_t bin[4];
-            bin_only(__funnelshift_r(q0.x, q1.x, lane), __funnelshift_r(q0.y, q1.y, lane), k, bin);
-            atomicAdd(&sh[bin[0]], 1u);
-            atomicAdd(&sh[bin[1]], 1u);
-            atomicAdd(&sh[bin[2]], 1u);
-            atomicAdd(&sh[bin[3]], 1u);
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t w_first = b0 >> 5, w_end = (b1 + 31) >> 5;
+    // a warp takes 32 consecutive plane words per step: ONE coalesced 512-byte load (lane i holds word i, lane 0
+    // also the first word of the next group), then the words are handed round by shuffles -- a warp-uniform
+    // 16-byte load per word keeps a single request in flight per warp and is latency-bound (155 GB/s measured)
+    for (uint64_t g0 = w_first + warp * 32; g0 < w_end; g0 += n_warps * 32) {
+        const uint64_t wi = g0 + lane;
+        uint4 mine = make_uint4(0u, 0u, 0u, 0u), extra = mine;
+        if (wi <= w_end) mine = planes[wi];                          // planes carry 4 zero words past the end
+        if (lane == 0 && g0 + 32 <= w_end) extra = planes[g0 + 32];
+        const uint32_t ex = __shfl_sync(0xffffffffu, extra.x, 0), ey = __shfl_sync(0xffffffffu, extra.y, 0);
+        uint32_t q0x = __shfl_sync(0xffffffffu, mine.x, 0), q0y = __shfl_sync(0xffffffffu, mine.y, 0);
+#pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+            const uint32_t q1x = j == 31 ? ex : __shfl_sync(0xffffffffu, mine.x, (j + 1) & 31);
+            const uint32_t q1y = j == 31 ? ey : __shfl_sync(0xffffffffu, mine.y, (j + 1) & 31);
+            uint32_t W = __shfl_sync(0xffffffffu, mine.w, j);
+            if (g0 + j < w_end) W = w_in_range(W, g0 + j, b0, b1); else W = 0;
+            if ((W >> lane) & 1u) {
+                uint32_t bin[4];
+                bin_only(__funnelshift_r(q0x, q1x, lane), __funnelshift_r(q0y, q1y, lane), k, bin);
+                if (JOINT) atomicAdd(&sh_cnt[bin[0] * n_bins + bin[1]], 1u);
+                else {
+                    atomicAdd(&sh_cnt[bin[0]], 1u);
+                    atomicAdd(&sh_cnt[bin[1]], 1u);
+                    atomicAdd(&sh_cnt[bin[2]], 1u);
+                    atomicAdd(&sh_cnt[bin[3]], 1u);
+                }
+            }
+            q0x = q1x;
+            q0y = q1y;
         }
     }
     __syncthreads();
+    if (JOINT) {
+        for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) {
+            unsigned int c = sh_cnt[i];
+            if (c) {
+                unsigned int x = i / n_bins, y = i - x * n_bins;
+                atomicAdd(&marg[x], c);
+                atomicAdd(&marg[y], c);
+                atomicAdd(&marg[x ^ y], c);
+                atomicAdd(&marg[x | y], c);
+            }
+        }
+        __syncthreads();
+    }
     for (int i = threadIdx.x; i < n_bins; i += blockDim.x)
-        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+        if (marg[i]) atomicAdd(&hist[i], (unsigned long long)marg[i]);
 }
 
 // base[b] = exclusive prefix of hist, base[n_bins] = total; cursor[b] = base[b]; tile counter reset
@@ -437,7 +484,7 @@ k_bin_scatter(const uint4 *__restrict__ planes, uint64_t b0, uint64_t b1, int k,
 // blocks touch one or two regions: the RED.OR hit L2.  The next tile is claimed while the current one is
 // processed (the claimer also looks up the region of the tile's first record, once per tile instead of a
 // binary search per thread), and every thread has its 16-byte record loads in flight before the first RED.
-template <int TILE>
+template <int TILE, bool PREFETCH>
 __global__ void __launch_bounds__(256)
 k_bin_apply(uint32_t *__restrict__ filter, const uint32_t *__restrict__ recs,
             const unsigned long long *__restrict__ base, int n_bins,
@@ -482,6 +529,21 @@ k_bin_apply(uint32_t *__restrict__ filter, const uint32_t *__restrict__ recs,
         }
         int bin = bin0;
         unsigned long long lim = sbase[bin + 1];
+        if (PREFETCH && bin0 + 1 < n_bins) {
+            // A RED that misses L2 is served at the DRAM random-access rate, and every line of a region misses
+            // once per sweep (measured: ~3-4.5 ms of every apply pass, whatever the number of records).  The
+            // tiles of region b therefore pull region b+1 into L2 ahead of its first RED, each tile an equal
+            // slice, as sequential line prefetches -- unless b+1 receives too few records to touch most lines.
+            const unsigned long long rb = sbase[bin0], re = sbase[bin0 + 1], ne = sbase[bin0 + 2];
+            if (ne - re >= (1ull << (kRegionLog2 - 8))) {                       // >= half a record per line
+                const unsigned long long tf = rb / TILE, n_t = (re - 1) / TILE - tf + 1, rel = tl - tf;
+                const unsigned long long lines = 1ull << (kRegionLog2 - 7);
+                const unsigned long long l0 = lines * rel / n_t, l1 = lines * (rel + 1) / n_t;
+                const char *nxt_region = reinterpret_cast<const char *>(filter) + ((uint64_t)(bin0 + 1) << kRegionLog2);
+                for (unsigned long long l = l0 + threadIdx.x; l < l1; l += 256)
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(nxt_region + (l << 7)));
+            }
+        }
 #pragma unroll
         for (int it = 0; it < U; it++) {
             unsigned long long idx = t0 + ((unsigned long long)it * 256 + threadIdx.x) * 4;
@@ -592,11 +654,11 @@ k_index_regions(uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
 __device__ __forceinline__ bool probe_bcd(const uint32_t *__restrict__ filter, const Keys &q, unsigned int &tests)
 {
     tests++;
-    if (!(ld_nc_u32(filter + key_word(q.b)) & key_bit(q.b, 1))) return false;
+    if (!(ld_probe_u32(filter + key_word(q.b)) & key_bit(q.b, 1))) return false;
     tests++;
-    if (!(ld_nc_u32(filter + key_word(q.c)) & key_bit(q.c, 2))) return false;
+    if (!(ld_probe_u32(filter + key_word(q.c)) & key_bit(q.c, 2))) return false;
     tests++;
-    return (ld_nc_u32(filter + key_word(q.d)) & key_bit(q.d, 3)) != 0;
+    return (ld_probe_u32(filter + key_word(q.d)) & key_bit(q.d, 3)) != 0;
 }
 
 // One strand of search_reads (search_reads.h:46-64 forward, :66-83 reverse):
@@ -650,7 +712,7 @@ __device__ __forceinline__ bool scan_strand(const uint32_t *__restrict__ filter,
             if (rev) ka[u] = ~(hv >> u) & mask;
             else ka[u] = __brevll(hv >> u) >> (64 - k);
             av[u] = 0;
-            if ((m >> u) & 1u) av[u] = ld_nc_u32(filter + key_word(ka[u]));
+            if ((m >> u) & 1u) av[u] = ld_probe_u32(filter + key_word(ka[u]));
         }
         bool hit = false;
 #pragma unroll
