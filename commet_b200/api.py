@@ -50,6 +50,8 @@ _SIGS = {
     "commet_reads_free": (None, [C.c_void_p]),
     "commet_reads_count": (C.c_uint64, [C.c_void_p]),
     "commet_reads_bases": (C.c_uint64, [C.c_void_p]),
+    "commet_reads_select": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "commet_reads_selected": (C.c_uint64, [C.c_void_p]),
     "commet_reads_kmer_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "commet_chunk_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64, _u64p, _u64p]),
     "commet_index_begin": (C.c_int, [C.c_void_p, C.c_int]),
@@ -69,10 +71,15 @@ _SIGS = {
                                           C.c_void_p, C.c_void_p]),
     "commet_index_and_search_staged": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_int,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "commet_index_and_search_resident": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_int,
+                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p]),
     "commet_filter_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_float,
                                       C.c_int64, C.c_void_p, C.c_void_p]),
     "commet_filter_reads_staged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_int64,
                                              C.c_void_p, C.c_void_p]),
+    "commet_filter_reads_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_float,
+                                            C.c_int64, C.c_void_p, C.c_void_p]),
     "commet_filter_reads_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_float,
                                           C.c_int64, C.c_void_p, C.c_void_p]),
     "commet_bvop": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -230,6 +237,14 @@ class Context:
                                                    C.byref(h)))
         return ReadStream(self, h.value)
 
+    def select(self, reads: ReadStream, bv: np.ndarray | None):
+        """restrict a staged stream to the reads whose bit is set in `bv` (.bv payload over its records; None = all):
+        the input boolean vector of ReadFile (fasta_file.h:143-152)"""
+        if bv is not None:
+            bv = np.ascontiguousarray(bv, dtype=np.uint8)
+            assert bv.size >= reads.n_reads // 8 + 1
+        self._ck(self.lib.commet_reads_select(self.handle, reads.handle, _ptr(bv)))
+
     def kmer_counts(self, reads: ReadStream, k: int) -> np.ndarray:
         out = np.zeros(max(reads.n_reads, 1), dtype=np.uint32)
         self._ck(self.lib.commet_reads_kmer_counts(self.handle, reads.handle, k, _ptr(out)))
@@ -368,6 +383,15 @@ class Context:
         self._ck(self.lib.commet_filter_reads_staged(self.handle, reads.handle, min_len, max_N, C.c_float(min_shannon),
                                                      max_reads, _ptr(d_bv), _ptr(cnt)))
         return dict(rm_length=int(cnt[0]), rm_N=int(cnt[1]), rm_shannon=int(cnt[2]), selected=int(cnt[3]))
+
+    def filter_reads_range(self, reads: ReadStream, first: int, count: int, min_len=0, max_N=-1, min_shannon=0.0,
+                           max_reads=-1):
+        """filter_reads on records [first, first+count) of a staged stream (one file of a set staged as a whole)"""
+        bv = np.zeros(count // 8 + 1, dtype=np.uint8)
+        cnt = np.zeros(4, dtype=np.uint64)
+        self._ck(self.lib.commet_filter_reads_range(self.handle, reads.handle, first, count, min_len, max_N,
+                                                    C.c_float(min_shannon), max_reads, _ptr(bv), _ptr(cnt)))
+        return bv, dict(rm_length=int(cnt[0]), rm_N=int(cnt[1]), rm_shannon=int(cnt[2]), selected=int(cnt[3]))
 
     def filter_reads_device(self, d_bases: int, d_offs: int, n_reads: int, d_bv: int, min_len=0, max_N=-1, min_shannon=0.0,
                             max_reads=-1):

@@ -153,7 +153,11 @@ struct commet_reads {
     uint64_t n_reads = 0, n_bases = 0, n_words = 0;
     uint4 *planes = nullptr;          // n_words + 4 (zero tail)
     uint64_t *offs = nullptr;         // n_reads + 1, device
-    int k_prepared = 0;               // W plane valid for this k (0: none)
+    int k_prepared = 0;               // W plane valid for this k (0: none) and the current selection
+    // read selection = the input boolean vectors of the set's files (commet_reads_select); null: every read
+    uint32_t *sel = nullptr;          // device, ceil((n_reads/8+1)/4) words
+    std::vector<uint8_t> h_sel;       // host copy (n_reads/8+1 bytes) for the chunk-boundary walk
+    uint64_t n_selected = 0;
     // upload in flight: ASCII chunks arrive on the copy stream, each followed by an event; the
     // encode of a chunk is enqueued on the compute stream behind its event (flush_encode)
     uint8_t *ascii = nullptr;         // device staging of the ASCII bases (pool allocation)
@@ -482,6 +486,7 @@ extern "C" void commet_reads_free(commet_reads *r)
     if (r->ctx) {
         if (r->planes) r->ctx->arena.free(r->planes);
         if (r->offs) r->ctx->arena.free(r->offs);
+        if (r->sel) r->ctx->arena.free(r->sel);
     }
     delete r;
 }
@@ -505,10 +510,62 @@ static int prepare(commet_ctx *c, commet_reads *r, int k)
         }
         k_windows<<<grid_for(c, r->n_words, 256, 8), 256, 0, c->stream>>>(r->planes, S.as<uint32_t>(), r->n_words, k);
         c->launches++;
+        if (r->sel && r->n_reads) {
+            k_mask_unselected<<<grid_for(c, r->n_reads, 256, 8), 256, 0, c->stream>>>(r->planes, r->offs, r->n_reads, r->sel);
+            c->launches++;
+        }
         CK(cudaGetLastError());                    // S is released in stream order
     }
     r->k_prepared = k;
     return 0;
+}
+
+// ------------------------------------------------------------ read selection --
+namespace {
+inline bool sel_get(const commet_reads *r, uint64_t i)
+{
+    return r->h_sel.empty() || ((r->h_sel[i >> 3] >> (i & 7)) & 1u);
+}
+inline uint64_t sel_count(const commet_reads *r, uint64_t a, uint64_t b)      // selected reads in [a, b)
+{
+    if (r->h_sel.empty() || b <= a) return b > a ? b - a : 0;
+    uint64_t n = 0, i = a;
+    for (; i < b && (i & 7); i++) n += (r->h_sel[i >> 3] >> (i & 7)) & 1u;
+    for (; i + 8 <= b; i += 8) n += (uint64_t)__builtin_popcount(r->h_sel[i >> 3]);
+    for (; i < b; i++) n += (r->h_sel[i >> 3] >> (i & 7)) & 1u;
+    return n;
+}
+}  // namespace
+
+extern "C" int commet_reads_select(commet_ctx *c, commet_reads *r, const uint8_t *bv)
+{
+    if (!c || !r) return fail("commet_reads_select: null argument");
+    CKR(set_device(c));
+    r->k_prepared = 0;                              // the W plane depends on the selection
+    if (!bv) {
+        if (r->sel) { c->arena.free(r->sel); r->sel = nullptr; }
+        r->h_sel.clear();
+        r->n_selected = r->n_reads;
+        return 0;
+    }
+    const uint64_t nb = r->n_reads / 8 + 1, nw = tag_words(r->n_reads);
+    r->h_sel.assign(bv, bv + nb);
+    if (r->n_reads & 7) r->h_sel[nb - 1] &= (uint8_t)((1u << (r->n_reads & 7)) - 1u);     // padding bits never select
+    else r->h_sel[nb - 1] = 0;
+    r->n_selected = 0;
+    for (uint64_t i = 0; i < nb; i++) r->n_selected += (uint64_t)__builtin_popcount(r->h_sel[i]);
+    if (!r->sel && c->arena.alloc((void **)&r->sel, nw * 4) != cudaSuccess) return fail("selection allocation failed");
+    CK(cudaMemsetAsync(r->sel, 0, nw * 4, c->stream));
+    // h_sel is owned by the stream object and outlives the copy; pageable source: staged by the driver
+    CK(cudaMemcpyAsync(r->sel, r->h_sel.data(), nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" uint64_t commet_reads_selected(const commet_reads *r)
+{
+    if (!r) return 0;
+    return r->sel ? r->n_selected : r->n_reads;
 }
 
 extern "C" int commet_reads_kmer_counts(commet_ctx *c, commet_reads *r, int k, uint32_t *counts)
@@ -551,26 +608,36 @@ static int chunk_plan(commet_ctx *c, commet_reads *r, int k, uint64_t max_kmer,
     CK(cudaStreamSynchronize(c->stream));
     if (n_kmers) *n_kmers = total;
     if (total < max_kmer) {            // the limit is never reached: one chunk, nothing dropped
-        bounds.push_back(0);
-        bounds.push_back(n);
-        if (chunk_kmers) chunk_kmers->push_back(total);
-        if (n_indexed) *n_indexed = n;
+        const uint64_t n_sel = sel_count(r, 0, n);
+        if (n_sel) {
+            bounds.push_back(0);
+            bounds.push_back(n);
+            if (chunk_kmers) chunk_kmers->push_back(total);
+        }
+        if (n_indexed) *n_indexed = n_sel;
         return 0;
     }
-    // index_reads.h:48-49,60 + index_and_search.cpp:255: walk the per-read counts
+    // index_reads.h:48-49,60 + index_and_search.cpp:255: walk the per-read counts (of the selected reads)
     std::vector<uint32_t> cnt(n);
     CK(cudaMemcpyAsync(cnt.data(), d.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     uint64_t i = 0, indexed = 0, kmers = 0;
     while (i < n) {
-        uint64_t start = i, cum = 0;
-        while (i < n && cum < max_kmer) cum += cnt[i++];
+        uint64_t start = i, cum = 0, taken = 0;
+        while (i < n && cum < max_kmer) {
+            if (sel_get(r, i)) { cum += cnt[i]; taken++; }
+            i++;
+        }
+        if (taken == 0) break;                 // only unselected reads were left
         bounds.push_back(start);
         bounds.push_back(i);
-        indexed += i - start;
+        indexed += taken;
         kmers += cum;
         if (chunk_kmers) chunk_kmers->push_back(cum);
-        if (i < n && cum >= max_kmer) i++;     // fetched, then lost
+        if (cum >= max_kmer) {                 // the next valid read is fetched, then lost
+            while (i < n && !sel_get(r, i)) i++;
+            if (i < n) i++;
+        }
     }
     if (n_indexed) *n_indexed = indexed;
     if (n_kmers) *n_kmers = kmers;             // k-mers actually fed (lost reads excluded)
@@ -829,9 +896,9 @@ static int search_launch(commet_ctx *c, commet_reads *r, int k, int t, uint32_t 
     CKR(prepare(c, r, k));
     unsigned g = grid_for(c, r->n_reads, 256, 8);
     if (c->count_probes)
-        k_search<true><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters);
+        k_search<true><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
     else
-        k_search<false><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters);
+        k_search<false><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -945,14 +1012,14 @@ static int chunk_loop(commet_ctx *c, int k, int t, uint64_t max_kmer, const std:
         dirty = false;
         return 0;
     };
-    auto insert = [&](commet_reads *r, uint64_t first, uint64_t count, uint64_t kmers) -> int {
+    auto insert = [&](commet_reads *r, uint64_t first, uint64_t count, uint64_t kmers, uint64_t n_sel) -> int {
         CKR(open_filter());
         CKR(t_index.begin(c->stream));
         CKR(index_range(c, r, first, count, kmers));
         CKR(t_index.end(c->stream));
-        n_indexed += count;
+        n_indexed += n_sel;
         n_kmers += kmers;
-        open_reads += count;
+        open_reads += n_sel;
         return 0;
     };
     auto close_chunk = [&]() -> int {
@@ -974,9 +1041,12 @@ static int chunk_loop(commet_ctx *c, int k, int t, uint64_t max_kmer, const std:
         return 0;
     };
 
+    // "reads" below are the SELECTED reads of a part (commet_reads_select); unselected ones carry no k-mer
+    // (their W bits are cleared) and are invisible to the stop rule, exactly like reads the reference's
+    // get_next_read skips (fasta_file.h:143-152)
     for (commet_reads *r : parts) {
         const uint64_t n = r->n_reads;
-        if (n == 0) continue;
+        if (n == 0 || sel_count(r, 0, n) == 0) continue;
         DevBuf counts(c);
         unsigned long long total = 0;
         CKR(count_kmers(c, r, k, counts, &total));
@@ -984,16 +1054,17 @@ static int chunk_loop(commet_ctx *c, int k, int t, uint64_t max_kmer, const std:
         std::vector<uint32_t> cnt;          // fetched only when a chunk boundary falls inside this part
         uint64_t first = 0, rem = total;
         if (pending_drop) {                 // the read fetched and lost by the previous chunk (index_reads.h:60)
+            while (first < n && !sel_get(r, first)) first++;
             uint32_t c0 = 0;
-            CK(cudaMemcpyAsync(&c0, counts.p, sizeof c0, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(&c0, counts.as<uint32_t>() + first, sizeof c0, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaStreamSynchronize(c->stream));
             rem -= c0;
-            first = 1;
+            first++;
             pending_drop = false;
         }
         while (first < n) {
             if (cum + rem < max_kmer) {     // the rest of the part fits in the open chunk
-                CKR(insert(r, first, n - first, rem));
+                CKR(insert(r, first, n - first, rem, sel_count(r, first, n)));
                 trace("part: insert queued");
                 cum += rem;
                 break;
@@ -1003,11 +1074,15 @@ static int chunk_loop(commet_ctx *c, int k, int t, uint64_t max_kmer, const std:
                 CK(cudaMemcpyAsync(cnt.data(), counts.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
                 CK(cudaStreamSynchronize(c->stream));
             }
-            uint64_t i = first, fed = 0;
-            while (i < n && cum < max_kmer) { cum += cnt[i]; fed += cnt[i]; i++; }
-            if (i > first) CKR(insert(r, first, i - first, fed));
+            uint64_t i = first, fed = 0, taken = 0;
+            while (i < n && cum < max_kmer) {
+                if (sel_get(r, i)) { cum += cnt[i]; fed += cnt[i]; taken++; }
+                i++;
+            }
+            if (i > first) CKR(insert(r, first, i - first, fed, taken));
             rem -= fed;
             CKR(close_chunk());             // cum >= max_kmer here, because cum + rem was
+            while (i < n && !sel_get(r, i)) i++;
             if (i < n) { rem -= cnt[i]; i++; } else pending_drop = true;
             first = i;
         }
@@ -1043,6 +1118,37 @@ extern "C" int commet_index_and_search_staged(commet_ctx *c, int k, int t, uint6
     if (k < 1 || k > kMaxK) return fail("k=%d unsupported (1..%d)", k, kMaxK);
     std::vector<commet_reads *> parts(1, index);
     return chunk_loop(c, k, t, max_kmer, parts, n_sets, queries, d_tags, searched, shared, stats);
+}
+
+// The same loop on resident streams with HOST outputs: what a persistent driver calls once per
+// index_and_search round of Commet.py:186-240 (commet_b200/csrc/tools/commet_nxn.cpp).  Tag words live in the
+// context's arena for the duration of the call; ones[s] is the device-side popcount of set s's tag vector
+// (k_popcount), i.e. the number `bvop -i` would print for the .bv files of that set (Commet.py:252-271).
+extern "C" int commet_index_and_search_resident(commet_ctx *c, int k, int t, uint64_t max_kmer, commet_reads *index,
+                                                int n_sets, commet_reads *const *queries, uint8_t *const *tags,
+                                                uint64_t *searched, uint64_t *shared, uint64_t *ones, uint64_t *stats)
+{
+    CKR(set_device(c));
+    if (n_sets < 0 || n_sets > kMaxSets) return fail("n_sets=%d unsupported (0..%d)", n_sets, kMaxSets);
+    if (k < 1 || k > kMaxK) return fail("k=%d unsupported (1..%d)", k, kMaxK);
+    std::vector<uint32_t *> dt(n_sets, nullptr);
+    int rc = 0;
+    for (int s = 0; rc == 0 && s < n_sets; s++) {
+        const uint64_t nw = tag_words(queries[s]->n_reads);
+        if (c->arena.alloc((void **)&dt[s], nw * 4) != cudaSuccess) rc = fail("tag allocation failed");
+        else if (cudaMemsetAsync(dt[s], 0, nw * 4, c->stream) != cudaSuccess) rc = fail("tag memset failed");
+    }
+    std::vector<commet_reads *> parts(1, index);
+    if (rc == 0) rc = chunk_loop(c, k, t, max_kmer, parts, n_sets, queries, dt.data(), searched, shared, stats);
+    for (int s = 0; rc == 0 && s < n_sets; s++) {
+        if (ones) rc = commet_bv_popcount_dev(c, dt[s], queries[s]->n_reads, &ones[s]);
+        if (rc == 0 && tags && tags[s] &&
+            cudaMemcpyAsync(tags[s], dt[s], queries[s]->n_reads / 8 + 1, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+            rc = fail("tag download failed");
+    }
+    if (rc == 0 && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail("stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    for (int s = 0; s < n_sets; s++) if (dt[s]) c->arena.free(dt[s]);
+    return rc;
 }
 
 // Read ranges of the parts a host-resident index set is uploaded in: 20 % / 30 % / 50 % of the bases, cut at
@@ -1206,6 +1312,27 @@ extern "C" int commet_filter_reads_staged(commet_ctx *c, commet_reads *r, int64_
                           k_filter<<<n_blocks, kFilterBlock, 0, c->stream>>>(r->planes, r->offs, n, fp, d_bv, n_bv_words, classes,
                                                                              totals, border, border_cap, nb);
                       });
+}
+
+extern "C" int commet_filter_reads_range(commet_ctx *c, commet_reads *r, uint64_t first, uint64_t count, int64_t min_len,
+                                         int64_t max_N, float min_shannon, int64_t max_reads, uint8_t *bv,
+                                         uint64_t *counters)
+{
+    CKR(set_device(c));
+    if (first + count > r->n_reads) return fail("commet_filter_reads_range: range out of bounds");
+    CKR(flush_encode(c, r));
+    DevBuf d(c);
+    const uint64_t nw = tag_words(count);
+    if (d.alloc(nw * 4) != cudaSuccess) return fail("filter_reads: selection allocation failed");
+    CKR(filter_run(c, count, min_len, max_N, min_shannon, max_reads, d.as<uint32_t>(), counters,
+                   [&](unsigned n_blocks, const FilterParams &fp, uint64_t n_bv_words, uint8_t *classes, unsigned int *totals,
+                       BorderRec *border, unsigned int border_cap, unsigned int *nb) {
+                       k_filter<<<n_blocks, kFilterBlock, 0, c->stream>>>(r->planes, r->offs + first, count, fp, d.as<uint32_t>(),
+                                                                          n_bv_words, classes, totals, border, border_cap, nb);
+                   }));
+    CK(cudaMemcpyAsync(bv, d.p, count / 8 + 1, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
 extern "C" int commet_filter_reads_dev(commet_ctx *c, const uint8_t *d_bases, const uint64_t *d_offs, uint64_t n_reads,

@@ -167,6 +167,29 @@ k_windows(uint4 *__restrict__ planes, const uint32_t *__restrict__ S, uint64_t n
     }
 }
 
+// Read selection (the input boolean vector of a read file, fasta_file.h:143-152: reads whose bit is 0 are never
+// handed out by get_next_read): the W bits of every position of an unselected read are cleared, so the flat
+// per-position kernels (k-mer counts, insert) skip those reads without knowing about reads at all.
+__global__ void __launch_bounds__(256)
+k_mask_unselected(uint4 *__restrict__ planes, const uint64_t *__restrict__ offs, uint64_t n_reads,
+                  const uint32_t *__restrict__ sel)
+{
+    uint32_t *P32 = reinterpret_cast<uint32_t *>(planes);
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += stride) {
+        if ((sel[r >> 5] >> (r & 31)) & 1u) continue;
+        uint64_t o = offs[r], e = offs[r + 1];
+        for (uint64_t wi = o >> 5; (wi << 5) < e; wi++) {
+            uint32_t m = ~0u;
+            uint64_t lo = wi << 5;
+            if (lo < o) m &= ~0u << (o - lo);
+            if (lo + 32 > e) m &= ~0u >> (lo + 32 - e);
+            if (m == ~0u) P32[4 * wi + 3] = 0u;               // the whole word belongs to this read
+            else atomicAnd(&P32[4 * wi + 3], ~m);             // shared with a neighbouring read
+        }
+    }
+}
+
 // per-read k-mer count = popcount of W over the read's positions
 __global__ void __launch_bounds__(256)
 k_kmer_counts(const uint4 *__restrict__ planes, const uint64_t *__restrict__ offs,
@@ -746,12 +769,14 @@ template <bool COUNT>
 __global__ void __launch_bounds__(256)
 k_search(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
          const uint64_t *__restrict__ offs, uint64_t n_reads, int k, int t,
-         uint32_t *__restrict__ tags, unsigned long long *__restrict__ counters)
+         uint32_t *__restrict__ tags, unsigned long long *__restrict__ counters,
+         const uint32_t *__restrict__ sel)
 {
     const uint64_t mask = (1ull << k) - 1;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     unsigned int found = 0, searched = 0, tests = 0, lookups = 0;
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += stride) {
+        if (sel && !((sel[r >> 5] >> (r & 31)) & 1u)) continue;   // not in the input vector: fasta_file.h:143-152
         if ((tags[r >> 5] >> (r & 31)) & 1u) continue;        // file_manager.h:99
         searched++;
         uint64_t o = offs[r];

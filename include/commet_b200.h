@@ -82,6 +82,15 @@ void commet_reads_free(commet_reads *r);
 uint64_t commet_reads_count(const commet_reads *r);
 uint64_t commet_reads_bases(const commet_reads *r);
 
+/* Read selection = the input boolean vector of a read file (ReadFile::bv, include/fasta_file.h:143-152,
+ * include/fastq_file.h:132-180: get_next_read skips reads whose bit is 0).  A stream staged with ALL the records
+ * of a set's files can be re-used under different vectors without another parse or upload: unselected reads are
+ * neither indexed, nor counted by the stop rule, nor searched, nor tagged.  bv: n_reads/8+1 bytes in the .bv
+ * payload layout over the stream's records (host memory, copied); NULL selects every read again.  This is what
+ * lets one process run all N^2-1 index_and_search rounds of Commet.py:186-240 on resident sets. */
+int commet_reads_select(commet_ctx *ctx, commet_reads *r, const uint8_t *bv);
+uint64_t commet_reads_selected(const commet_reads *r);
+
 /* Number of k-mers index_reads would feed for each read (windows of k
  * consecutive ACGTacgt chars, include/index_reads.h:52-58). counts: n_reads u32. */
 int commet_reads_kmer_counts(commet_ctx *ctx, commet_reads *r, int k, uint32_t *counts);
@@ -164,6 +173,14 @@ int commet_index_and_search_staged(commet_ctx *ctx, int k, int t, uint64_t max_k
                                    uint32_t *const *d_tags, uint64_t *searched, uint64_t *shared,
                                    uint64_t *stats);
 
+/* same loop on resident streams (with their current commet_reads_select vectors) and HOST outputs: tags[s] =
+ * n_reads/8+1 bytes over ALL records of set s (unselected reads stay 0), ones[s] = device-side popcount of that
+ * vector = what `bvop -i` prints for the set's .bv files (src/bvop.cpp:155-160, Commet.py:252-271).  One call =
+ * one index_and_search invocation of Commet.py:197,220,233 without parse, upload or process start. */
+int commet_index_and_search_resident(commet_ctx *ctx, int k, int t, uint64_t max_kmer, commet_reads *index,
+                                     int n_sets, commet_reads *const *queries, uint8_t *const *tags,
+                                     uint64_t *searched, uint64_t *shared, uint64_t *ones, uint64_t *stats);
+
 /* ---- stage 3: filter_reads --------------------------------------------------
  * The per-read selection of src/filter_reads.cpp:181-205: length < min_len ->
  * drop; #non-ACGTacgt > max_N -> drop (max_N<0: infinite); shannon_index
@@ -179,6 +196,11 @@ int commet_filter_reads(commet_ctx *ctx, const uint8_t *bases, const uint64_t *o
 int commet_filter_reads_staged(commet_ctx *ctx, commet_reads *r, int64_t min_len, int64_t max_N,
                                float min_shannon, int64_t max_reads, uint32_t *d_bv,
                                uint64_t *counters);
+/* the same selection on records [first, first+count) of a staged stream (one FILE of a set staged as a whole):
+ * bv (host) gets count/8+1 bytes, bit i = record first+i. */
+int commet_filter_reads_range(commet_ctx *ctx, commet_reads *r, uint64_t first, uint64_t count, int64_t min_len,
+                              int64_t max_N, float min_shannon, int64_t max_reads, uint8_t *bv,
+                              uint64_t *counters);
 /* the selection fused into the staging pass: ASCII bases already on the device are read once (16-byte vector
  * loads) and only the selection bits are written.  d_bases: 16-byte aligned, readable up to the next multiple of
  * 16 bytes; d_bv: ceil((n_reads/8+1)/4) u32 words.  commet_filter_reads is this after an H2D copy. */

@@ -165,6 +165,54 @@ def test_chunk_loop_over_uploaded_parts(ctx, seed, monkeypatch):
     assert info["searched"] == exp["searched"] and info["shared"] == exp["shared"]
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_selection_equals_compacted_streams(ctx, seed):
+    """commet_reads_select: a stream staged with ALL records of a file, restricted by an input boolean vector,
+    must behave exactly like the reference's valid-read stream (fasta_file.h:143-152): chunk boundaries, the
+    fetched-and-lost read, the counters and every tag bit equal the oracle run on the compacted streams."""
+    import torch
+    rng = np.random.default_rng(12000 + seed)
+    k = int(rng.integers(8, 19))
+    t = int(rng.integers(1, 3))
+    L = int(rng.integers(k, 4 * k))
+    ref = H.make_ref_set(rng, int(rng.integers(30, 1500)), max(1, L - 10), L + 10, **DIRT[seed % 3])
+    queries = [H.make_query_set(rng, ref, int(rng.integers(1, 300)), max(1, L - 10), L + 10, **DIRT[seed % 3])
+               for _ in range(2)]
+    p_sel = [0.5, 0.9, 0.1, 0.0][seed % 4]
+    masks = [rng.random(len(x)) < (p_sel if i == 0 else 0.7) for i, x in enumerate([ref] + queries)]
+    if seed % 6 == 5:
+        masks[1][:] = False                           # a query set with no valid read at all
+    sub = [[r for r, m in zip(x, mk) if m] for x, mk in zip([ref] + queries, masks)]
+    total_kmers = sum(max(0, len(r) - k + 1) for r in sub[0])
+    maxk = [None, max(1, total_kmers // 2), max(1, total_kmers // 9), 1][(seed // 4) % 4]
+    exp_tags, exp = oracle.index_and_search(k, t, H.to_stream(sub[0]), [H.to_stream(q) for q in sub[1:]], maxk)
+
+    streams = [ctx.stage(*H.to_stream(x)) for x in [ref] + queries]
+    for st, mk in zip(streams, masks):
+        ctx.select(st, np.packbits(np.concatenate([mk, np.zeros(8, bool)]), bitorder="little")[:len(mk) // 8 + 1])
+    d_tags = [torch.zeros((len(q) // 8 + 4) // 4 + 1, dtype=torch.int32, device="cuda") for q in queries]
+    info = ctx.index_and_search_staged(k, t, streams[0], streams[1:], [x.data_ptr() for x in d_tags], maxk)
+    ctx.sync()
+    assert info["chunks"] == exp["chunks"] and info["indexed"] == exp["indexed"] and info["kmers"] == exp["kmers"]
+    assert info["searched"] == exp["searched"] and info["shared"] == exp["shared"]
+    for s, q in enumerate(queries):
+        got = np.unpackbits(d_tags[s].cpu().numpy().view(np.uint8), bitorder="little")[:len(q)].astype(bool)
+        want = np.zeros(len(q), bool)
+        want[np.flatnonzero(masks[s + 1])] = np.asarray(exp_tags[s], dtype=bool)[:int(masks[s + 1].sum())]
+        assert np.array_equal(got, want), (seed, s)
+    # back to "every read": the same streams, no vector
+    for st in streams:
+        ctx.select(st, None)
+    exp_tags, exp = oracle.index_and_search(k, t, H.to_stream(ref), [H.to_stream(q) for q in queries], maxk)
+    for x in d_tags:
+        x.zero_()
+    info = ctx.index_and_search_staged(k, t, streams[0], streams[1:], [x.data_ptr() for x in d_tags], maxk)
+    ctx.sync()
+    assert info["chunks"] == exp["chunks"] and info["indexed"] == exp["indexed"] and info["shared"] == exp["shared"]
+    for st in streams:
+        st.free()
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_probe_counts_match_reference_semantics(ctx, seed):
     """N_probes: the instrumented kernel counts exactly the byte tests / lookups the reference does."""

@@ -207,3 +207,104 @@ def test_filter_reads_vs_reference_binary(bin_dir, tmp_path, seed):
         res[who] = (outp.read_bytes(), [ln for ln in r.stdout.split("\n") if not ln.startswith("Total  time")])
     assert res["ref"][0] == res["gpu"][0], (seed, args)
     assert res["ref"][1] == res["gpu"][1], (seed, args)
+
+
+# ---- commet_nxn: the whole Commet.py run in one process on resident sets ----------------------------------
+def _nxn(bin_dir, cwd, config, out="output_commet/", gpus=None, **kw):
+    args = [str(bin_dir / "commet_nxn"), config, "-o", out, "-q"]
+    for key, val in kw.items():
+        args += [f"-{key}", str(val)]
+    if gpus:
+        args += ["--gpus", str(gpus)]
+    r = subprocess.run(args, cwd=cwd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    o = Path(cwd) / out
+    return {n: (o / f"matrix_{n}.csv").read_text() for n in ("plain", "percentage", "normalized")}
+
+
+@pytest.mark.parametrize("case,config,kw", [
+    ("abcde_3sets_k32", "ABCDE_bench/sets_config.txt", dict(k=32)),
+    ("abcde_5sets_k32", "ABCDE_bench/five_sets.txt", dict(k=32)),
+    ("dissymmetry_k33", "test_dissymmetry/fof.txt", dict(k=33)),
+    ("abcde_3sets_k21_filtered", "ABCDE_bench/sets_config.txt", dict(k=21, t=3, l=100, e=1.9, n=0, m=9000)),
+])
+def test_commet_nxn_bit_exact(bin_dir, tmp_path, case, config, kw):
+    """One process, resident sets, device-side matrices: every .bv and the three CSVs byte-identical to the
+    unmodified Commet.py + reference binaries (golden)."""
+    fixtures.materialize(tmp_path)
+    res = _nxn(bin_dir, tmp_path, config, **kw)
+    check_flow(tmp_path, res, GOLDEN[case])
+
+
+def _random_config(rng, tmp, n_sets, L, dirt):
+    base = H.make_ref_set(rng, int(rng.integers(60, 400)), max(1, L - 10), L + 10, **dirt)
+    lines = []
+    for s in range(n_sets):
+        files = []
+        for _ in range(int(rng.integers(1, 3))):
+            files.append(H.make_query_set(rng, base, int(rng.integers(20, 300)), max(1, L - 10), L + 10,
+                                          frac_shared=float(rng.uniform(0.2, 0.9)), **dirt))
+        items = _write_set(rng, tmp, f"s{s}", files, with_bv=False)
+        lines.append(f"set{s} : " + " ; ".join(str(Path(i).relative_to(tmp)) for i in items))
+    (tmp / "cfg.txt").write_text("\n".join(lines) + "\n")
+    return "cfg.txt"
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_commet_nxn_vs_tool_flow(bin_dir, tmp_path, seed):
+    """Random multi-file sets (FASTA/FASTQ/gz), several chunks per index, filters on: commet_nxn against the
+    Commet.py flow driven over the drop-in tools (themselves pinned against the reference binaries)."""
+    rng = np.random.default_rng(15000 + seed)
+    k = int(rng.integers(10, 19))
+    t = int(rng.integers(1, 4))
+    L = int(rng.integers(2 * k, 5 * k))
+    dirt = dict(p_N=float(rng.choice([0, 0.02])), p_lower=float(rng.choice([0, 0.3])))
+    cfg = _random_config(rng, tmp_path, int(rng.integers(2, 4)), L, dirt)     # 3 or 8 tool rounds + filters + bvop -i forks
+    kw = dict(k=k, t=t)
+    if seed % 2 == 1:
+        kw.update(l=int(rng.integers(1, L)), e=round(float(rng.uniform(0.5, 1.95)), 3), n=int(rng.integers(0, 3)))
+    if seed % 4 == 2:
+        kw.update(m=int(rng.integers(10, 400)))
+    exp = commet_flow.run(cfg, bin_dir, tmp_path, out_dir="flow_out/", **kw)
+    got = _nxn(bin_dir, tmp_path, cfg, out="nxn_out/", **kw)
+    assert got == exp, (seed, kw)
+    a = {p.name: p.read_bytes() for p in (tmp_path / "flow_out").glob("*.bv")}
+    b = {p.name: p.read_bytes() for p in (tmp_path / "nxn_out").glob("*.bv")}
+    assert a.keys() == b.keys() and len(a) > 0
+    for name in a:
+        # the comments embed the output directory only through the file paths given in the config: identical here
+        assert a[name] == b[name], (seed, name)
+    pat = re.compile(r"\[indexed \d+, searched \d+, shared \d+\]")
+    for lg in (tmp_path / "flow_out").glob("*.log"):
+        assert pat.search(lg.read_text()).group(0) == pat.search((tmp_path / "nxn_out" / lg.name).read_text()).group(0), lg.name
+
+
+def test_commet_nxn_multi_gpu_matches_single(bin_dir, tmp_path):
+    """rounds spread over every visible GPU give the files of the single-GPU run"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    fixtures.materialize(tmp_path)
+    one = _nxn(bin_dir, tmp_path, "ABCDE_bench/five_sets.txt", out="one/", gpus=1, k=32)
+    many = _nxn(bin_dir, tmp_path, "ABCDE_bench/five_sets.txt", out="many/", k=32)
+    assert one == many == GOLDEN["abcde_5sets_k32"]["csv"]
+    a = {p.name: sha(p) for p in (tmp_path / "one").glob("*.bv")}
+    b = {p.name: sha(p) for p in (tmp_path / "many").glob("*.bv")}
+    assert a == b == GOLDEN["abcde_5sets_k32"]["bv"]
+
+
+def test_python_float_formatting_of_matrices(bin_dir, tmp_path):
+    """CSV numbers are Python 3 str(float): exponent form below 1e-4, shortest round-trip digits"""
+    rng = np.random.default_rng(5)
+    big = [H.random_read(rng, 40).tobytes() for _ in range(30011)]
+    H.write_fasta(tmp_path / "big.fa", big)
+    H.write_fasta(tmp_path / "small.fa", [big[7], big[123], H.random_read(rng, 40).tobytes()])
+    (tmp_path / "c.txt").write_text("big:big.fa\nsmall:small.fa\n")
+    got = _nxn(bin_dir, tmp_path, "c.txt", out="o/", k=20, t=1)
+    rows = [ln.split(";") for ln in got["percentage"].strip().split("\n")]
+    shared = [ln.split(";") for ln in got["plain"].strip().split("\n")]
+    c, n = int(shared[1][2]), int(shared[1][1])
+    assert c == 2 and n == 30011
+    assert rows[1][2] == str(100 * c / float(n)) and "e-" not in rows[1][2]
+    norm = [ln.split(";") for ln in got["normalized"].strip().split("\n")]
+    assert norm[1][2] == str(100 * (c + int(shared[2][1])) / float(n + 3))
