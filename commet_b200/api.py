@@ -47,6 +47,7 @@ _SIGS = {
     "commet_reads_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "commet_reads_from_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
                                            C.POINTER(C.c_void_p)]),
+    "commet_reads_clone": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "commet_reads_free": (None, [C.c_void_p]),
     "commet_reads_count": (C.c_uint64, [C.c_void_p]),
     "commet_reads_bases": (C.c_uint64, [C.c_void_p]),

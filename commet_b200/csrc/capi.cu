@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace commet;
@@ -146,6 +147,10 @@ struct commet_ctx {
     uint64_t recs_cap = 0;            // capacity in records
     unsigned long long *bins = nullptr;   // hist[512] | base[513] | cursor[512] | tile counter
     Arena arena;                      // cached device temporaries (see Arena)
+    // pinned bounce ring for H2D copies out of pageable host memory (see h2d_copy)
+    uint8_t *bounce[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t bounce_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned bounce_next = 0;
 };
 
 struct commet_reads {
@@ -252,6 +257,10 @@ extern "C" void commet_ctx_destroy(commet_ctx *c)
     if (c->recs) cudaFree(c->recs);
     if (c->bins) cudaFree(c->bins);
     for (Arena::Block &b : c->arena.blocks) cudaFree(b.p);
+    for (int i = 0; i < 4; i++) {
+        if (c->bounce[i]) cudaFreeHost(c->bounce[i]);
+        if (c->bounce_done[i]) cudaEventDestroy(c->bounce_done[i]);
+    }
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
@@ -343,6 +352,49 @@ static bool queueable(const void *p)
     return a.type != cudaMemoryTypeUnregistered;
 }
 
+// H2D copy on the copy stream.  Page-locked sources are handed to the DMA engine as they are.  Pageable sources
+// go through a ring of four pinned 32 MB buffers owned by the context: the host thread fills slot i+1 while the
+// DMA engine drains slot i.  (cudaMemcpyAsync on pageable memory does the same inside the driver, at a measured
+// ~3 GB/s; pinning the whole source first costs ~0.5 s per GB.)
+static void host_copy(uint8_t *dst, const uint8_t *src, uint64_t len)
+{
+    // one core moves ~4 GB/s out of pageable memory on the hosts measured; four keep the DMA engine busier
+    constexpr int kThreads = 4;
+    if (len < (8u << 20)) { memcpy(dst, src, len); return; }
+    std::thread th[kThreads - 1];
+    const uint64_t per = (len / kThreads + 4095) & ~4095ull;
+    for (int i = 1; i < kThreads; i++) {
+        const uint64_t a = std::min(len, per * i), b = std::min(len, per * (i + 1));
+        th[i - 1] = std::thread([=]() { if (b > a) memcpy(dst + a, src + a, b - a); });
+    }
+    memcpy(dst, src, std::min(len, per));
+    for (auto &t : th) t.join();
+}
+
+static int h2d_copy(commet_ctx *c, void *dst, const void *src, uint64_t bytes, bool pinned_src)
+{
+    if (bytes == 0) return 0;
+    if (pinned_src) {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        return 0;
+    }
+    if (!c->bounce[0]) {
+        for (int i = 0; i < 4; i++) {
+            CK(cudaHostAlloc((void **)&c->bounce[i], kUploadChunk, cudaHostAllocDefault));
+            CK(cudaEventCreateWithFlags(&c->bounce_done[i], cudaEventDisableTiming));
+        }
+    }
+    for (uint64_t off = 0; off < bytes; off += kUploadChunk) {
+        const uint64_t len = std::min<uint64_t>(kUploadChunk, bytes - off);
+        const unsigned slot = c->bounce_next++ & 3u;
+        CK(cudaEventSynchronize(c->bounce_done[slot]));        // never-recorded events are complete
+        host_copy(c->bounce[slot], static_cast<const uint8_t *>(src) + off, len);
+        CK(cudaMemcpyAsync(static_cast<uint8_t *>(dst) + off, c->bounce[slot], len, cudaMemcpyHostToDevice, c->copy_stream));
+        CK(cudaEventRecord(c->bounce_done[slot], c->copy_stream));
+    }
+    return 0;
+}
+
 // copy stream: offsets, then the bases in chunks with one arrival event each
 static int enqueue_copies(commet_ctx *c, commet_reads *r)
 {
@@ -356,11 +408,12 @@ static int enqueue_copies(commet_ctx *c, commet_reads *r)
     CK(cudaEventRecord(ready, c->stream));
     CK(cudaStreamWaitEvent(c->copy_stream, ready, 0));
     c->ev_pool.push_back(ready);
-    CK(cudaMemcpyAsync(r->offs, offs, (r->n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->copy_stream));
+    CKR(h2d_copy(c, r->offs, offs, (r->n_reads + 1) * sizeof(uint64_t), queueable(offs)));
     r->chunk_words = kUploadChunk / 32;
+    const bool pinned_bases = r->n_bases == 0 || queueable(bases);
     for (uint64_t b = 0; b < r->n_bases || b == 0; b += kUploadChunk) {
         uint64_t len = std::min(kUploadChunk, r->n_bases - b);
-        if (len) CK(cudaMemcpyAsync(r->ascii + b, bases + b, len, cudaMemcpyHostToDevice, c->copy_stream));
+        if (len) CKR(h2d_copy(c, r->ascii + b, bases + b, len, pinned_bases));
         cudaEvent_t e;
         CKR(take_event(c, &e));
         CK(cudaEventRecord(e, c->copy_stream));
@@ -468,6 +521,29 @@ extern "C" int commet_reads_from_device(commet_ctx *c, const uint8_t *d_bases, c
         if (rc == 0) CK(cudaStreamSynchronize(c->stream));
     }
     if (rc != 0) { commet_reads_free(r); return rc; }
+    *out = r;
+    return 0;
+}
+
+// A staged stream copied to another GPU of the same process over NVLink (cudaMemcpyPeerAsync): the planes are
+// half a byte per base, so a set that was parsed, uploaded and encoded once reaches every other GPU at peer
+// bandwidth instead of crossing PCIe again.  The H/L/V planes are immutable once encoded; the W plane and the
+// selection are per-copy state (the clone starts with every read selected and no W plane).
+extern "C" int commet_reads_clone(commet_ctx *c, const commet_reads *src, commet_reads **out)
+{
+    if (!c || !src || !out || !src->ctx) return fail("commet_reads_clone: null argument");
+    if (src->ascii || !src->chunk_ev.empty()) return fail("commet_reads_clone: the source stream is still being uploaded");
+    CKR(set_device(c));
+    commet_reads *r = nullptr;
+    CKR(reads_alloc(c, src->n_reads, src->n_bases, &r));
+    cudaError_t e = cudaMemcpyPeerAsync(r->planes, c->device, src->planes, src->ctx->device, (src->n_words + 4) * sizeof(uint4), c->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyPeerAsync(r->offs, c->device, src->offs, src->ctx->device, (src->n_reads + 1) * sizeof(uint64_t), c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        commet_reads_free(r);
+        return fail("peer copy of a staged stream failed: %s", cudaGetErrorString(e));
+    }
     *out = r;
     return 0;
 }

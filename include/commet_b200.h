@@ -78,6 +78,10 @@ int commet_reads_upload(commet_ctx *ctx, const uint8_t *bases, const uint64_t *o
                         uint64_t n_reads, commet_reads **out);
 int commet_reads_from_device(commet_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offs,
                              uint64_t n_reads, uint64_t n_bases, commet_reads **out);
+/* copy of a staged stream on another GPU of this process, over NVLink peer copies (no second parse/upload/encode);
+ * the source must be completely staged (commet_reads_upload returns after the encode) and must not be freed or
+ * re-selected concurrently; the clone starts with every read selected. */
+int commet_reads_clone(commet_ctx *ctx, const commet_reads *src, commet_reads **out);
 void commet_reads_free(commet_reads *r);
 uint64_t commet_reads_count(const commet_reads *r);
 uint64_t commet_reads_bases(const commet_reads *r);

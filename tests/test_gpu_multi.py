@@ -94,4 +94,4 @@ def test_sharded_index_merge_search_two_gpus(tmp_path, k, t, maxk, seed):
     assert indexed == e["indexed"]
     assert np.array_equal(np.load(tmp_path / "filt0.npy"), np.load(tmp_path / "filt1.npy"))
     if maxk:
-        assert e["chunks"] > 2
+        assert e["chunks"] >= 2

@@ -24,3 +24,48 @@ def test_py_float_matches_python_str(tmp_path):
                          text=True, check=True).stdout.split("\n")
     bad = [(v, o) for v, o in zip(vals, out) if o != str(v)]
     assert not bad, bad[:5]
+
+
+def test_parallel_fasta_loader_equals_sequential_reader(tmp_path):
+    """fast_fasta.hpp (mmap, chunked, two passes) yields the records of readers.hpp's parse_fasta -- the restatement of
+    the reference's FastaFile -- for any chunk size: multi-line records, blank lines, CR, '>' inside lines, no final newline."""
+    import numpy as np
+    from tests import helpers as H
+    host = ROOT / "commet_b200" / "csrc" / "host"
+    (tmp_path / "h.cpp").write_text(r'''
+#include "fast_fasta.hpp"
+#include "readers.hpp"
+#include <cstdio>
+#include <cstdlib>
+using namespace commet_host;
+int main(int argc, char **argv) {
+    ParsedFile pf;
+    if (!parse_reads_file(argv[1], pf, "x")) return 2;
+    FastaMap m;
+    if (!m.open(argv[1], (size_t)atol(argv[2]))) return 3;
+    for (size_t c = 0; c < m.n_chunks(); c++) m.pass<false>(c, nullptr, 0, nullptr, 0);
+    m.finish_scan();
+    if (m.n_records != pf.nb_reads || m.n_bytes != pf.seq.size()) { printf("counts %lu %lu vs %lu %lu\n", (unsigned long)m.n_records, (unsigned long)m.n_bytes, (unsigned long)pf.nb_reads, (unsigned long)pf.seq.size()); return 1; }
+    std::vector<uint8_t> seq(m.n_bytes + 1);
+    std::vector<uint64_t> off(m.n_records + 1, 0);
+    off[m.n_records] = m.n_bytes;
+    uint64_t pos = 0, rec = 0;
+    for (size_t c = 0; c < m.n_chunks(); c++) { m.pass<true>(c, seq.data(), pos, off.data(), rec); pos += m.bytes[c]; rec += m.records[c]; }
+    seq.resize(m.n_bytes);
+    if (seq != pf.seq || off != pf.off) { puts("content differs"); return 1; }
+    printf("ok %lu records %lu chunks\n", (unsigned long)m.n_records, (unsigned long)m.n_chunks());
+    return 0;
+}''')
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", str(host), "-o", str(tmp_path / "h"), str(tmp_path / "h.cpp"), "-lz"], check=True)
+    rng = np.random.default_rng(3)
+    for case in range(12):
+        reads = H.make_ref_set(rng, int(rng.integers(1, 400)), 1, int(rng.integers(2, 300)), p_N=0.02, p_lower=0.2)
+        if case % 3 == 0:
+            reads = [r.replace(b"C", b">", 1) if i % 5 == 0 and len(r) > 3 and not r.startswith(b"C") else r for i, r in enumerate(reads)]
+        p = H.write_fasta(tmp_path / f"c{case}.fa", reads, width=[None, 7, 60, 13][case % 4], final_newline=case % 2 == 0,
+                          blank_every=[0, 3, 1][case % 3])
+        if case % 4 == 3:
+            p.write_bytes(p.read_bytes().replace(b"\n", b"\r\n", 5))
+        for chunk in (16, 64, 1000, 1 << 20):
+            r = subprocess.run([str(tmp_path / "h"), str(p), str(chunk)], capture_output=True, text=True)
+            assert r.returncode == 0, (case, chunk, r.stdout)
