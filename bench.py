@@ -389,7 +389,8 @@ def main():
         idx.free(); q.free()
         return int(counters_d[0])
 
-    step_e2e()
+    for _ in range(max(1, args.warmup)):
+        step_e2e()
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))

@@ -88,8 +88,10 @@ struct Arena {
     {
         const size_t want = round_up(bytes);
         int best = -1;
-        for (size_t i = 0; i < blocks.size(); i++)          // best fit, but never waste more than half a block
-            if (!blocks[i].used && blocks[i].cap >= want && blocks[i].cap <= 2 * want + (1u << 20) &&
+        for (size_t i = 0; i < blocks.size(); i++)          // best fit, but never waste more than a fifth of a block:
+            // a loose fit lets a small request take the block a later, larger request was sized for, and the
+            // cache keeps re-shuffling (and calling cudaMalloc) for several calls before it settles
+            if (!blocks[i].used && blocks[i].cap >= want && blocks[i].cap <= want + want / 4 + (1u << 20) &&
                 (best < 0 || blocks[i].cap < blocks[best].cap))
                 best = (int)i;
         if (best >= 0) {
@@ -534,6 +536,16 @@ extern "C" int commet_reads_clone(commet_ctx *c, const commet_reads *src, commet
     if (!c || !src || !out || !src->ctx) return fail("commet_reads_clone: null argument");
     if (src->ascii || !src->chunk_ev.empty()) return fail("commet_reads_clone: the source stream is still being uploaded");
     CKR(set_device(c));
+    if (src->ctx->device != c->device) {
+        // direct NVLink path; without peer access the copy is staged through host memory (PCIe twice)
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, c->device, src->ctx->device) == cudaSuccess && can) {
+            cudaError_t pe = cudaDeviceEnablePeerAccess(src->ctx->device, 0);
+            if (pe != cudaSuccess) cudaGetLastError();      // already enabled: fine
+        } else {
+            cudaGetLastError();
+        }
+    }
     commet_reads *r = nullptr;
     CKR(reads_alloc(c, src->n_reads, src->n_bases, &r));
     cudaError_t e = cudaMemcpyPeerAsync(r->planes, c->device, src->planes, src->ctx->device, (src->n_words + 4) * sizeof(uint4), c->stream);

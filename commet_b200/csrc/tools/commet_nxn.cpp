@@ -589,7 +589,10 @@ int main(int argc, char **argv)
     std::vector<std::vector<uint64_t>> shared(N, std::vector<uint64_t>(N, 0));
     std::mutex res_mu;
 
-    struct Task { int kind, i, j; };               // kind 0: "all in Si"; 1: the two refinement rounds of pair (i, j)
+    // kind 0: "all in Si" for the query sets [j, j + nj) ; kind 1: the two refinement rounds of pair (i, j).
+    // With several GPUs an "all in Si" round is cut into slices of a few query sets (Si is indexed once per slice):
+    // one call over all N-1-i query sets would be the critical path of the whole run.
+    struct Task { int kind, i, j, nj; };
     std::deque<Task> ready;
     std::mutex q_mu;
     std::condition_variable q_cv;
@@ -605,14 +608,15 @@ int main(int argc, char **argv)
                 if (!seen.insert("file:" + basename_of(f.path)).second) unique_names = false;
         }
     }
-    auto run_all_in = [&](Driver::Worker &w, int i) {
+    auto run_all_in = [&](Driver::Worker &w, int i, int j0, int nj) {
         Round r;
         r.index_set = i;
         r.index_bvs = filter_bvs(i);
-        for (int j = i + 1; j < N; j++) { r.query_sets.push_back(j); r.query_bvs.push_back(filter_bvs(j)); }
+        for (int j = j0; j < j0 + nj; j++) { r.query_sets.push_back(j); r.query_bvs.push_back(filter_bvs(j)); }
         r.write_logs = false;                     // overwritten by the third round of every pair
         RoundOut o = d.run_round(w, r);
-        d.say("  all in " + d.sets[i].name + ": " + std::to_string(o.chunks) + " chunk(s), " + std::to_string(o.total_s * 1e3) + " ms on GPU " + std::to_string(w.device));
+        d.say("  sets " + std::to_string(j0) + ".." + std::to_string(j0 + nj - 1) + " in " + d.sets[i].name + ": " + std::to_string(o.chunks) +
+              " chunk(s), " + std::to_string(o.total_s * 1e3) + " ms on GPU " + std::to_string(w.device));
     };
     auto run_pair = [&](Driver::Worker &w, int i, int j) {
         Round b;                                   // Si in (Sj in Si)
@@ -639,11 +643,13 @@ int main(int argc, char **argv)
     if (!unique_names || d.workers.size() == 1) {
         Driver::Worker &w = d.workers[0];
         for (int i = 0; i + 1 < N; i++) {
-            run_all_in(w, i);
+            run_all_in(w, i, i + 1, N - 1 - i);
             for (int j = i + 1; j < N; j++) run_pair(w, i, j);
         }
     } else {
-        for (int i = 0; i + 1 < N; i++) ready.push_back({0, i, 0});
+        const int slice = std::max(1, (N + 2) / 4);
+        for (int i = 0; i + 1 < N; i++)
+            for (int j = i + 1; j < N; j += slice) ready.push_back({0, i, j, std::min(slice, N - j)});
         outstanding = (int)ready.size();
         std::vector<std::thread> th;
         for (size_t g = 0; g < d.workers.size(); g++)
@@ -663,12 +669,12 @@ int main(int argc, char **argv)
                         t = ready[pick];
                         ready.erase(ready.begin() + (std::ptrdiff_t)pick);
                     }
-                    if (t.kind == 0) run_all_in(w, t.i);
+                    if (t.kind == 0) run_all_in(w, t.i, t.j, t.nj);
                     else run_pair(w, t.i, t.j);
                     {
                         std::lock_guard<std::mutex> lk(q_mu);
                         if (t.kind == 0)
-                            for (int j = t.i + 1; j < N; j++) { ready.push_back({1, t.i, j}); outstanding++; }
+                            for (int j = t.j; j < t.j + t.nj; j++) { ready.push_back({1, t.i, j, 1}); outstanding++; }
                         outstanding--;
                     }
                     q_cv.notify_all();
@@ -734,8 +740,14 @@ int main(int argc, char **argv)
     }
     d.say("commet_nxn: done in " + std::to_string(std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count()) + " s; matrices in " + opt.out_dir);
     // every output is on disk: leave without tearing down gigabytes of device and host allocations one by one
-    // (measured: 0.3 s on one GPU, 2 s on two)
     std::cout.flush();
     std::cerr.flush();
+    if (const char *e = getenv("COMMET_NXN_EXIT")) {          // A/B of the ways out (diagnostic)
+        if (!strcmp(e, "return")) return 0;
+        if (!strcmp(e, "destroy")) {
+            for (Driver::Worker &w : d.workers) commet_ctx_destroy(w.ctx);
+            _exit(0);
+        }
+    }
     _exit(0);
 }
