@@ -252,9 +252,12 @@ struct Driver {
             from = owner[s];
             if (from == -1) owner[s] = -2;
         }
+        auto t0 = std::chrono::steady_clock::now();
         if (from >= 0) {
             if (commet_reads_clone(w.ctx, workers[from].staged[s], &w.staged[s]) != 0)
                 die(std::string("cloning set ") + set.name + ": " + commet_last_error());
+            say("  set " + set.name + " cloned GPU " + std::to_string(from) + " -> GPU " + std::to_string(w.device) + " in " +
+                std::to_string(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()) + " ms");
         } else {
             static const uint8_t none = 0;
             if (commet_reads_upload(w.ctx, set.n_bases ? set.bases : &none, set.offs.data(), set.n_records(), &w.staged[s]) != 0)
@@ -264,6 +267,8 @@ struct Driver {
                 owner[s] = w.device;
             }
             stage_cv.notify_all();
+            say("  set " + set.name + " uploaded to GPU " + std::to_string(w.device) + " in " +
+                std::to_string(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()) + " ms");
         }
         return w.staged[s];
     }
