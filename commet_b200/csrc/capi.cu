@@ -142,6 +142,7 @@ struct commet_ctx {
     unsigned long long *scratch = nullptr;   // kScratch u64 of device counters
     uint64_t launches = 0;
     bool count_probes = false;        // instrumented search kernel (reference-semantics probe counts)
+    bool search_both = true;          // both strands in one pass (scan_both); false: forward scan, then reverse (A/B)
     bool binned_index = true;         // L2-blocked insert for DRAM-resident filters
     bool region_passes = false;       // ... by region passes over the stream (false, default: sort keys by region first)
     int region_log2 = 26;             // bytes of filter one pass covers
@@ -241,6 +242,7 @@ extern "C" int commet_ctx_create(int device, commet_ctx **out)
         if (const char *e = getenv("COMMET_B200_L2_FETCH")) gran = (size_t)atoi(e);
         if (gran) { if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) cudaGetLastError(); }
     }
+    if (const char *e = getenv("COMMET_B200_SEARCH_BOTH")) c->search_both = atoi(e) != 0;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&c->scratch, kScratch * sizeof(unsigned long long)));
@@ -984,9 +986,11 @@ static int search_launch(commet_ctx *c, commet_reads *r, int k, int t, uint32_t 
     CKR(prepare(c, r, k));
     unsigned g = grid_for(c, r->n_reads, 256, 8);
     if (c->count_probes)
-        k_search<true><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
+        k_search<true, false><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
+    else if (c->search_both)
+        k_search<false, true><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
     else
-        k_search<false><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
+        k_search<false, false><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
     c->launches++;
     CK(cudaGetLastError());
     return 0;

@@ -762,10 +762,99 @@ __device__ __forceinline__ bool scan_strand(const uint32_t *__restrict__ filter,
     return false;
 }
 
+// Both strands of search_reads in ONE left-to-right pass.  The reference scans the forward strand to the end
+// before it looks at the reverse-complement keys (search_reads.h:46-83); the tag it sets is
+// "forward greedy count >= t OR reverse greedy count >= t", which does not depend on the order the two scans are
+// evaluated in.  Both scans walk the same windows of the same planes (rv_add also goes left to right,
+// hash_key.h:99-125), so as long as neither strand has a hit the lane probes a window's forward AND reverse
+// a-keys together (2 x kSearchBatch independent DRAM probes in flight).  The first hit FOCUSES the scan on its
+// strand: that strand alone follows its k-jumps (search_reads.h:53-60) to the end of the read; only if it ends
+// below t hits does the other strand resume where it stopped.  A reverse-complement copy is then found after a
+// few batches instead of after a full fruitless forward scan, and a forward copy wastes one batch of reverse
+// probes.  Each strand keeps its own hit count and its own next position, so every strand's greedy count is
+// exactly the reference's.
+__device__ __forceinline__ bool scan_both(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
+                                          uint64_t o, uint32_t npos, int k, int t, uint64_t mask)
+{
+    constexpr int U = kSearchBatch;
+    uint64_t wi = o >> 5;
+    uint4 q0 = planes[wi], q1 = planes[wi + 1], q2 = planes[wi + 2];
+    int seen_f = 0, seen_r = 0;
+    uint32_t nf = 0, nr = 0;                         // next position of each strand (>= npos: strand finished)
+    int focus = 0;                                   // 0: both strands, 1: forward only, 2: reverse only
+    unsigned int dummy = 0;
+    while (true) {
+        const bool use_f = focus != 2 && nf < npos, use_r = focus != 1 && nr < npos;
+        if (!use_f && !use_r) {
+            if (focus == 0) return false;            // both strands scanned to the end
+            focus = 0;                               // the focused strand ended below t: the other one resumes
+            continue;
+        }
+        const uint32_t p = use_f && use_r ? (nf < nr ? nf : nr) : (use_f ? nf : nr);
+        uint64_t b = o + p;
+        uint64_t need = b >> 5;
+        if (need != wi) {
+            if (need < wi || need - wi >= 3) {       // a resumed strand may be behind the window
+                wi = need;
+                q0 = planes[wi]; q1 = planes[wi + 1]; q2 = planes[wi + 2];
+            } else {
+                do {
+                    q0 = q1; q1 = q2; q2 = planes[wi + 3]; wi++;
+                } while (wi != need);
+            }
+        }
+        uint32_t sh = (uint32_t)b & 31u;
+        uint32_t rem = npos - p;
+        uint32_t wv = __funnelshift_r(q0.w, q1.w, sh);
+        uint32_t m = wv & ((rem >= (uint32_t)U) ? ((1u << U) - 1u) : ((1u << rem) - 1u));
+        if (m == 0) {
+            // no k-mer starts in this batch: both active strands jump to the next W bit among the 32 visible ones
+            uint32_t vis = rem < 32u ? rem : 32u;
+            uint32_t mv = (vis >= 32u) ? wv : (wv & ((1u << vis) - 1u));
+            const uint32_t to = p + (mv ? (uint32_t)(__ffs(mv) - 1) : vis);
+            if (use_f && nf < to) nf = to;
+            if (use_r && nr < to) nr = to;
+            continue;
+        }
+        // positions of this batch each strand still has to look at
+        const uint32_t mf = !use_f || nf >= p + U ? 0u : (nf > p ? (m & (~0u << (nf - p))) : m);
+        const uint32_t mr = !use_r || nr >= p + U ? 0u : (nr > p ? (m & (~0u << (nr - p))) : m);
+        uint64_t hv = window64(q0.x, q1.x, q2.x, sh);
+        uint64_t lv = window64(q0.y, q1.y, q2.y, sh);
+        uint32_t af[U], ar[U];
+        uint64_t kf[U], kr[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            kf[u] = __brevll(hv >> u) >> (64 - k);
+            kr[u] = ~(hv >> u) & mask;
+            af[u] = ar[u] = 0;
+            if ((mf >> u) & 1u) af[u] = ld_probe_u32(filter + key_word(kf[u]));
+            if ((mr >> u) & 1u) ar[u] = ld_probe_u32(filter + key_word(kr[u]));
+        }
+        bool hit_f = false, hit_r = false;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!hit_f && ((mf >> u) & 1u) && (af[u] & key_bit(kf[u], 0))) {
+                Keys q = make_keys(hv >> u, lv >> u, k, mask, false);
+                if (probe_bcd(filter, q, dummy)) { hit_f = true; seen_f++; nf = p + (uint32_t)u + (uint32_t)k; }
+            }
+            if (!hit_r && ((mr >> u) & 1u) && (ar[u] & key_bit(kr[u], 0))) {
+                Keys q = make_keys(hv >> u, lv >> u, k, mask, true);
+                if (probe_bcd(filter, q, dummy)) { hit_r = true; seen_r++; nr = p + (uint32_t)u + (uint32_t)k; }
+            }
+        }
+        // `seen >= t` is only looked at after a hit (search_reads.h:55-57): t <= 1 behaves as t = 1
+        if ((hit_f && seen_f >= t) || (hit_r && seen_r >= t)) return true;
+        if (use_f && !hit_f && nf < p + U) nf = p + U;      // this batch is settled for a strand without a hit
+        if (use_r && !hit_r && nr < p + U) nr = p + U;
+        if (focus == 0) focus = hit_f ? 1 : (hit_r ? 2 : 0);
+    }
+}
+
 // search_reads (search_reads.h:34-87): one lane per read, grid-stride.
 // counters[0] += newly found, counters[1] += reads scanned; with COUNT also
 // counters[2] += filter byte tests, counters[3] += k-mer lookups (reference semantics).
-template <bool COUNT>
+template <bool COUNT, bool BOTH>
 __global__ void __launch_bounds__(256)
 k_search(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
          const uint64_t *__restrict__ offs, uint64_t n_reads, int k, int t,
@@ -783,8 +872,13 @@ k_search(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
         uint64_t len = offs[r + 1] - o;
         if (len < (uint64_t)k) continue;
         uint32_t npos = (uint32_t)(len - k + 1);
-        bool f = scan_strand<COUNT>(filter, planes, o, npos, k, t, mask, false, tests, lookups);
-        if (!f) f = scan_strand<COUNT>(filter, planes, o, npos, k, t, mask, true, tests, lookups);
+        bool f;
+        if (COUNT || !BOTH) {      // the reference's order: forward scan, then reverse (what the probe counters describe)
+            f = scan_strand<COUNT>(filter, planes, o, npos, k, t, mask, false, tests, lookups);
+            if (!f) f = scan_strand<COUNT>(filter, planes, o, npos, k, t, mask, true, tests, lookups);
+        } else {
+            f = scan_both(filter, planes, o, npos, k, t, mask);
+        }
         if (f) {
             atomicOr(&tags[r >> 5], 1u << (r & 31));
             found++;

@@ -119,6 +119,33 @@ def test_search_against_reference_built_filter(ctx, seed):
     assert (found, searched) == (st["found"], st["searched"])
 
 
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7, 27, 31, 32, 33, 34, 35])
+def test_search_small_and_large_k(ctx, k):
+    """k below the probe batch (the k-jump after a hit lands inside the batch that found it) and k up to the 61-base
+    limit, t = 0..3, reads shorter than k, both the one-pass two-strand scan and the reference-order scan
+    (probe counting on) against the oracle (k <= 24; above that the two scans are compared with each other).  Low-complexity references keep small-k filters from saturating."""
+    rng = np.random.default_rng(300 + k)
+    L = max(3 * k, 12)
+    alphabet = np.frombuffer(b"AC" if k < 8 else b"ACGT", dtype=np.uint8)
+    ref = [alphabet[rng.integers(0, len(alphabet), size=int(rng.integers(max(1, k - 2), L)))].tobytes() for _ in range(40 if k < 28 else 300)]
+    qry = H.make_query_set(rng, ref, 300, max(1, k - 3), L, frac_shared=0.5, sub_rate=0.05, p_N=0.03)
+    for t in range(0, 4):
+        if k <= 24:
+            exp_tags, exp = oracle.index_and_search(k, t, H.to_stream(ref), [H.to_stream(qry)], 1 << 60)
+        for count in (False, True):
+            ctx.count_probes(count)
+            tags, info = ctx.index_and_search(k, t, H.to_stream(ref), [H.to_stream(qry)], 1 << 60)
+            if k <= 24:
+                assert np.array_equal(tags[0], oracle.tags_to_bv(exp_tags[0])), (k, t, count)
+                assert info["shared"] == exp["shared"]
+            if count:
+                ref_order = tags[0].copy()
+            else:
+                one_pass = tags[0].copy()
+        ctx.count_probes(False)
+        assert np.array_equal(one_pass, ref_order), (k, t)        # the two scan orders agree at every k
+
+
 @pytest.mark.parametrize("seed", range(30))
 def test_index_and_search_chunk_loop(ctx, seed):
     """Full chunk loop incl. the dropped read at every chunk boundary and the log counters."""
