@@ -142,7 +142,7 @@ struct commet_ctx {
     unsigned long long *scratch = nullptr;   // kScratch u64 of device counters
     uint64_t launches = 0;
     bool count_probes = false;        // instrumented search kernel (reference-semantics probe counts)
-    bool search_both = true;          // both strands in one pass (scan_both); false: forward scan, then reverse (A/B)
+    int search_both = 4;              // both strands in one pass, this many positions per strand and batch (scan_both); 0: forward scan, then reverse (A/B)
     bool binned_index = true;         // L2-blocked insert for DRAM-resident filters
     bool region_passes = false;       // ... by region passes over the stream (false, default: sort keys by region first)
     int region_log2 = 26;             // bytes of filter one pass covers
@@ -178,6 +178,7 @@ struct commet_reads {
 
 namespace {
 
+constexpr unsigned kGridBps = 8;       // blocks per SM of the streaming kernels' grids (see grid_for)
 constexpr int kScratch = 256;         // [0,128): 4 counters per query set; [128,256): misc
 constexpr int kMaxSets = 30;
 
@@ -191,8 +192,19 @@ struct DevBuf {                       // scoped, stream-ordered device temporary
     template <class T> T *as() { return static_cast<T *>(p); }
 };
 
+inline unsigned env_or(const char *name, unsigned dflt)
+{
+    const char *e = getenv(name);
+    return e && atoi(e) > 0 ? (unsigned)atoi(e) : dflt;
+}
+
+// Grid of a grid-stride kernel.  The SMs of a B200 do not all see the same memory bandwidth/latency (two dies), so
+// a grid of exactly one resident wave -- every block an equal, static share -- finishes with its slowest SM
+// (measured on random DRAM loads: 37.9 G/s with <= 8 blocks per SM, 49.7 G/s with 64).  Several waves of smaller
+// shares let the hardware scheduler even it out.
 inline unsigned grid_for(const commet_ctx *c, uint64_t items, unsigned block, unsigned blocks_per_sm)
 {
+    if (blocks_per_sm == 8) blocks_per_sm = env_or("COMMET_B200_GRID_BPS", kGridBps);
     uint64_t need = (items + block - 1) / block;
     uint64_t cap = (uint64_t)c->sm_count * blocks_per_sm;
     if (need < 1) need = 1;
@@ -242,7 +254,7 @@ extern "C" int commet_ctx_create(int device, commet_ctx **out)
         if (const char *e = getenv("COMMET_B200_L2_FETCH")) gran = (size_t)atoi(e);
         if (gran) { if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) cudaGetLastError(); }
     }
-    if (const char *e = getenv("COMMET_B200_SEARCH_BOTH")) c->search_both = atoi(e) != 0;
+    if (const char *e = getenv("COMMET_B200_SEARCH_BOTH")) c->search_both = atoi(e);
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&c->scratch, kScratch * sizeof(unsigned long long)));
@@ -820,12 +832,12 @@ static int index_range_binned(commet_ctx *c, commet_reads *r, uint64_t b0, uint6
         unsigned g = grid_for(c, s1 - s0 + 32, 256, 8);
         if (n_bins <= 128) {     // pair table: n_bins^2 + n_bins counters of dynamic shared memory
             const size_t sh = ((size_t)n_bins * n_bins + n_bins) * sizeof(unsigned int);
-            k_bin_count<true><<<std::min(g, (unsigned)c->sm_count * 3), 256, sh, c->stream>>>(r->planes, s0, s1, k, n_bins, hist);
+            k_bin_count<true><<<std::min(g, (unsigned)c->sm_count * env_or("COMMET_B200_COUNT_BPS", 3)), 256, sh, c->stream>>>(r->planes, s0, s1, k, n_bins, hist);
         } else
             k_bin_count<false><<<g, 256, n_bins * sizeof(unsigned int), c->stream>>>(r->planes, s0, s1, k, n_bins, hist);
         k_bin_scan<<<1, 32, 0, c->stream>>>(hist, n_bins, base, cursor, tile_counter);
         uint64_t n_tiles = (((s1 + 31) >> 5) - (s0 >> 5) + kScatTileWords - 1) / kScatTileWords;
-        unsigned gs = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * 2);
+        unsigned gs = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * env_or("COMMET_B200_SCATTER_BPS", 2));
         k_bin_scatter<<<gs, kScatThreads, sizeof(ScatterSmem), c->stream>>>(r->planes, s0, s1, k, n_bins, cursor, c->recs);
         {
             int tile = 2048, bps = 8, pf = 1;
@@ -984,13 +996,30 @@ static int search_launch(commet_ctx *c, commet_reads *r, int k, int t, uint32_t 
     if (c->k != k || !c->filter) return fail("commet_search: no filter for k=%d (current k=%d)", k, c->k);
     if (r->n_reads == 0) return 0;
     CKR(prepare(c, r, k));
-    unsigned g = grid_for(c, r->n_reads, 256, 8);
+    // One read per thread (up to 512 blocks per SM): the cost of a read varies from a dozen probes (a copy, found
+    // at once) to 2(L-k+1) (no k-mer in common), and a grid-stride loop over a grid of 8 blocks per SM left the
+    // SMs unevenly loaded (measured: 27.4 ms with 1184 blocks, 22.8 ms with 9472, same kernel).
+    unsigned bps = 512;
+    if (const char *e = getenv("COMMET_B200_SEARCH_BPS")) bps = (unsigned)atoi(e);
+    unsigned g = grid_for(c, r->n_reads, 256, bps);
     if (c->count_probes)
-        k_search<true, false><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
+        k_search<true, 0><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
+    else if (c->search_both == 2)
+        k_search<false, 2><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
+    else if (c->search_both == 3)
+        k_search<false, 3><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
+    else if (c->search_both == 5)
+        k_search<false, 5><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
+    else if (c->search_both == 6)
+        k_search<false, 6><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
+    else if (c->search_both == 7)
+        k_search<false, 7><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
+    else if (c->search_both == 8)
+        k_search<false, 8><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
     else if (c->search_both)
-        k_search<false, true><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
+        k_search<false, 4><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
     else
-        k_search<false, false><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
+        k_search<false, 0><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -1542,7 +1571,7 @@ extern "C" int commet_bench_random_sectors(commet_ctx *c, uint64_t bytes, uint64
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    unsigned g = grid_for(c, n_ops / 4, 256, 8);
+    unsigned g = grid_for(c, n_ops / 4, 256, 64);  // several waves: see grid_for
     for (int rep = 0; rep < 2; rep++) {          // first pass warms up, second is timed
         if (rep == 1) CK(cudaEventRecord(e0, c->stream));
         if (atomic_or) k_random_sectors<true><<<g, 256, 0, c->stream>>>(buf.as<uint32_t>(), mask, n_ops, c->scratch + 144);

@@ -773,10 +773,10 @@ __device__ __forceinline__ bool scan_strand(const uint32_t *__restrict__ filter,
 // few batches instead of after a full fruitless forward scan, and a forward copy wastes one batch of reverse
 // probes.  Each strand keeps its own hit count and its own next position, so every strand's greedy count is
 // exactly the reference's.
+template <int U>
 __device__ __forceinline__ bool scan_both(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
                                           uint64_t o, uint32_t npos, int k, int t, uint64_t mask)
 {
-    constexpr int U = kSearchBatch;
     uint64_t wi = o >> 5;
     uint4 q0 = planes[wi], q1 = planes[wi + 1], q2 = planes[wi + 2];
     int seen_f = 0, seen_r = 0;
@@ -854,7 +854,9 @@ __device__ __forceinline__ bool scan_both(const uint32_t *__restrict__ filter, c
 // search_reads (search_reads.h:34-87): one lane per read, grid-stride.
 // counters[0] += newly found, counters[1] += reads scanned; with COUNT also
 // counters[2] += filter byte tests, counters[3] += k-mer lookups (reference semantics).
-template <bool COUNT, bool BOTH>
+// BOTH: 0 = the reference's order (forward scan, then reverse); > 0 = one pass over both strands with BOTH
+// positions per strand and batch (scan_both)
+template <bool COUNT, int BOTH>
 __global__ void __launch_bounds__(256)
 k_search(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
          const uint64_t *__restrict__ offs, uint64_t n_reads, int k, int t,
@@ -877,7 +879,7 @@ k_search(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
             f = scan_strand<COUNT>(filter, planes, o, npos, k, t, mask, false, tests, lookups);
             if (!f) f = scan_strand<COUNT>(filter, planes, o, npos, k, t, mask, true, tests, lookups);
         } else {
-            f = scan_both(filter, planes, o, npos, k, t, mask);
+            f = scan_both<(BOTH > 0 ? BOTH : 1)>(filter, planes, o, npos, k, t, mask);
         }
         if (f) {
             atomicOr(&tags[r >> 5], 1u << (r & 31));

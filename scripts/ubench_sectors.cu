@@ -67,6 +67,42 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t *__restrict__ buf
     if (acc == 0x12345678u) atomicAdd(sink, 1ull);
 }
 
+// how many independent random loads per thread and how many blocks does it take to reach the DRAM random-access rate?
+template <int ILP>
+__global__ void __launch_bounds__(256) k_gather_ilp(const uint32_t *__restrict__ buf, uint64_t mask, uint64_t n_ops,
+                                                    unsigned long long *sink)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i + (ILP - 1) * stride < n_ops; i += ILP * stride) {
+        uint32_t v[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; u++) v[u] = ld_variant<2>(buf + (splitmix64(i + u * stride) & mask), 0);
+#pragma unroll
+        for (int u = 0; u < ILP; u++) acc += v[u];
+    }
+    if (acc == 0x12345678u) atomicAdd(sink, 1ull);
+}
+
+template <int ILP>
+static void run_ilp(const uint32_t *buf, uint64_t bytes, uint64_t n_ops, unsigned blocks, unsigned long long *sink)
+{
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    uint64_t mask = bytes / 4 - 1;
+    k_gather_ilp<ILP><<<blocks, 256>>>(buf, mask, n_ops / 8, sink);
+    cudaEventRecord(e0);
+    k_gather_ilp<ILP><<<blocks, 256>>>(buf, mask, n_ops, sink);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    printf("{\"variant\": \"L2::64B, %d loads in flight per thread, %u blocks\", \"MiB\": %llu, \"ms\": %.3f, \"Gops_s\": %.2f}\n", ILP,
+           blocks, (unsigned long long)(bytes >> 20), ms, n_ops / (ms * 1e6));
+    fflush(stdout);
+}
+
 template <int V, int MODE>
 static void run(const char *name, const uint32_t *buf, uint64_t bytes, uint64_t n_ops, unsigned long long *sink)
 {
@@ -127,6 +163,13 @@ int main(int argc, char **argv)
     run<0, 5>("4 lines of one 2 KiB block", buf, G4, n, sink);
     run<0, 6>("4 lines of one 4 KiB block", buf, G4, n, sink);
     run<0, 7>("4 lines of one 16 KiB block", buf, G4, n, sink);
+    for (unsigned blocks : {148u * 4, 148u * 8, 148u * 16, 148u * 64}) {
+        run_ilp<1>(buf, G4, n, blocks, sink);
+        run_ilp<2>(buf, G4, n, blocks, sink);
+        run_ilp<4>(buf, G4, n, blocks, sink);
+        run_ilp<8>(buf, G4, n, blocks, sink);
+        run_ilp<16>(buf, G4, n, blocks, sink);
+    }
     run<0, 0>("nc.no_allocate", buf, 256ull << 20, n, sink);
     run<0, 0>("nc.no_allocate", buf, 1ull << 30, n, sink);
     run<0, 0>("nc.no_allocate", buf, 16ull << 30, n, sink);
