@@ -2,7 +2,7 @@
 
     python -m commet_b200.build          # library + tools
     commet_b200/lib/libcommet_b200.so    # CUDA kernels + C-ABI (include/commet_b200.h)
-    commet_b200/bin/{index_and_search,filter_reads,bvop}   # drop-in executables
+    commet_b200/bin/{index_and_search,filter_reads,bvop,extract_reads}   # drop-in executables (+ commet_nxn)
 """
 from __future__ import annotations
 
@@ -17,7 +17,8 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libcommet_b200.so"
 BIN = PKG / "bin"
-TOOLS = ("index_and_search", "filter_reads", "bvop", "commet_nxn")
+TOOLS = ("index_and_search", "filter_reads", "bvop", "commet_nxn", "extract_reads")
+HOST_ONLY = ("extract_reads",)          # pure I/O tools: no CUDA library behind them
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-Wall,-Wno-unknown-pragmas", "-shared"]
@@ -60,7 +61,11 @@ def build_tools(force: bool = False) -> list[Path]:
         if not src.exists():
             continue
         exe = BIN / t
-        if force or _stale(exe, [src, *hdrs, LIB]):
+        if t in HOST_ONLY:
+            if force or _stale(exe, [src, *hdrs]):
+                subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-I", str(CSRC / "host"), "-o", str(exe), str(src),
+                                "-lz"], check=True)
+        elif force or _stale(exe, [src, *hdrs, LIB]):
             subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-I", str(ROOT / "include"), "-I", str(CSRC / "host"),
                             "-o", str(exe), str(src), "-L", str(LIB.parent), "-lcommet_b200",
                             "-Wl,-rpath,$ORIGIN/../lib", "-lz", "-lpthread"], check=True)
