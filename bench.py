@@ -241,7 +241,9 @@ def main():
     ap.add_argument("--len", type=int, default=100, dest="length")
     ap.add_argument("-k", type=int, default=33)
     ap.add_argument("-t", type=int, default=2)
-    ap.add_argument("--cpu-sample", type=int, default=500_000)
+    ap.add_argument("--cpu-sample", type=int, default=2_000_000,
+                    help="reads per set of the bounded CPU sample (2 M: ~20 s for one reference process at C2, so that the "
+                         "fixed cost of zeroing the 4 GiB filter is amortised as it is at full size)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--direct-index", action="store_true", help="disable the L2-blocked insert (A/B)")
     ap.add_argument("--index-mode", type=int, default=None, help="commet_ctx_binned_index mode (A/B): 0 direct, 1 "
@@ -507,21 +509,35 @@ def reference_arm(args, rank, world, config):
     cp = np.where(mut, acgt[rng.integers(0, 4, size=(sample, L))], cp)
     shared = rng.random(sample) < 0.5
     qry = np.where(shared[:, None], cp, acgt[rng.integers(0, 4, size=(sample, L))]).astype(np.uint8).reshape(-1)
-    procs = max(1, min(os.cpu_count() or 1, 16, _mem_procs(1 << (k - 1))))
-    vals = []
-    for _ in range(max(1, min(args.steps, 2))):
+    # The reference is single-threaded; its only parallelism is independent processes.  Every process
+    # must index the whole reference sample (and calloc + touch its own 2^(k-1)-byte filter), so more processes
+    # only split the search half of the job and contend for DRAM during the index half: the process count that
+    # is fastest on this box is found by trying 1, 4 and the most that fit, and the best one is the arm's value.
+    most = max(1, min(os.cpu_count() or 1, 16, _mem_procs(1 << (k - 1))))
+    tried = {}
+    for procs in sorted({1, min(4, most), most}):
         r = cpu_reference_run(ref, qry, L, sample, sample, k, t, procs)
         if r is None:
             r = cpu_port_run(ref, qry, L, sample, sample, k, t)
-        vals.append(r)
-    wall, kind, cores = min(vals)
+        tried[r[2]] = r
+        if r[1] == "port":
+            break
+    best = min(tried.values())
+    for _ in range(max(0, min(args.steps, 3) - 1)):      # repeat the best configuration, keep its fastest run
+        r = cpu_reference_run(ref, qry, L, sample, sample, k, t, best[2]) if best[1] == "reference" else None
+        if r is not None:
+            best = min(best, r)
+    wall, kind, cores = best
     v = sample / wall
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-                             "sample": f"{sample} reference reads indexed by each of {cores} processes, {sample} query "
-                                       f"reads split across them ({L} bp, k={k}, t={t}); value = query reads / wall"},
+                             "host_cpus": os.cpu_count(),
+                             "tried_reads_per_s": {str(c): round(sample / r[0], 1) for c, r in sorted(tried.items())},
+                             "sample": f"{sample} reference reads indexed by each of {cores} process(es), {sample} query "
+                                       f"reads split across them ({L} bp, k={k}, t={t}); value = query reads / wall of the "
+                                       "fastest process count tried"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
