@@ -11,9 +11,12 @@ reverse-complement greedy scan).  Workload at N=1 = BASELINE.json configs[1]:
 2 synthetic sets x 10M reads x 100 bp, k=33, t=2.
 
 At N>1 (weak scaling): every rank owns its own 10M-read query set; the
-reference set is sharded N ways, each rank builds a partial filter from its
-shard, partials are merged (all_gather over NCCL + word-wise OR kernel), then
-each rank probes locally.  value = total query reads / max-over-ranks time.
+reference set is dealt block-cyclically over the ranks (each rank holds,
+uploads and encodes only its 1/N of it), each rank builds a partial filter
+from its shard, the partials are merged by ONE kernel per rank over NVLink
+peer memory (reduce-scatter + all-gather of the OR, commet_index_merge), then
+each rank probes locally (commet_b200/multi.py, distributed placement).
+value = total query reads / max-over-ranks time.
 
 `value`   : inputs (ASCII bases + offsets) already resident in HBM.
 `e2e`     : same pass through Context.index_and_search with HOST buffers
@@ -254,7 +257,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = (f"C2: 2 synthetic sets x {args.reads} reads x {args.length} bp, k={args.k} t={args.t}, "
-                "single index_and_search" + (f", reference set sharded over {world} GPUs, one query set per GPU" if world > 1 else ""))
+                "single index_and_search" + (f", reference set dealt block-cyclically over {world} GPUs (each holds 1/{world}), one "
+                                             f"query set per GPU" if world > 1 else ""))
     config = {"workload": workload, "reads_per_set": args.reads, "read_len": args.length, "k": args.k, "t": args.t,
               "filter_bytes": 1 << (args.k - 1), "l2_policy": "inputs larger than L2 (2 GB of bases + 4 GiB filter per step)"}
 
@@ -298,27 +302,46 @@ def main():
             return out
         be0.connect(k_arg, world, rank, all_gather_bytes)
         peers = be0.peers
+        # this rank's shard of the reference set: blocks b = rank (mod world) of BLOCK consecutive reads -- what a
+        # rank's loader delivers when every process parses only its own blocks of the files
+        BLOCK = multi.DEFAULT_BLOCK
+        own = torch.as_tensor(multi.owned_mask(n, world, rank, BLOCK), device=dev)
+        n_loc = int(own.sum())
+        ref_loc_d = ref_d.view(n, L)[own].reshape(-1).contiguous()
+        offs_loc_d = torch.arange(0, n_loc + 1, dtype=torch.int64, device=dev) * L
+        gather_buf = torch.zeros(world, dtype=torch.int64, device=dev)
+
+        def all_gather(obj):
+            """multi.distributed_plan's exchange: one integer per rank on the fast path (one NCCL all-gather of
+            8 bytes), pickled per-read counts only when the reference set reaches max_kmer"""
+            if isinstance(obj, int):
+                dist.all_gather_into_tensor(gather_buf, torch.tensor([obj], dtype=torch.int64, device=dev))
+                return gather_buf.tolist()
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
 
     def step_device():
         """one pass with inputs resident in HBM; returns info dict"""
         tags_d.zero_()
         ext.wait_stream(torch.cuda.current_stream())
         q = ctx.stage_device(qry_d.data_ptr(), offs_d.data_ptr(), n, n * L)
-        idx = ctx.stage_device(ref_d.data_ptr(), offs_d.data_ptr(), n, n * L)
         if world == 1:
+            idx = ctx.stage_device(ref_d.data_ptr(), offs_d.data_ptr(), n, n * L)
             info = ctx.index_and_search_staged(k, t, idx, [q], [tags_d.data_ptr()])
         else:
-            # every chunk of the reference set is sharded over the ranks, partial filters are merged by the
-            # one-kernel OR all-reduce over peer memory, every rank probes its own query set (commet_b200/multi.py)
+            # the rank stages ITS shard of the reference set; every chunk's partial filters are merged by the
+            # one-kernel OR all-reduce over peer memory; every rank probes its own query set
+            idx = ctx.stage_device(ref_loc_d.data_ptr(), offs_loc_d.data_ptr(), n_loc, n_loc * L)
             counters_d.zero_()
             torch.cuda.current_stream().synchronize()
             be = multi.DeviceBackend(ctx, idx, [q], [tags_d.data_ptr()], [counters_d.data_ptr()])
             be.peers, be.rank, be.k = peers, rank, k
-            r = multi.sharded_index_and_search(be, dist.barrier, world, rank, k, t)
+            r = multi.distributed_index_and_search(be, dist.barrier, all_gather, world, rank, k, t, n, BLOCK)
             ctx.sync()
             c = counters_d.tolist()
             info = {"shared": [c[0]], "searched": [c[1]], "chunks": r["chunks"], "index_ns": 0, "search_ns": 0, "kmers": 0,
-                    "phases_ms": {key[:-2]: round(r[key] * 1e3, 3) for key in ("index_s", "merge_s", "barrier_s")}}
+                    "phases_ms": {key[:-2]: round(r[key] * 1e3, 3) for key in ("plan_s", "index_s", "merge_s", "barrier_s")}}
         idx.free()
         q.free()
         return info
@@ -330,6 +353,12 @@ def main():
     offs_ht = torch.empty(n + 1, dtype=torch.int64).pin_memory()       # page-locked like the bases: H2D copies queue ahead
     offs_ht.copy_(offs_d)
     offs_h = offs_ht.numpy().view(np.uint64)
+    if world > 1:
+        ref_loc_h = torch.empty(n_loc * L, dtype=torch.uint8).pin_memory()
+        ref_loc_h.copy_(ref_loc_d)
+        offs_loc_ht = torch.empty(n_loc + 1, dtype=torch.int64).pin_memory()
+        offs_loc_ht.copy_(offs_loc_d)
+        offs_loc_h = offs_loc_ht.numpy().view(np.uint64)
 
     def barrier():
         if world > 1:
@@ -368,10 +397,11 @@ def main():
         ctx.count_probes(False)
         assert probes["shared"][0] == shared
 
-    # end-to-end leg: the same pass through the public API with HOST (pinned) buffers: H2D of both sets and D2H
+    # end-to-end leg: the same pass through the public API with HOST (pinned) buffers: H2D of the sets and D2H
     # of the tag vector inside the timed region.  N=1: Context.index_and_search (= the C-ABI call the drop-in
-    # index_and_search tool makes).  N>1: every rank uploads the reference set and its own query set, then
-    # the sharded loop of commet_b200/multi.py; wall clock, max over ranks.
+    # index_and_search tool makes).  N>1: every rank queues the upload of its shard of the reference set, then of
+    # its own query set (commet_reads_upload_async: the query bytes cross PCIe during the insert and the merge),
+    # then runs the distributed loop of commet_b200/multi.py; wall clock, max over ranks.
     tags_h = torch.empty(n // 8 + 1, dtype=torch.uint8).pin_memory()
 
     def step_e2e():
@@ -381,11 +411,11 @@ def main():
         tags_d.zero_()
         counters_d.zero_()
         torch.cuda.current_stream().synchronize()
-        idx = ctx.stage(ref_h.numpy(), offs_h)
-        q = ctx.stage(qry_h.numpy(), offs_h)
+        idx = ctx.stage_async(ref_loc_h.numpy(), offs_loc_h)
+        q = ctx.stage_async(qry_h.numpy(), offs_h)
         be = multi.DeviceBackend(ctx, idx, [q], [tags_d.data_ptr()], [counters_d.data_ptr()])
         be.peers, be.rank, be.k = peers, rank, k
-        multi.sharded_index_and_search(be, dist.barrier, world, rank, k, t)
+        multi.distributed_index_and_search(be, dist.barrier, all_gather, world, rank, k, t, n, BLOCK)
         ctx.sync()
         tags_h.copy_(tags_d.view(torch.uint8)[:n // 8 + 1])
         idx.free(); q.free()
@@ -406,7 +436,8 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt)
     e2e = {"value": n * world / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
-           "h2d_bytes_per_step": int(world * (2 * n * L + 2 * 8 * (n + 1))), "d2h_bytes_per_step": int(world * (n // 8 + 1))}
+           "h2d_bytes_per_step": int(world * (n * L + 8 * (n + 1)) + n * L + 8 * (n + world)),
+           "d2h_bytes_per_step": int(world * (n // 8 + 1))}
 
     if rank != 0:
         if world > 1:

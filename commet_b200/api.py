@@ -45,6 +45,7 @@ _SIGS = {
     "commet_filter_bytes": (C.c_uint64, [C.c_int]),
     "commet_max_kmer": (C.c_uint64, [C.c_int]),
     "commet_reads_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "commet_reads_upload_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "commet_reads_from_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
                                            C.POINTER(C.c_void_p)]),
     "commet_reads_clone": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -54,6 +55,7 @@ _SIGS = {
     "commet_reads_select": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "commet_reads_selected": (C.c_uint64, [C.c_void_p]),
     "commet_reads_kmer_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "commet_reads_kmer_total": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _u64p]),
     "commet_chunk_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64, _u64p, _u64p]),
     "commet_index_begin": (C.c_int, [C.c_void_p, C.c_int]),
     "commet_index_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
@@ -231,6 +233,16 @@ class Context:
         self._ck(self.lib.commet_reads_upload(self.handle, _ptr(bases), _ptr(offs), offs.size - 1, C.byref(h)))
         return ReadStream(self, h.value)
 
+    def stage_async(self, bases, offs) -> ReadStream:
+        """Queue the upload of a host read stream (commet_reads_upload_async): returns at once, the encode happens at
+        first use.  The arrays are kept alive by the returned stream object until it is freed."""
+        bases, offs = _as_stream(bases, offs)
+        h = C.c_void_p()
+        self._ck(self.lib.commet_reads_upload_async(self.handle, _ptr(bases), _ptr(offs), offs.size - 1, C.byref(h)))
+        rs = ReadStream(self, h.value)
+        rs._keep = (bases, offs)
+        return rs
+
     def stage_device(self, d_bases: int, d_offs: int, n_reads: int, n_bases: int) -> ReadStream:
         """Encode a stream whose ASCII bases/offsets already sit in device memory."""
         h = C.c_void_p()
@@ -250,6 +262,11 @@ class Context:
         out = np.zeros(max(reads.n_reads, 1), dtype=np.uint32)
         self._ck(self.lib.commet_reads_kmer_counts(self.handle, reads.handle, k, _ptr(out)))
         return out[:reads.n_reads]
+
+    def kmer_total(self, reads: ReadStream, k: int) -> int:
+        tot = C.c_uint64(0)
+        self._ck(self.lib.commet_reads_kmer_total(self.handle, reads.handle, k, C.byref(tot)))
+        return int(tot.value)
 
     def chunk_plan(self, reads: ReadStream, k: int, maxk: int | None = None):
         """[(first, end), ...] read ranges of the index chunks, and reads indexed."""

@@ -503,6 +503,20 @@ extern "C" int commet_reads_upload(commet_ctx *c, const uint8_t *bases, const ui
     return 0;
 }
 
+// The same staging without waiting: the H2D copies are queued on the context's copy stream (page-locked sources;
+// pageable ones are copied when first needed) and the 2-bit encode is enqueued the first time the stream is used
+// (index, search, counts, filter), behind the arrival events of its chunks.  Streams uploaded this way cross
+// PCIe in call order while kernels queued earlier run: a multi-GPU rank uploads its shard of the reference
+// set, then its query set, and the query bytes travel during the insert and the merge.
+extern "C" int commet_reads_upload_async(commet_ctx *c, const uint8_t *bases, const uint64_t *offs,
+                                         uint64_t n_reads, commet_reads **out)
+{
+    if (!c || !offs || !out) return fail("commet_reads_upload_async: null argument");
+    if (offs[0] != 0) return fail("commet_reads_upload_async: offs[0] must be 0");
+    CKR(set_device(c));
+    return reads_upload_async(c, bases, offs, n_reads, out);
+}
+
 extern "C" int commet_reads_from_device(commet_ctx *c, const uint8_t *d_bases, const uint64_t *d_offs,
                                         uint64_t n_reads, uint64_t n_bases, commet_reads **out)
 {
@@ -684,6 +698,29 @@ extern "C" int commet_reads_kmer_counts(commet_ctx *c, commet_reads *r, int k, u
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(counts, d.p, r->n_reads * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// sum of the per-read counts only (8 bytes come back): what a rank of the distributed placement contributes to
+// the global "does the set reach max_kmer at all" test (commet_b200/multi.py)
+extern "C" int commet_reads_kmer_total(commet_ctx *c, commet_reads *r, int k, uint64_t *total)
+{
+    if (!c || !r || !total) return fail("commet_reads_kmer_total: null argument");
+    CKR(set_device(c));
+    CKR(prepare(c, r, k));
+    *total = 0;
+    if (r->n_reads == 0) return 0;
+    DevBuf d(c);
+    if (d.alloc(r->n_reads * sizeof(uint32_t)) != cudaSuccess) return fail("allocation of k-mer counts failed");
+    CK(cudaMemsetAsync(c->scratch + 150, 0, sizeof(unsigned long long), c->stream));
+    k_kmer_counts<<<grid_for(c, r->n_reads, 256, 8), 256, 0, c->stream>>>(r->planes, r->offs, r->n_reads,
+                                                                         d.as<uint32_t>(), c->scratch + 150);
+    c->launches++;
+    CK(cudaGetLastError());
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, c->scratch + 150, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *total = h;
     return 0;
 }
 

@@ -14,7 +14,19 @@ filter of the chunk, and every query bit is the single-GPU bit (axes 
 collective is needed besides the merge; torch.distributed only carries the 64-byte IPC handles and the
 barriers.
 
-The loop is written against a small backend protocol so that the sharding/merge logic is testable on CPU
+Two placements of the reference set are supported:
+
+    replicated    every rank holds the whole set and inserts its share of each chunk  (sharded_index_and_search)
+    distributed   every rank holds (parsed / uploaded / encoded) only ITS blocks of the set, dealt block-cyclically:
+                  block b of `block` consecutive reads lives on rank b % world.  A chunk is a contiguous range of
+                  global reads, so on every rank it is a contiguous range of LOCAL reads, evenly loaded whatever
+                  the chunk.  The stop rule of index_reads needs the k-mer counts of all reads in global order:
+                  the ranks exchange their local totals (one number each) and, only if the limit is reached at
+                  all, their per-read counts (4 bytes per read); every rank then walks the same array
+                  (distributed_index_and_search).  Host-to-device traffic and device memory for the reference
+                  set are 1/world of the replicated placement.
+
+The loops are written against a small backend protocol so that the sharding/merge logic is testable on CPU
 (tests/test_multi_gloo.py runs it with world_size 2 over gloo and an oracle-backed stand-in); the product
 backend is `DeviceBackend` over the C-ABI.
 """
@@ -43,6 +55,10 @@ class Backend(Protocol):
     def flush(self) -> None: ...
     def merge(self) -> None: ...
     def search(self, k: int, t: int) -> None: ...
+    # distributed placement only:
+    def local_kmer_total(self, k: int) -> int: ...
+    def local_kmer_counts(self, k: int): ...
+    def max_kmer(self, k: int) -> int: ...
 
 
 class Barrier(Protocol):
@@ -81,6 +97,129 @@ def sharded_index_and_search(backend: Backend, barrier: Barrier, world: int, ran
             t_wait += (t2 - t1) + (t4 - t3)
         backend.search(k, t)
     return {"chunks": len(plan), "indexed_here": indexed, "index_s": t_index, "merge_s": t_merge, "barrier_s": t_wait}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# distributed placement: block-cyclic shards of the reference set
+# ----------------------------------------------------------------------------------------------------------------
+DEFAULT_BLOCK = 1 << 16
+
+
+def local_index(g: int, world: int, rank: int, block: int) -> int:
+    """number of reads with global index < g that live on `rank` (= local index of global read g if it is local)"""
+    cycle = block * world
+    full, o = divmod(g, cycle)
+    return full * block + min(max(o - rank * block, 0), block)
+
+
+def owned_mask(n_global: int, world: int, rank: int, block: int):
+    """boolean numpy mask over the global reads: True where the read lives on `rank`"""
+    import numpy as np
+    return (np.arange(n_global, dtype=np.int64) // block) % world == rank
+
+
+def shard_stream(bases, offs, world: int, rank: int, block: int):
+    """(bases, offs) of the reads of a host stream that live on `rank`, in global order (numpy; what a rank's
+    loader delivers: it parses only its own blocks of the files)"""
+    import numpy as np
+    offs = np.asarray(offs, dtype=np.uint64)
+    n = offs.size - 1
+    keep = np.nonzero(owned_mask(n, world, rank, block))[0]
+    lens = (offs[1:] - offs[:-1])[keep]
+    out_offs = np.zeros(keep.size + 1, dtype=np.uint64)
+    np.cumsum(lens, out=out_offs[1:])
+    out = np.empty(int(out_offs[-1]), dtype=np.uint8)
+    # block-wise copies: consecutive owned reads are contiguous in the source
+    b = 0
+    while b * block < n:
+        if b % world == rank:
+            g0, g1 = b * block, min(n, (b + 1) * block)
+            l0 = local_index(g0, world, rank, block)
+            out[int(out_offs[l0]):int(out_offs[l0 + (g1 - g0)])] = bases[int(offs[g0]):int(offs[g1])]
+        b += 1
+    return out, out_offs
+
+
+def chunk_bounds(counts, max_kmer: int) -> list[tuple[int, int]]:
+    """The stop rule of index_reads on per-read k-mer counts in stream order (include/index_reads.h:48-49,60;
+    src/index_and_search.cpp:255): a chunk closes after the read at which the cumulative count reaches max_kmer,
+    and the next read is fetched and lost.  Same walk as commet_chunk_plan, vectorised over the prefix sums."""
+    import numpy as np
+    n = len(counts)
+    if n == 0 or max_kmer <= 0:
+        return []
+    cs = np.cumsum(np.asarray(counts, dtype=np.uint64), dtype=np.uint64)
+    if int(cs[-1]) < max_kmer:
+        return [(0, n)]
+    out, i = [], 0
+    while i < n:
+        base = int(cs[i - 1]) if i else 0
+        j = int(np.searchsorted(cs, np.uint64(base + max_kmer), side="left"))   # first read where cum >= max_kmer
+        if j >= n:
+            out.append((i, n))
+            break
+        out.append((i, j + 1))
+        i = j + 2                                                               # read j+1 is fetched and lost
+    return out
+
+
+def distributed_plan(local_total: int, local_counts, n_global: int, world: int, rank: int, block: int, max_kmer: int,
+                     all_gather):
+    """Chunk plan of the whole reference set from every rank's local k-mer counts.  all_gather(obj) -> list of
+    every rank's obj.  Fast path: the total never reaches max_kmer (one chunk) and only the totals travel;
+    local_counts() (per-read u32 counts of the local shard) is called only otherwise."""
+    import numpy as np
+    totals = all_gather(int(local_total))
+    if n_global == 0:
+        return []
+    if sum(totals) < max_kmer:
+        return [(0, n_global)]
+    parts = all_gather(np.ascontiguousarray(local_counts(), dtype=np.uint32))
+    counts = np.empty(n_global, dtype=np.uint32)
+    for r in range(world):
+        m = owned_mask(n_global, world, r, block)
+        if int(m.sum()) != len(parts[r]):
+            raise ValueError(f"rank {r} holds {len(parts[r])} reads, its blocks of {n_global} reads are {int(m.sum())}")
+        counts[m] = parts[r]
+    return chunk_bounds(counts, max_kmer)
+
+
+def distributed_index_and_search(backend, barrier: Barrier, all_gather, world: int, rank: int, k: int, t: int,
+                                 n_global: int, block: int = DEFAULT_BLOCK, maxk: int | None = None) -> dict:
+    """src/index_and_search.cpp:255-277 with the reference set dealt block-cyclically over the ranks (the
+    backend's index stream is this rank's shard) and every rank searching its own query sets."""
+    maxk = backend.max_kmer(k) if maxk is None else maxk
+    t0 = time.perf_counter()
+    plan = distributed_plan(backend.local_kmer_total(k), lambda: backend.local_kmer_counts(k), n_global, world, rank,
+                            block, maxk, all_gather)
+    t_plan = time.perf_counter() - t0
+    backend.begin(k)
+    indexed = 0
+    t_index = t_merge = t_wait = 0.0
+    for ci, (c0, c1) in enumerate(plan):
+        if ci:
+            backend.clear()
+        lo, hi = local_index(c0, world, rank, block), local_index(c1, world, rank, block)
+        t0 = time.perf_counter()
+        if hi > lo:
+            backend.index(lo, hi - lo)
+            indexed += hi - lo
+        if world > 1:
+            backend.flush()
+            t1 = time.perf_counter()
+            barrier()
+            t2 = time.perf_counter()
+            backend.merge()
+            backend.flush()
+            t3 = time.perf_counter()
+            barrier()
+            t4 = time.perf_counter()
+            t_index += t1 - t0
+            t_merge += t3 - t2
+            t_wait += (t2 - t1) + (t4 - t3)
+        backend.search(k, t)
+    return {"chunks": len(plan), "indexed_here": indexed, "plan_s": t_plan, "index_s": t_index, "merge_s": t_merge,
+            "barrier_s": t_wait, "plan": plan}
 
 
 class DeviceBackend:
@@ -132,3 +271,14 @@ class DeviceBackend:
     def search(self, k, t):
         for q, tg, cn in zip(self.queries, self.d_tags, self.d_counters):
             self.ctx.search_reads_device(q, k, t, tg, cn)
+
+    # -- distributed placement: index_stream is this rank's shard -----------------------------------
+    def local_kmer_total(self, k):
+        return self.ctx.kmer_total(self.index_stream, k)
+
+    def local_kmer_counts(self, k):
+        return self.ctx.kmer_counts(self.index_stream, k)
+
+    def max_kmer(self, k):
+        from . import api
+        return api.max_kmer(k)

@@ -76,6 +76,12 @@ uint64_t commet_max_kmer(int k);
  * upload: H2D copy from host memory + encode.  from_device: encode only. */
 int commet_reads_upload(commet_ctx *ctx, const uint8_t *bases, const uint64_t *offs,
                         uint64_t n_reads, commet_reads **out);
+/* upload without waiting: copies are queued on the context's copy stream in call order and the encode happens
+ * when the stream is first used, so later uploads overlap kernels queued earlier.  `bases` and `offs` must stay
+ * valid and unchanged until the stream has been used by a call that synchronises (or commet_ctx_sync after one
+ * that does not); page-locked memory (commet_host_alloc) is copied by DMA without host involvement. */
+int commet_reads_upload_async(commet_ctx *ctx, const uint8_t *bases, const uint64_t *offs,
+                              uint64_t n_reads, commet_reads **out);
 int commet_reads_from_device(commet_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offs,
                              uint64_t n_reads, uint64_t n_bases, commet_reads **out);
 /* copy of a staged stream on another GPU of this process, over NVLink peer copies (no second parse/upload/encode);
@@ -98,6 +104,8 @@ uint64_t commet_reads_selected(const commet_reads *r);
 /* Number of k-mers index_reads would feed for each read (windows of k
  * consecutive ACGTacgt chars, include/index_reads.h:52-58). counts: n_reads u32. */
 int commet_reads_kmer_counts(commet_ctx *ctx, commet_reads *r, int k, uint32_t *counts);
+/* their sum only (selected reads), without the per-read download */
+int commet_reads_kmer_total(commet_ctx *ctx, commet_reads *r, int k, uint64_t *total);
 
 /* ---- chunk plan: the stop rule of index_reads -----------------------------
  * include/index_reads.h:48-49,60 + src/index_and_search.cpp:255: a chunk ends

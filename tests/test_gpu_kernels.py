@@ -369,3 +369,44 @@ def test_bvop_known_answer_not_counts_padding(ctx):
     bv = oracle.tags_to_bv(tags)
     out = ctx.bvop(cb.BV_NOT, bv)
     assert ctx.nb_one(out, n) == 8008 and out[-1] == 0xFF
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("seed", range(4))
+def test_upload_async_streams_behave_like_uploaded_ones(ctx, seed, pinned):
+    """commet_reads_upload_async: copies queued in call order, encode at first use -- same bits as the synchronous
+    upload, whichever entry point touches the stream first (counts, chunk plan, insert, search, filter)."""
+    import torch
+    rng = np.random.default_rng(12000 + seed)
+    k, t = int(rng.integers(9, 19)), 2
+    ref = H.make_ref_set(rng, 2500, 30, 130, p_N=0.01)
+    qry = H.make_query_set(rng, ref, 1200, 30, 130, p_N=0.01)
+    rs, qs = H.to_stream(ref), H.to_stream(qry)
+    if pinned:
+        def pin(a, dt):
+            tt = torch.from_numpy(a.view(dt).copy()).pin_memory()
+            return tt, tt.numpy().view(a.dtype)
+        keep_r, rb = pin(rs[0], np.uint8); keep_ro, ro = pin(rs[1], np.int64)
+        keep_q, qb = pin(qs[0], np.uint8); keep_qo, qo = pin(qs[1], np.int64)
+        rs, qs = (rb, ro), (qb, qo)
+    idx = ctx.stage_async(*rs)
+    q = ctx.stage_async(*qs)
+    order = seed % 4
+    if order == 0:
+        assert np.array_equal(ctx.kmer_counts(idx, k), ctx.kmer_counts(ctx.stage(*rs), k))
+    elif order == 1:
+        assert ctx.kmer_total(idx, k) == int(ctx.kmer_counts(ctx.stage(*rs), k).sum())
+    elif order == 2:
+        bv, cnt = ctx.filter_reads_range(q, 0, len(qry), min_len=40, max_N=1, min_shannon=1.2)
+        ebv, ecnt = oracle.filter_reads(*H.to_stream(qry), min_len=40, max_N=1, min_shannon=1.2)
+        assert np.array_equal(bv, ebv) and cnt == ecnt
+    exp_tags, exp = oracle.index_and_search(k, t, H.to_stream(ref), [H.to_stream(qry)])
+    tags = torch.zeros((len(qry) // 8 + 1 + 3) // 4, dtype=torch.int32, device="cuda:0")
+    torch.cuda.synchronize()
+    info = ctx.index_and_search_staged(k, t, idx, [q], [tags.data_ptr()])
+    ctx.sync()
+    got = tags.cpu().numpy().view(np.uint8)[:len(qry) // 8 + 1]
+    assert np.array_equal(got, oracle.tags_to_bv(exp_tags[0]))
+    assert info["chunks"] == exp["chunks"] and info["shared"] == exp["shared"] and info["searched"] == exp["searched"]
+    idx.free()
+    q.free()

@@ -68,6 +68,52 @@ def _worker(rank, world, port, k, t, maxk, seed, out_dir):
         dist.destroy_process_group()
 
 
+def _worker_distributed(rank, world, port, k, t, maxk, seed, block, n_dev, out_dir):
+    """reference set dealt block-cyclically: every rank uploads (asynchronously) only its shard, then its query set"""
+    import faulthandler
+    faulthandler.enable()
+    import torch
+    import torch.distributed as dist
+    import commet_b200
+    from commet_b200 import multi
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dev = rank % n_dev                       # n_dev == 1: both ranks share the GPU (IPC mapping within one device)
+        torch.cuda.set_device(dev)
+        ctx = commet_b200.Context(dev)
+        rng = np.random.default_rng(seed)
+        ref = H.make_ref_set(rng, 3000, 40, 120, p_N=0.01)
+        queries = [H.make_query_set(rng, ref, 1500, 40, 120, p_N=0.01) for _ in range(world)]
+        shard = multi.shard_stream(*H.to_stream(ref), world, rank, block)
+        idx = ctx.stage_async(*shard)
+        q = ctx.stage_async(*H.to_stream(queries[rank]))
+        nq = len(queries[rank])
+        tags = torch.zeros((nq // 8 + 1 + 3) // 4, dtype=torch.int32, device=f"cuda:{dev}")
+        counters = torch.zeros(4, dtype=torch.int64, device=f"cuda:{dev}")
+        torch.cuda.synchronize()
+        be = multi.DeviceBackend(ctx, idx, [q], [tags.data_ptr()], [counters.data_ptr()])
+
+        def all_gather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        be.connect(k, world, rank, all_gather)
+        info = multi.distributed_index_and_search(be, dist.barrier, all_gather, world, rank, k, t, len(ref), block, maxk)
+        ctx.sync()
+        filt = ctx.filter_download(k)
+        dist.barrier()
+        be.disconnect()
+        np.save(Path(out_dir) / f"tags{rank}.npy", tags.cpu().numpy().view(np.uint8)[:nq // 8 + 1])
+        np.save(Path(out_dir) / f"meta{rank}.npy", np.array([info["chunks"], info["indexed_here"], int(counters[0]), int(counters[1]),
+                                                            idx.n_reads]))
+        np.save(Path(out_dir) / f"filt{rank}.npy", filt)
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -92,6 +138,34 @@ def test_sharded_index_merge_search_two_gpus(tmp_path, k, t, maxk, seed):
         assert chunks == e["chunks"] and shared == e["shared"][r] and searched == e["searched"][r]
         indexed += indexed_here
     assert indexed == e["indexed"]
+    assert np.array_equal(np.load(tmp_path / "filt0.npy"), np.load(tmp_path / "filt1.npy"))
+    if maxk:
+        assert e["chunks"] >= 2
+
+
+@pytest.mark.skipif(_n_gpus() < 1, reason="needs a GPU")
+@pytest.mark.parametrize("k,t,maxk,block,seed", [(16, 2, None, 64, 1), (20, 2, 60000, 100, 2), (29, 2, 90000, 7, 3)])
+def test_distributed_reference_set_two_ranks(tmp_path, k, t, maxk, block, seed):
+    """Two ranks (two GPUs when the box has them, else both on one GPU), each holding only its block-cyclic shard of
+    the reference set, uploaded with commet_reads_upload_async: global chunk plan from exchanged k-mer counts,
+    one-kernel merge over IPC-mapped filters, tags of the single-process oracle."""
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_worker_distributed, args=(world, _free_port(), k, t, maxk, seed, block, min(_n_gpus(), world), str(tmp_path)),
+             nprocs=world, join=True)
+    rng = np.random.default_rng(seed)
+    ref = H.make_ref_set(rng, 3000, 40, 120, p_N=0.01)
+    queries = [H.make_query_set(rng, ref, 1500, 40, 120, p_N=0.01) for _ in range(world)]
+    e_tags, e = oracle.index_and_search(k, t, H.to_stream(ref), [H.to_stream(q) for q in queries], maxk)
+    indexed = held = 0
+    for r in range(world):
+        tags = np.load(tmp_path / f"tags{r}.npy")
+        chunks, indexed_here, shared, searched, n_local = np.load(tmp_path / f"meta{r}.npy").tolist()
+        assert np.array_equal(tags, oracle.tags_to_bv(e_tags[r])), f"rank {r}: tags differ from the oracle"
+        assert chunks == e["chunks"] and shared == e["shared"][r] and searched == e["searched"][r]
+        indexed += indexed_here
+        held += n_local
+    assert indexed == e["indexed"] and held == len(ref)
     assert np.array_equal(np.load(tmp_path / "filt0.npy"), np.load(tmp_path / "filt1.npy"))
     if maxk:
         assert e["chunks"] >= 2

@@ -80,6 +80,27 @@ class OracleBackend:
         self.shared += r["found"]
         self.searched = r["searched"]
 
+    # distributed placement: index_stream is this rank's block-cyclic shard
+    def local_kmer_counts(self, k):
+        bases, offs = self.index_stream
+        return np.array([_kmers(bases[int(offs[i]):int(offs[i + 1])], k) for i in range(len(offs) - 1)], dtype=np.uint32)
+
+    def local_kmer_total(self, k):
+        return int(self.local_kmer_counts(k).sum())
+
+    def max_kmer(self, k):
+        return oracle.max_kmer(k)
+
+
+def _kmers(seq, k):
+    """k-mers index_reads feeds for one read: windows of k consecutive ACGTacgt chars (index_reads.h:52-58)"""
+    valid = np.isin(seq, np.frombuffer(b"ACGTacgt", dtype=np.uint8))
+    n = run = 0
+    for v in valid:
+        run = run + 1 if v else 0
+        n += run >= k
+    return n
+
 
 def _worker(rank, world, port, k, t, maxk, seed, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -93,6 +114,29 @@ def _worker(rank, world, port, k, t, maxk, seed, out_dir):
         info = multi.sharded_index_and_search(be, dist.barrier, world, rank, k, t, maxk)
         np.save(Path(out_dir) / f"tags{rank}.npy", be.tags)
         np.save(Path(out_dir) / f"meta{rank}.npy", np.array([info["chunks"], info["indexed_here"], be.shared, be.searched]))
+    finally:
+        dist.destroy_process_group()
+
+
+def _worker_distributed(rank, world, port, k, t, maxk, seed, block, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(seed)
+        ref = H.make_ref_set(rng, 700, 30, 90, p_N=0.01)
+        queries = [H.make_query_set(rng, ref, 300, 30, 90, p_N=0.01) for _ in range(world)]
+        shard = multi.shard_stream(*H.to_stream(ref), world, rank, block)      # this rank never sees the other blocks
+        be = OracleBackend(k, shard, H.to_stream(queries[rank]), world, rank)
+
+        def all_gather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        info = multi.distributed_index_and_search(be, dist.barrier, all_gather, world, rank, k, t, len(ref), block, maxk)
+        np.save(Path(out_dir) / f"tags{rank}.npy", be.tags)
+        np.save(Path(out_dir) / f"meta{rank}.npy", np.array([info["chunks"], info["indexed_here"], be.shared, be.searched,
+                                                            len(shard[1]) - 1]))
     finally:
         dist.destroy_process_group()
 
@@ -132,3 +176,62 @@ def test_shard_and_slice_ranges_partition():
             assert max(h - l for l, h in got) - min(h - l for l, h in got) <= 1
             sl = [multi.slice_range(n, world, r) for r in range(world)]
             assert sl[0][0] == 0 and sl[-1][1] == n and all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+
+
+@pytest.mark.parametrize("world,k,t,maxk,block,seed", [(2, 13, 2, None, 64, 1), (2, 16, 2, 9000, 7, 2), (3, 11, 1, 4000, 50, 3),
+                                                      (2, 12, 2, 2500, 1, 4)])
+def test_distributed_reference_set_matches_single_process_oracle(tmp_path, world, k, t, maxk, block, seed):
+    """The reference set dealt block-cyclically over the ranks (every rank holds only its blocks): global chunk
+    boundaries from exchanged k-mer counts, contiguous local ranges per chunk, same bits as one process."""
+    mp.spawn(_worker_distributed, args=(world, _free_port(), k, t, maxk, seed, block, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(seed)
+    ref = H.make_ref_set(rng, 700, 30, 90, p_N=0.01)
+    queries = [H.make_query_set(rng, ref, 300, 30, 90, p_N=0.01) for _ in range(world)]
+    e_tags, e = oracle.index_and_search(k, t, H.to_stream(ref), [H.to_stream(q) for q in queries], maxk)
+    indexed = held = 0
+    for r in range(world):
+        tags = np.load(tmp_path / f"tags{r}.npy")
+        chunks, indexed_here, shared, searched, n_local = np.load(tmp_path / f"meta{r}.npy").tolist()
+        assert np.array_equal(tags[:len(queries[r])], e_tags[r]), f"rank {r}: tags differ from the single-process oracle"
+        assert chunks == e["chunks"] and shared == e["shared"][r] and searched == e["searched"][r]
+        indexed += indexed_here
+        held += n_local
+    assert indexed == e["indexed"] and held == len(ref)
+    if maxk:
+        assert e["chunks"] > 2
+
+
+def test_block_cyclic_helpers():
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 3, 8):
+        for block in (1, 3, 8, 1000):
+            n = 53
+            masks = [multi.owned_mask(n, world, r, block) for r in range(world)]
+            assert np.array_equal(np.sum(masks, axis=0), np.ones(n))                     # a partition of the reads
+            for r in range(world):
+                for g in range(n + 1):
+                    assert multi.local_index(g, world, r, block) == int(masks[r][:g].sum())
+            reads = H.make_ref_set(rng, n, 1, 20)
+            bases, offs = H.to_stream(reads)
+            for r in range(world):
+                b, o = multi.shard_stream(bases, offs, world, r, block)
+                got = [bytes(b[int(o[i]):int(o[i + 1])]) for i in range(len(o) - 1)]
+                assert got == [x for x, m in zip(reads, masks[r]) if m]
+
+
+def test_chunk_bounds_is_the_stop_rule_of_index_reads():
+    """multi.chunk_bounds against the oracle's chunk walk on the same per-read counts"""
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        k = int(rng.integers(8, 16))
+        reads = H.make_ref_set(rng, int(rng.integers(1, 120)), 5, 60, p_N=0.03)
+        counts = [_kmers(np.frombuffer(r, dtype=np.uint8), k) for r in reads]
+        maxk = int(rng.choice([1, 7, 50, 400, 10**9]))
+        stream = H.to_stream(reads)
+        scratch = np.zeros(oracle.filter_bytes(k), dtype=np.uint8)
+        pos, plan = 0, []
+        while pos < len(reads):
+            nxt, ni, _ = oracle.index_chunk(scratch, k, *stream, pos, maxk)
+            plan.append((pos, pos + ni))
+            pos = nxt
+        assert multi.chunk_bounds(counts, maxk) == plan, (trial, k, maxk)
