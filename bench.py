@@ -461,12 +461,13 @@ def main():
         # (short-circuit a,b,c,d; greedy k-jump; reverse strand only when the forward scan failed).
         ncu = ncu_traffic("k_search", config)
         ach = probes["tests"] * 32 / (srch_ms / 1e3) / 1e9
-        ceil = random_sector_ceiling()
+        ceil = random_sector_ceiling(1 << (k - 1))
         line["roofline"] = {"bound": "hbm", "kernel": "k_search", "achieved": ach, "peak": peak, "unit": "GB/s",
                             "frac": ach / peak, "traffic": ncu, "peak_source": peak_src,
                             "algorithmic": f"{probes['tests']} filter bit tests x 32 B sector per launch",
                             "ms_per_launch": srch_ms,
-                            "random_sector_ceiling_GBps": ceil, "frac_of_random_sector_ceiling": (ach / ceil) if ceil else None}
+                            "random_sector_ceiling_GBps": ceil, "frac_of_random_sector_ceiling": (ach / ceil) if ceil else None,
+                            "random_sector_ceiling_residency": "dram" if (1 << (k - 1)) > (64 << 20) else "l2"}
         ins_bytes = kmers * 4 * 64            # 64 B per key insert, 4 keys per k-mer
         line["roofline_index"] = {"bound": "hbm", "kernel": "k_bin_count+k_bin_scatter+k_bin_apply", "achieved": ins_bytes / (idx_ms / 1e3) / 1e9,
                                   "peak": peak, "unit": "GB/s", "frac": ins_bytes / (idx_ms / 1e3) / 1e9 / peak,
@@ -497,11 +498,13 @@ def ncu_traffic(kernel: str, config: dict):
     return None
 
 
-def random_sector_ceiling():
-    """measured random 32-byte-sector load ceiling over a 4 GiB buffer (profiles/r01_ceilings.json), in GB/s"""
+def random_sector_ceiling(filter_bytes: int = 1 << 32):
+    """measured random 32-byte-sector load ceiling for the filter's residency (profiles/r01_ceilings.json), in GB/s:
+    over a 4 GiB buffer (DRAM) for filters larger than L2, over a 64 MiB buffer (L2-resident) otherwise"""
     try:
         d = json.loads((ROOT / "profiles" / "r01_ceilings.json").read_text())
-        return d["dram_4GiB_load_Gsectors_s"] * 32
+        key = "dram_4GiB_load_Gsectors_s" if filter_bytes > (64 << 20) else "l2_64MiB_load_Gsectors_s"
+        return d[key] * 32
     except Exception:
         return None
 

@@ -99,6 +99,7 @@ def test_c2_filter_sorted_insert_equals_direct_and_oracle_keys(env):
     ctx.index_reads(idx, K)
     ctx.sync()
     sorted_f = torch.as_tensor(_DevMem(ctx.filter_ptr, F), device=e["dev"]).clone()
+    torch.cuda.synchronize()              # the copy runs on torch's stream: it must land before the context clears the filter
     ctx.binned_index(0)
     try:
         ctx.index_reads(idx, K)
