@@ -142,6 +142,7 @@ struct commet_ctx {
     unsigned long long *scratch = nullptr;   // kScratch u64 of device counters
     uint64_t launches = 0;
     bool count_probes = false;        // instrumented search kernel (reference-semantics probe counts)
+    int search_dynamic = 0;           // k_search_dyn: lanes take the next read when theirs is done (A/B; see kernels.cuh)
     int search_both = 4;              // both strands in one pass, this many positions per strand and batch (scan_both); 0: forward scan, then reverse (A/B)
     bool binned_index = true;         // L2-blocked insert for DRAM-resident filters
     bool region_passes = false;       // ... by region passes over the stream (false, default: sort keys by region first)
@@ -255,6 +256,7 @@ extern "C" int commet_ctx_create(int device, commet_ctx **out)
         if (gran) { if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) cudaGetLastError(); }
     }
     if (const char *e = getenv("COMMET_B200_SEARCH_BOTH")) c->search_both = atoi(e);
+    if (const char *e = getenv("COMMET_B200_SEARCH_DYNAMIC")) c->search_dynamic = atoi(e);
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&c->scratch, kScratch * sizeof(unsigned long long)));
@@ -1039,7 +1041,13 @@ static int search_launch(commet_ctx *c, commet_reads *r, int k, int t, uint32_t 
     unsigned bps = 512;
     if (const char *e = getenv("COMMET_B200_SEARCH_BPS")) bps = (unsigned)atoi(e);
     unsigned g = grid_for(c, r->n_reads, 256, bps);
-    if (c->count_probes)
+    if (!c->count_probes && c->search_dynamic) {
+        // persistent warps, reads handed out from a cursor (scratch[170]); search_dynamic = resident blocks per SM
+        unsigned long long *cursor = c->scratch + 170;
+        CK(cudaMemsetAsync(cursor, 0, sizeof *cursor, c->stream));
+        const unsigned gd = (unsigned)std::min<uint64_t>((r->n_reads + 255) / 256, (uint64_t)c->sm_count * (unsigned)c->search_dynamic);
+        k_search_dyn<4><<<gd, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel, cursor);
+    } else if (c->count_probes)
         k_search<true, 0><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
     else if (c->search_both == 2)
         k_search<false, 2><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);

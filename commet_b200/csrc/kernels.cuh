@@ -907,6 +907,172 @@ k_search(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
     }
 }
 
+// ---- search with dynamic read hand-out (A/B: COMMET_B200_SEARCH_DYNAMIC=1) ----
+// k_search gives every thread ONE read; the lanes of a warp finish at different times (a copy is found after a few
+// probes, a read without a shared k-mer costs 2(L-k+1)), and reads already tagged by an earlier chunk leave their
+// lanes idle from the start: 9.9 of 32 lanes are active on average at C2.  That does not matter while the DRAM
+// row-activation rate is the limit (k >= 28), it does when the filter is L2-resident (k <= 27).  Here a lane that
+// finishes its read takes the next one: warps claim runs of kDynChunk reads from a global cursor and hand them to
+// their free lanes by ballot rank; the scan of a read is the state machine below, one batch per step, the same
+// probes in the same order as scan_both.
+struct ScanState {
+    uint64_t o, wi;
+    uint4 q0, q1, q2;
+    uint32_t npos, nf, nr;
+    int seen_f, seen_r, focus;
+};
+
+__device__ __forceinline__ void scan_init(ScanState &s, const uint4 *__restrict__ planes, uint64_t o, uint32_t npos)
+{
+    s.o = o;
+    s.npos = npos;
+    s.wi = o >> 5;
+    s.q0 = planes[s.wi]; s.q1 = planes[s.wi + 1]; s.q2 = planes[s.wi + 2];
+    s.seen_f = s.seen_r = 0;
+    s.nf = s.nr = 0;
+    s.focus = 0;
+}
+
+// one iteration of scan_both's loop: 0 = go on, 1 = read found, 2 = both strands scanned without t hits
+template <int U>
+__device__ __forceinline__ int scan_step(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
+                                         ScanState &s, int k, int t, uint64_t mask)
+{
+    const bool use_f = s.focus != 2 && s.nf < s.npos, use_r = s.focus != 1 && s.nr < s.npos;
+    if (!use_f && !use_r) {
+        if (s.focus == 0) return 2;
+        s.focus = 0;                                     // the focused strand ended below t: the other one resumes
+        return 0;
+    }
+    const uint32_t p = use_f && use_r ? (s.nf < s.nr ? s.nf : s.nr) : (use_f ? s.nf : s.nr);
+    const uint64_t b = s.o + p;
+    const uint64_t need = b >> 5;
+    if (need != s.wi) {
+        if (need < s.wi || need - s.wi >= 3) {
+            s.wi = need;
+            s.q0 = planes[s.wi]; s.q1 = planes[s.wi + 1]; s.q2 = planes[s.wi + 2];
+        } else {
+            do {
+                s.q0 = s.q1; s.q1 = s.q2; s.q2 = planes[s.wi + 3]; s.wi++;
+            } while (s.wi != need);
+        }
+    }
+    const uint32_t sh = (uint32_t)b & 31u;
+    const uint32_t rem = s.npos - p;
+    const uint32_t wv = __funnelshift_r(s.q0.w, s.q1.w, sh);
+    const uint32_t m = wv & ((rem >= (uint32_t)U) ? ((1u << U) - 1u) : ((1u << rem) - 1u));
+    if (m == 0) {
+        const uint32_t vis = rem < 32u ? rem : 32u;
+        const uint32_t mv = (vis >= 32u) ? wv : (wv & ((1u << vis) - 1u));
+        const uint32_t to = p + (mv ? (uint32_t)(__ffs(mv) - 1) : vis);
+        if (use_f && s.nf < to) s.nf = to;
+        if (use_r && s.nr < to) s.nr = to;
+        return 0;
+    }
+    const uint32_t mf = !use_f || s.nf >= p + U ? 0u : (s.nf > p ? (m & (~0u << (s.nf - p))) : m);
+    const uint32_t mr = !use_r || s.nr >= p + U ? 0u : (s.nr > p ? (m & (~0u << (s.nr - p))) : m);
+    const uint64_t hv = window64(s.q0.x, s.q1.x, s.q2.x, sh);
+    const uint64_t lv = window64(s.q0.y, s.q1.y, s.q2.y, sh);
+    uint32_t af[U], ar[U];
+    uint64_t kf[U], kr[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        kf[u] = __brevll(hv >> u) >> (64 - k);
+        kr[u] = ~(hv >> u) & mask;
+        af[u] = ar[u] = 0;
+        if ((mf >> u) & 1u) af[u] = ld_probe_u32(filter + key_word(kf[u]));
+        if ((mr >> u) & 1u) ar[u] = ld_probe_u32(filter + key_word(kr[u]));
+    }
+    bool hit_f = false, hit_r = false;
+    unsigned int dummy = 0;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if (!hit_f && ((mf >> u) & 1u) && (af[u] & key_bit(kf[u], 0))) {
+            Keys q = make_keys(hv >> u, lv >> u, k, mask, false);
+            if (probe_bcd(filter, q, dummy)) { hit_f = true; s.seen_f++; s.nf = p + (uint32_t)u + (uint32_t)k; }
+        }
+        if (!hit_r && ((mr >> u) & 1u) && (ar[u] & key_bit(kr[u], 0))) {
+            Keys q = make_keys(hv >> u, lv >> u, k, mask, true);
+            if (probe_bcd(filter, q, dummy)) { hit_r = true; s.seen_r++; s.nr = p + (uint32_t)u + (uint32_t)k; }
+        }
+    }
+    if ((hit_f && s.seen_f >= t) || (hit_r && s.seen_r >= t)) return 1;
+    if (use_f && !hit_f && s.nf < p + U) s.nf = p + U;
+    if (use_r && !hit_r && s.nr < p + U) s.nr = p + U;
+    if (s.focus == 0) s.focus = hit_f ? 1 : (hit_r ? 2 : 0);
+    return 0;
+}
+
+constexpr unsigned kDynChunk = 256;          // reads a warp claims at a time
+
+template <int U>
+__global__ void __launch_bounds__(256, 4)
+k_search_dyn(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
+             const uint64_t *__restrict__ offs, uint64_t n_reads, int k, int t,
+             uint32_t *__restrict__ tags, unsigned long long *__restrict__ counters,
+             const uint32_t *__restrict__ sel, unsigned long long *__restrict__ cursor)
+{
+    const uint64_t mask = (1ull << k) - 1;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    uint64_t cur = 0, end = 0, r = 0;                  // cur/end: the warp's claimed run (warp-uniform)
+    bool exhausted = false, active = false;
+    ScanState s;
+    unsigned int found = 0, searched = 0;
+    while (true) {
+        // hand the next reads of the run to the lanes without one, in lane order
+        while (true) {
+            const unsigned need = __ballot_sync(0xffffffffu, !active);
+            if (!need) break;
+            if (cur >= end) {
+                if (exhausted) break;
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kDynChunk);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= n_reads) { exhausted = true; break; }
+                cur = base;
+                end = base + kDynChunk < n_reads ? base + kDynChunk : n_reads;
+            }
+            const uint64_t avail = end - cur;
+            const unsigned rank = __popc(need & lt), cnt = __popc(need);
+            if (!active && rank < avail) {
+                const uint64_t rr = cur + rank;
+                const bool selected = !sel || ((sel[rr >> 5] >> (rr & 31)) & 1u);        // fasta_file.h:143-152
+                if (selected && !((tags[rr >> 5] >> (rr & 31)) & 1u)) {                  // file_manager.h:99
+                    searched++;
+                    const uint64_t o = offs[rr];
+                    const uint64_t len = offs[rr + 1] - o;
+                    if (len >= (uint64_t)k) {
+                        scan_init(s, planes, o, (uint32_t)(len - k + 1));
+                        r = rr;
+                        active = true;
+                    }
+                }
+            }
+            cur += cnt < avail ? cnt : avail;
+        }
+        if (!__any_sync(0xffffffffu, active)) break;   // no read left to claim and none in flight
+        if (active) {
+            const int st = scan_step<U>(filter, planes, s, k, t, mask);
+            if (st) {
+                active = false;
+                if (st == 1) {
+                    atomicOr(&tags[r >> 5], 1u << (r & 31));
+                    found++;
+                }
+            }
+        }
+    }
+    for (int d = 16; d; d >>= 1) {
+        found += __shfl_xor_sync(0xffffffffu, found, d);
+        searched += __shfl_xor_sync(0xffffffffu, searched, d);
+    }
+    if (lane == 0) {
+        if (found) atomicAdd(&counters[0], (unsigned long long)found);
+        if (searched) atomicAdd(&counters[1], (unsigned long long)searched);
+    }
+}
+
 // ------------------------------------------------ stage 3: filter_reads ----
 // classes: 0 selected, 1 too short, 2 too many N, 3 low Shannon, 4 undecided
 // (|H - e| within the device/glibc log margin: resolved by the host from the
