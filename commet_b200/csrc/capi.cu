@@ -1046,7 +1046,10 @@ static int search_launch(commet_ctx *c, commet_reads *r, int k, int t, uint32_t 
         unsigned long long *cursor = c->scratch + 170;
         CK(cudaMemsetAsync(cursor, 0, sizeof *cursor, c->stream));
         const unsigned gd = (unsigned)std::min<uint64_t>((r->n_reads + 255) / 256, (uint64_t)c->sm_count * (unsigned)c->search_dynamic);
-        k_search_dyn<4><<<gd, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel, cursor);
+        if (c->search_dynamic >= 4)      // 64 registers (a few spilled), 4 resident blocks per SM
+            k_search_dyn<4, 4><<<gd, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel, cursor);
+        else                             // 73 registers, 3 resident blocks per SM
+            k_search_dyn<4, 3><<<gd, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel, cursor);
     } else if (c->count_probes)
         k_search<true, 0><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
     else if (c->search_both == 2)

@@ -1005,8 +1005,8 @@ __device__ __forceinline__ int scan_step(const uint32_t *__restrict__ filter, co
 
 constexpr unsigned kDynChunk = 256;          // reads a warp claims at a time
 
-template <int U>
-__global__ void __launch_bounds__(256, 4)
+template <int U, int BPS>
+__global__ void __launch_bounds__(256, BPS)
 k_search_dyn(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
              const uint64_t *__restrict__ offs, uint64_t n_reads, int k, int t,
              uint32_t *__restrict__ tags, unsigned long long *__restrict__ counters,
