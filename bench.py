@@ -260,7 +260,9 @@ def main():
                 "single index_and_search" + (f", reference set dealt block-cyclically over {world} GPUs (each holds 1/{world}), one "
                                              f"query set per GPU" if world > 1 else ""))
     config = {"workload": workload, "reads_per_set": args.reads, "read_len": args.length, "k": args.k, "t": args.t,
-              "filter_bytes": 1 << (args.k - 1), "l2_policy": "inputs larger than L2 (2 GB of bases + 4 GiB filter per step)"}
+              "filter_bytes": 1 << (args.k - 1),
+              "l2_policy": f"inputs larger than L2 ({2 * args.reads * args.length / 1e9:.1f} GB of bases + "
+                           f"{(1 << (args.k - 1)) / 2**20:.0f} MiB filter per step, 126 MB L2)"}
 
     if args.impl == "reference":
         return reference_arm(args, rank, world, config)
