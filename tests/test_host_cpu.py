@@ -1,0 +1,148 @@
+"""CPU: the C++ host side of the drop-in tools without a GPU -- the fof grammar (csrc/host/set_parser.hpp =
+include/set_parser.h:46-102), the read-file parsers (csrc/host/readers.hpp = FastaFile/FastqFile and their gzip
+twins), the valid-read stream and per-file vectors of a set (csrc/host/read_set.hpp = FileManager,
+include/file_manager.h:88-112,117-222,245-252) and the .bv files (csrc/host/bv.hpp = boolean_vector.h:302-414).
+A tiny driver built from those headers dumps what the tools would hand to the C-ABI; the expectation comes from the
+oracle's restatements of the same formats (pinned against the reference binaries in test_oracle_vs_ref.py)."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import helpers as H
+
+ROOT = Path(__file__).resolve().parent.parent
+HOST = ROOT / "commet_b200" / "csrc" / "host"
+
+DRIVER = r'''
+#include "read_set.hpp"
+#include "set_parser.hpp"
+#include <cstdio>
+using namespace commet_host;
+// argv: <fof> <out_dir> <suffix>: dumps every set's valid-read stream, tags every 3rd valid read (and the last one)
+// and writes the per-file vectors as FileManager::save_bv does
+int main(int argc, char **argv)
+{
+    if (argc < 4) return 2;
+    std::map<std::string, SetSpec> sets = read_sets(argv[1]);
+    for (auto &kv : sets) {
+        ReadSet rs;
+        rs.nickname = kv.first;
+        for (size_t i = 0; i < kv.second.files.size(); i++) rs.add_file(kv.second.files[i], kv.second.bvs[i]);
+        rs.build_stream(false);
+        printf("SET\t%s\t%zu\t%llu\n", kv.first.c_str(), rs.files.size(), (unsigned long long)rs.n_valid());
+        for (uint64_t r = 0; r < rs.n_valid(); r++) {
+            fwrite(rs.bases.data() + rs.offs[r], 1, rs.offs[r + 1] - rs.offs[r], stdout);
+            fputc('\n', stdout);
+        }
+        for (auto &f : rs.files) printf("FILE\t%s\t%llu\t%zu\n", f.fname.c_str(), (unsigned long long)f.nb_reads, f.valid_pos.size());
+        std::vector<uint8_t> tags(rs.n_valid() / 8 + 1, 0);
+        for (uint64_t r = 0; r < rs.n_valid(); r++)
+            if (r % 3 == 0 || r + 1 == rs.n_valid()) tags[r / 8] |= (uint8_t)(1u << (r % 8));
+        rs.scatter_tags(tags);
+        rs.save_bv(argv[2], std::string(argv[3]) + kv.first);
+    }
+    return 0;
+}
+'''
+
+
+@pytest.fixture(scope="module")
+def driver(tmp_path_factory):
+    d = tmp_path_factory.mktemp("hostdrv")
+    (d / "drv.cpp").write_text(DRIVER)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", str(HOST), "-o", str(d / "drv"), str(d / "drv.cpp"), "-lz"], check=True)
+    return d / "drv"
+
+
+def _write_file(rng, path, reads, kind):
+    if kind == 0:
+        return H.write_fasta(path.with_suffix(".fa"), reads, final_newline=bool(rng.integers(0, 2)))
+    if kind == 1:
+        return H.write_fasta(path.with_suffix(".fa"), reads, width=int(rng.integers(5, 40)), final_newline=bool(rng.integers(0, 2)),
+                             blank_every=int(rng.integers(0, 4)))
+    if kind == 2:
+        return H.write_fastq(path.with_suffix(".fq"), reads, final_newline=bool(rng.integers(0, 2)))
+    if kind == 3:
+        return H.write_fasta(path.with_suffix(".fa.gz"), reads, gz=True, width=int(rng.choice([0, 17])) or None)
+    return H.write_fastq(path.with_suffix(".fq.gz"), reads, gz=True)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_sets_streams_and_vectors(driver, tmp_path, seed):
+    rng = np.random.default_rng(4000 + seed)
+    n_sets = int(rng.integers(1, 4))
+    lines, expect = [], {}
+    for s in range(n_sets):
+        name = ["zeta", "Alpha", "m 1", "b"][s] if seed % 2 else f"S{9 - s}"
+        items, stream, files = [], [], []
+        for fi in range(int(rng.integers(1, 4))):
+            reads = H.make_ref_set(rng, int(rng.integers(1, 80)), 1, 70, p_N=0.03, p_lower=0.2)
+            p = _write_file(rng, tmp_path / f"s{s}_f{fi}", reads, int(rng.integers(0, 5)))
+            n = len(reads)
+            if rng.integers(0, 2):
+                valid = (rng.random(n) < 0.6).astype(np.uint8)
+                bvp = tmp_path / f"s{s}_f{fi}.in.bv"
+                oracle.write_bv_file(bvp, b"some input\nvector", n, oracle.tags_to_bv(valid))
+                items.append(f" {p} , {bvp} " if seed % 3 == 0 else f"{p},{bvp}")
+            else:
+                valid = np.ones(n, dtype=np.uint8)
+                items.append(f"  {p}" if seed % 3 == 0 else str(p))
+            stream += [r for r, v in zip(reads, valid) if v]
+            files.append((p, n, valid))
+        lines.append((name + ":" if not (seed % 4 == 3 and s == 0) else "") + ";".join(items))
+        expect[name if not (seed % 4 == 3 and s == 0) else "SET1"] = (stream, files)
+    fof = tmp_path / "sets.txt"
+    fof.write_text("\n".join(lines) + ("\n\n" if seed % 2 else ""))
+    # the oracle's restatement of the grammar agrees on names, order, files and vectors
+    parsed = oracle.parse_fof(fof)
+    assert [p[0] for p in parsed] == sorted(expect)
+    out = tmp_path / "bv"
+    out.mkdir()
+    r = subprocess.run([str(driver), str(fof), str(out), "in_"], capture_output=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    rows = r.stdout.split(b"\n")
+    i = 0
+    for name in sorted(expect):                    # std::map order = sorted names (set_parser.h:46)
+        stream, files = expect[name]
+        head = rows[i].split(b"\t")
+        assert head[0] == b"SET" and head[1].decode() == name and int(head[2]) == len(files) and int(head[3]) == len(stream)
+        assert rows[i + 1:i + 1 + len(stream)] == stream
+        i += 1 + len(stream)
+        # tags of every 3rd valid read (and the last) land on the reads' RECORD positions in their files
+        tag = np.zeros(len(stream), dtype=np.uint8)
+        tag[::3] = 1
+        if len(stream):
+            tag[-1] = 1
+        s0 = 0
+        for (p, n, valid) in files:
+            frow = rows[i].split(b"\t")
+            i += 1
+            nv = int(valid.sum())
+            assert frow[0] == b"FILE" and frow[1].decode() == str(p) and int(frow[2]) == n and int(frow[3]) == nv
+            exp_bits = np.zeros(n, dtype=np.uint8)
+            exp_bits[np.nonzero(valid)[0]] = tag[s0:s0 + nv]
+            s0 += nv
+            comment, nbits, payload = oracle.read_bv_file(out / f"{p.name}_in_in_{name}.bv")      # file_manager.h:247
+            assert comment == f"{p} in in_{name}".encode() and nbits == n                       # :248
+            assert np.array_equal(payload, oracle.tags_to_bv(exp_bits))
+
+
+def test_vector_size_mismatch_and_unknown_format_follow_the_reference(driver, tmp_path):
+    reads = [b"ACGT", b"GGCC"]
+    fa = H.write_fasta(tmp_path / "a.fa", reads)
+    bad = tmp_path / "bad.bv"
+    oracle.write_bv_file(bad, b"x", 3, oracle.tags_to_bv(np.ones(3, dtype=np.uint8)))
+    (tmp_path / "f1.txt").write_text(f"s:{fa},{bad}\n")
+    (tmp_path / "o").mkdir()
+    r = subprocess.run([str(driver), str(tmp_path / "f1.txt"), str(tmp_path / "o"), "x"], capture_output=True)
+    assert r.returncode == 1 and b"boolean vector size are not equal -> quit" in r.stderr       # fasta_file.h:104-107
+    junk = tmp_path / "junk.txt"
+    junk.write_bytes(b"not a read file\n")
+    (tmp_path / "f2.txt").write_text(f"s:{junk};{fa}\n")
+    r = subprocess.run([str(driver), str(tmp_path / "f2.txt"), str(tmp_path / "o"), "x"], capture_output=True)
+    # an unusable file is ignored with a message, the set goes on with the others (file_manager.h:150-156)
+    assert r.returncode == 0 and b"-> ignore" in r.stderr
+    assert r.stdout.split(b"\n")[0] == b"SET\ts\t1\t2"
