@@ -18,18 +18,26 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
-def write_fasta_fixed(path, arr):
-    """arr: (n, L) uint8 ACGT -> '>%09d\\n' + L bases + '\\n' per record, vectorised"""
+def write_fasta_fixed(path, arr, first=0, append=False):
+    """arr: (n, L) uint8 ACGT -> '>%09d\\n' + L bases + '\\n' per record (numbered from `first`), vectorised"""
     n, L = arr.shape
     rec = np.empty((n, 11 + L + 1), dtype=np.uint8)
     rec[:, 0] = ord(">")
-    idx = np.arange(n)
+    idx = np.arange(first, first + n)
     for d in range(9):
         rec[:, 9 - d] = ord("0") + (idx // 10 ** d) % 10
     rec[:, 10] = ord("\n")
     rec[:, 11:11 + L] = arr
     rec[:, 11 + L] = ord("\n")
-    rec.tofile(path)
+    with open(path, "ab" if append else "wb") as f:
+        rec.tofile(f)
+
+
+def write_fasta_blocks(path, blocks):
+    first = 0
+    for i, arr in enumerate(blocks):
+        write_fasta_fixed(path, arr, first, append=i > 0)
+        first += arr.shape[0]
 
 
 def main():
@@ -49,36 +57,50 @@ def main():
     from commet_b200 import build
     build.build_all()
     dev = torch.device("cuda", 0)
-    work = Path(tempfile.mkdtemp(prefix="nxn_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None))
     S, R, L = args.sets, args.reads, args.length
+    need = S * R * (L + 12) * 1.1                  # FASTA bytes + outputs
+    base = None
+    for cand in ("/dev/shm", tempfile.gettempdir()):
+        if os.path.isdir(cand) and shutil.disk_usage(cand).free > need:
+            base = cand
+            break
+    work = Path(tempfile.mkdtemp(prefix="nxn_", dir=base))
     g = torch.Generator(device=dev)
     g.manual_seed(1000)
     acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
     comp = torch.zeros(256, dtype=torch.uint8, device=dev)
     for a, b in zip(b"ACGT", b"TGCA"):
         comp[a] = b
-    pool = acgt[torch.randint(0, 4, (R, L), generator=g, device=dev)]
+    pool = torch.empty((R, L), dtype=torch.uint8, device=dev)
+    for b0 in range(0, R, 2_000_000):              # in blocks: the int64 index tensor of a 20 M x 150 draw alone is 24 GB
+        m = min(2_000_000, R - b0)
+        pool[b0:b0 + m] = acgt[torch.randint(0, 4, (m, L), generator=g, device=dev)]
     t0 = time.perf_counter()
     lines = []
     from concurrent.futures import ThreadPoolExecutor
     pool_w = ThreadPoolExecutor(max_workers=6)     # formatting + writing a set overlaps the generation of the next ones
     pending = []
+    BLOCK = 2_000_000                              # reads generated at a time: bounds the device memory of the recipe
     for s in range(S):
         g.manual_seed(2000 + s)
-        src = torch.randint(0, R, (R,), generator=g, device=dev)
-        cp = pool[src]
-        rc = torch.rand(R, generator=g, device=dev) < 0.5
-        cp = torch.where(rc[:, None], comp[cp.flip(1).long()], cp)
-        mut = torch.rand((R, L), generator=g, device=dev) < 0.01
-        rnd = acgt[torch.randint(0, 4, (R, L), generator=g, device=dev)]
-        cp = torch.where(mut, rnd, cp)
-        shared = torch.rand(R, generator=g, device=dev) < 0.5
-        fresh = acgt[torch.randint(0, 4, (R, L), generator=g, device=dev)]
-        arr = torch.where(shared[:, None], cp, fresh).cpu().numpy()
-        pending.append(pool_w.submit(write_fasta_fixed, work / f"set{s}.fa", arr))
+        blocks = []
+        for b0 in range(0, R, BLOCK):
+            m = min(BLOCK, R - b0)
+            src = torch.randint(0, R, (m,), generator=g, device=dev)
+            cp = pool[src]
+            rc = torch.rand(m, generator=g, device=dev) < 0.5
+            cp = torch.where(rc[:, None], comp[cp.flip(1).long()], cp)
+            mut = torch.rand((m, L), generator=g, device=dev) < 0.01
+            rnd = acgt[torch.randint(0, 4, (m, L), generator=g, device=dev)]
+            cp = torch.where(mut, rnd, cp)
+            shared = torch.rand(m, generator=g, device=dev) < 0.5
+            fresh = acgt[torch.randint(0, 4, (m, L), generator=g, device=dev)]
+            blocks.append(torch.where(shared[:, None], cp, fresh).cpu().numpy())
+        pending.append(pool_w.submit(write_fasta_blocks, work / f"set{s}.fa", blocks))
         lines.append(f"set{s}:set{s}.fa")
         if s < 3 and args.ref_sample:
-            write_fasta_fixed(work / f"sample{s}.fa", arr[:args.ref_sample])
+            write_fasta_fixed(work / f"sample{s}.fa", blocks[0][:args.ref_sample])
+        del blocks
     for f in pending:
         f.result()
     (work / "cfg.txt").write_text("\n".join(lines) + "\n")
