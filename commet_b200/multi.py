@@ -22,8 +22,8 @@ Two placements of the reference set are supported:
                   global reads, so on every rank it is a contiguous range of LOCAL reads, evenly loaded whatever
                   the chunk.  The stop rule of index_reads needs the k-mer counts of all reads in global order:
                   the ranks exchange their local totals (one number each) and, only if the limit is reached at
-                  all, their per-read counts (4 bytes per read); every rank then walks the same array
-                  (distributed_index_and_search).  Host-to-device traffic and device memory for the reference
+                  all, their per-block totals; the read that closes a chunk is resolved by the rank owning its
+                  block (distributed_plan, distributed_index_and_search).  Host-to-device traffic and device memory for the reference
                   set are 1/world of the replicated placement.
 
 The loops are written against a small backend protocol so that the sharding/merge logic is testable on CPU
@@ -165,23 +165,62 @@ def chunk_bounds(counts, max_kmer: int) -> list[tuple[int, int]]:
 
 def distributed_plan(local_total: int, local_counts, n_global: int, world: int, rank: int, block: int, max_kmer: int,
                      all_gather):
-    """Chunk plan of the whole reference set from every rank's local k-mer counts.  all_gather(obj) -> list of
-    every rank's obj.  Fast path: the total never reaches max_kmer (one chunk) and only the totals travel;
-    local_counts() (per-read u32 counts of the local shard) is called only otherwise."""
+    """Chunk plan of the whole reference set from every rank's local k-mer counts.  all_gather(obj) -> list of every
+    rank's obj.  Fast path: the total never reaches max_kmer (one chunk) and only the totals travel; local_counts()
+    (per-read u32 counts of the local shard) is called only otherwise.  Then the ranks exchange their per-BLOCK
+    totals (n_global / block numbers in all) and walk them together; the read at which a chunk closes is resolved by
+    the rank that owns the block it falls in, from its own per-read counts, and announced to the others -- one or
+    two small exchanges per chunk, nothing per read.  Same plan as chunk_bounds() on the global count array."""
     import numpy as np
     totals = all_gather(int(local_total))
     if n_global == 0:
         return []
     if sum(totals) < max_kmer:
         return [(0, n_global)]
-    parts = all_gather(np.ascontiguousarray(local_counts(), dtype=np.uint32))
-    counts = np.empty(n_global, dtype=np.uint32)
+    if max_kmer <= 0:
+        return []
+    counts = np.ascontiguousarray(local_counts(), dtype=np.uint64)
+    n_local = local_index(n_global, world, rank, block)
+    if len(counts) != n_local:
+        raise ValueError(f"rank {rank} holds {len(counts)} reads, its blocks of {n_global} reads are {n_local}")
+    n_blocks = (n_global + block - 1) // block
+    mine = np.add.reduceat(counts, np.arange(0, n_local, block)) if n_local else np.zeros(0, dtype=np.uint64)
+    parts = all_gather(np.ascontiguousarray(mine, dtype=np.uint64))
+    T = np.zeros(n_blocks, dtype=np.uint64)
     for r in range(world):
-        m = owned_mask(n_global, world, r, block)
-        if int(m.sum()) != len(parts[r]):
-            raise ValueError(f"rank {r} holds {len(parts[r])} reads, its blocks of {n_global} reads are {int(m.sum())}")
-        counts[m] = parts[r]
-    return chunk_bounds(counts, max_kmer)
+        T[r::world] = parts[r]
+    csT = np.cumsum(T, dtype=np.uint64)                    # inclusive prefix over blocks
+
+    def resolve(g0: int, g1: int, cum: int):
+        """reads [g0, g1) of ONE block: (index of the read where cum reaches max_kmer or None, k-mers of the range)"""
+        if (g0 // block) % world != rank:
+            return None
+        l0, l1 = local_index(g0, world, rank, block), local_index(g1, world, rank, block)
+        cs = np.cumsum(counts[l0:l1], dtype=np.uint64)
+        if len(cs) == 0:
+            return (None, 0)
+        idx = int(np.searchsorted(cs, np.uint64(max_kmer - cum), side="left"))
+        return (g0 + idx if idx < len(cs) else None, int(cs[-1]))
+
+    def ask(g0: int, g1: int, cum: int):
+        return next(a for a in all_gather(resolve(g0, g1, cum)) if a is not None)
+
+    plan, i = [], 0
+    while i < n_global:
+        b = i // block
+        j, head = ask(i, min((b + 1) * block, n_global), 0)          # from read i to the end of its block
+        if j is None:
+            # whole blocks after b: the first one in which the running count reaches max_kmer
+            target = np.uint64(max_kmer - head) + csT[b]
+            b2 = int(np.searchsorted(csT, target, side="left"))
+            if b2 >= n_blocks:
+                plan.append((i, n_global))                            # the limit is not reached again
+                break
+            cum = head + int(csT[b2 - 1] - csT[b])
+            j, _ = ask(b2 * block, min((b2 + 1) * block, n_global), cum)
+        plan.append((i, j + 1))
+        i = j + 2                                                     # read j+1 is fetched and lost (index_reads.h:60)
+    return plan
 
 
 def distributed_index_and_search(backend, barrier: Barrier, all_gather, world: int, rank: int, k: int, t: int,

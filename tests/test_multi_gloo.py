@@ -235,3 +235,52 @@ def test_chunk_bounds_is_the_stop_rule_of_index_reads():
             plan.append((pos, pos + ni))
             pos = nxt
         assert multi.chunk_bounds(counts, maxk) == plan, (trial, k, maxk)
+
+
+def _plan_in_lockstep(counts, world, block, maxk):
+    """multi.distributed_plan on `world` threads exchanging through a barrier (no process group needed)"""
+    import threading
+    n = len(counts)
+    barrier = threading.Barrier(world)
+    slots, results, errs = [None] * world, [None] * world, []
+
+    def gather_for(rank):
+        def all_gather(obj):
+            slots[rank] = obj
+            barrier.wait()
+            out = list(slots)
+            barrier.wait()
+            return out
+        return all_gather
+
+    def run(rank):
+        try:
+            loc = np.asarray(counts, dtype=np.uint32)[multi.owned_mask(n, world, rank, block)]
+            results[rank] = multi.distributed_plan(int(loc.sum()), lambda: loc, n, world, rank, block, maxk, gather_for(rank))
+        except Exception as e:              # pragma: no cover
+            errs.append(e)
+            barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errs, errs
+    assert all(r == results[0] for r in results)        # every rank arrives at the same plan
+    return results[0]
+
+
+def test_two_level_distributed_plan_equals_the_global_walk():
+    """per-block totals + owner-resolved boundary reads give chunk_bounds() of the global per-read counts, wherever
+    the boundaries and the lost reads fall relative to the blocks (block sizes 1..100, 1..4 ranks, zero-count reads)"""
+    rng = np.random.default_rng(0)
+    for trial in range(400):
+        n = int(rng.integers(0, 80))
+        world = int(rng.integers(1, 5))
+        block = int(rng.choice([1, 2, 3, 7, 16, 100]))
+        counts = rng.integers(0, int(rng.choice([1, 3, 30])), size=n)
+        if rng.random() < 0.3 and n:
+            counts[rng.integers(0, n, size=max(1, n // 4))] = 0
+        maxk = int(rng.choice([1, 2, 5, 17, 60, 10 ** 6]))
+        assert _plan_in_lockstep(counts, world, block, maxk) == multi.chunk_bounds(counts, maxk), (trial, n, world, block, maxk)
