@@ -276,6 +276,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries ONE JSON line: NCCL writes its version banner / warnings to stdout unless told otherwise
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     ctx = commet_b200.Context(local_rank)
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
