@@ -63,8 +63,8 @@ def build_tools(force: bool = False) -> list[Path]:
         exe = BIN / t
         if t in HOST_ONLY:
             if force or _stale(exe, [src, *hdrs]):
-                subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-I", str(CSRC / "host"), "-o", str(exe), str(src),
-                                "-lz"], check=True)
+                subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-I", str(CSRC / "host"), "-o", str(exe),
+                                str(src), "-lz"], check=True)
         elif force or _stale(exe, [src, *hdrs, LIB]):
             subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-I", str(ROOT / "include"), "-I", str(CSRC / "host"),
                             "-o", str(exe), str(src), "-L", str(LIB.parent), "-lcommet_b200",

@@ -10,11 +10,16 @@
 #include <stdint.h>
 #include <zlib.h>
 
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include "fast_fasta.hpp"
 
 namespace commet_host {
 
@@ -145,10 +150,46 @@ inline void parse_fastq(const std::string &t, ParsedFile &pf)
     pf.off.push_back(pf.seq.size());
 }
 
+// Plain FASTA files of at least COMMET_B200_FAST_FASTA_MIN bytes (default 64 MiB): mmap + chunked two-pass loader
+// on up to 16 threads (fast_fasta.hpp; same record rules as parse_fasta, checked against it in
+// tests/test_nxn_host.py and tests/test_host_cpu.py) instead of slurping the file and parsing it on one core.
+inline bool parse_fasta_parallel(const std::string &fname, ParsedFile &pf)
+{
+    uint64_t min_bytes = 64ull << 20;
+    if (const char *e = getenv("COMMET_B200_FAST_FASTA_MIN")) min_bytes = strtoull(e, nullptr, 10);
+    FastaMap m;
+    if (!m.open(fname, 16u << 20)) return false;
+    if (m.size < min_bytes) { m.close(); return false; }
+    const size_t nc = m.n_chunks();
+    const unsigned nt = (unsigned)std::min<size_t>(std::max(1u, std::min(std::thread::hardware_concurrency(), 16u)), nc);
+    auto parallel_for = [&](auto fn) {
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> th;
+        for (unsigned w = 1; w < nt; w++)
+            th.emplace_back([&]() { for (size_t c; (c = next.fetch_add(1)) < nc;) fn(c); });
+        for (size_t c; (c = next.fetch_add(1)) < nc;) fn(c);
+        for (auto &t : th) t.join();
+    };
+    parallel_for([&](size_t c) { m.pass<false>(c, nullptr, 0, nullptr, 0); });
+    m.finish_scan();
+    pf.seq.resize(m.n_bytes);
+    pf.off.assign(m.n_records + 1, 0);
+    pf.off[m.n_records] = m.n_bytes;
+    std::vector<uint64_t> pos(nc + 1, 0), rec(nc + 1, 0);
+    for (size_t c = 0; c < nc; c++) { pos[c + 1] = pos[c] + m.bytes[c]; rec[c + 1] = rec[c] + m.records[c]; }
+    parallel_for([&](size_t c) { m.pass<true>(c, pf.seq.data(), pos[c], pf.off.data(), rec[c]); });
+    pf.nb_reads = m.n_records;
+    pf.format = Format::Fasta;
+    pf.gz = false;
+    m.close();
+    return true;
+}
+
 inline bool parse_reads_file(const std::string &fname, ParsedFile &pf, const char *who)
 {
     std::string text;
     pf.fname = fname;
+    if (parse_fasta_parallel(fname, pf)) return true;
     if (!load_text(fname, text, pf.format, pf.gz, who)) return false;
     if (pf.format == Format::Fasta) parse_fasta(text, pf);
     else parse_fastq(text, pf);

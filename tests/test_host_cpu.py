@@ -53,7 +53,8 @@ int main(int argc, char **argv)
 def driver(tmp_path_factory):
     d = tmp_path_factory.mktemp("hostdrv")
     (d / "drv.cpp").write_text(DRIVER)
-    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", str(HOST), "-o", str(d / "drv"), str(d / "drv.cpp"), "-lz"], check=True)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-pthread", "-I", str(HOST), "-o", str(d / "drv"), str(d / "drv.cpp"), "-lz"],
+                   check=True)
     return d / "drv"
 
 
@@ -146,3 +147,35 @@ def test_vector_size_mismatch_and_unknown_format_follow_the_reference(driver, tm
     # an unusable file is ignored with a message, the set goes on with the others (file_manager.h:150-156)
     assert r.returncode == 0 and b"-> ignore" in r.stderr
     assert r.stdout.split(b"\n")[0] == b"SET\ts\t1\t2"
+
+
+def test_parallel_fasta_path_of_the_tools_equals_the_sequential_one(driver, tmp_path):
+    """parse_reads_file switches to the mmap + chunked loader for large plain FASTA files: a 3-chunk file (> 32 MiB,
+    multi-line records) must give the same stream through both paths (COMMET_B200_FAST_FASTA_MIN forces either)."""
+    import hashlib
+    import os
+    rng = np.random.default_rng(77)
+    n, L, width = 300_000, 120, 60
+    arr = H.ACGT[rng.integers(0, 4, size=(n, L))]
+    arr[rng.random(n) < 0.01, 33] = ord("N")
+    with open(tmp_path / "big.fa", "wb") as f:
+        lines = np.empty((n, 2, width + 1), dtype=np.uint8)
+        lines[:, :, :width] = arr.reshape(n, 2, width)
+        lines[:, :, width] = ord("\n")
+        for s in range(0, n, 50_000):
+            e = min(n, s + 50_000)
+            f.write(b"".join(b">read%d\n" % i + lines[i].tobytes() for i in range(s, e)))
+    assert (tmp_path / "big.fa").stat().st_size > (32 << 20)
+    (tmp_path / "big.txt").write_text(f"big:{tmp_path / 'big.fa'}\n")
+    outs = []
+    for min_bytes in ("0", str(1 << 40)):
+        o = tmp_path / f"o{len(outs)}"
+        o.mkdir()
+        r = subprocess.run([str(driver), str(tmp_path / "big.txt"), str(o), "x"], capture_output=True, timeout=120,
+                           env={**os.environ, "COMMET_B200_FAST_FASTA_MIN": min_bytes})
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout)
+    assert hashlib.sha256(outs[0]).digest() == hashlib.sha256(outs[1]).digest()
+    rows = outs[0].split(b"\n")
+    assert rows[0] == b"SET\tbig\t1\t%d" % n
+    assert rows[1] == arr[0].tobytes() and rows[n] == arr[n - 1].tobytes()
