@@ -159,6 +159,35 @@ class ClockSampler:
                 "samples": len(sm), "source": self.source}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """BENCH_NUMA_BIND=1 (opt-in, A/B for the N=8 end-to-end leg): run this rank on the CPUs of its GPU's NUMA node and
+    prefer that node's memory, so that the pinned buffers its H2D copies read from are local to the GPU's PCIe root.
+    Returns what was done (for the JSON line) or None."""
+    if os.environ.get("BENCH_NUMA_BIND", "0") in ("", "0"):
+        return None
+    try:
+        import ctypes
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bdf = f"{getattr(p, 'pci_domain_id', 0):04x}:{p.pci_bus_id:02x}:{getattr(p, 'pci_device_id', 0):02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return {"bdf": bdf, "node": node}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        use = cpus & os.sched_getaffinity(0)
+        if use:
+            os.sched_setaffinity(0, use)
+        libc = ctypes.CDLL("libc.so.6", use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(node + 2))     # x86-64 set_mempolicy(MPOL_PREFERRED)
+        return {"bdf": bdf, "node": node, "cpus": len(use), "set_mempolicy": int(rc)}
+    except Exception as e:                                                           # never fatal: it is an A/B switch
+        return {"error": str(e)[:200]}
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -275,6 +304,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         # stdout carries ONE JSON line: NCCL writes its version banner / warnings to stdout unless told otherwise
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -459,6 +489,8 @@ def main():
     }
     if "phases_ms" in info:
         line["phases_ms_rank0"] = info["phases_ms"]
+    if numa is not None:
+        line["numa_bind_rank0"] = numa
     if world == 1 and srch_ms > 0 and probes:
         # dominant kernel = k_search (one launch per query set and chunk).  Algorithmic bytes (SURVEY 8d,
         # DESIGN.md 5): one Bloom bit test = one 32-byte sector, counted with the REFERENCE's semantics
