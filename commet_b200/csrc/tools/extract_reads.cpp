@@ -199,6 +199,12 @@ int main(int argc, char **argv)
     std::string text;
     Format fmt = Format::Unknown;
     bool gz = false;
+    {
+        // src/extract_reads.cpp:111-114 reports an unreadable file once itself ("file file" is its wording) before the
+        // gzip probe reports it again and exits (:126-130)
+        std::ifstream probe(input_file_name.c_str());
+        if (!probe.good()) std::cerr << "Cannot open file file " << input_file_name << " -> ignore\n";
+    }
     if (!load_text(input_file_name, text, fmt, gz, " -> ignore\n")) return 1;
 
     // the reference's record count = the size the vector must have (fasta_file.h:104-107, fastq_file.h:99-102)

@@ -1,0 +1,54 @@
+"""CPU: what the drop-in executables do BEFORE they need the GPU -- usage, version, unknown options, missing option
+values, missing mandatory arguments, unreadable inputs -- is the reference's, byte for byte on stdout and stderr and in
+the exit code (oracle/_ref = the reference's own sources compiled by oracle/Makefile)."""
+import subprocess
+
+import numpy as np
+import pytest
+
+from commet_b200 import build
+from oracle import oracle
+
+TOOLS = ("index_and_search", "filter_reads", "bvop", "extract_reads")
+pytestmark = pytest.mark.skipif(not all((oracle.REF_DIR / t).exists() for t in TOOLS), reason="oracle/_ref not built")
+
+
+@pytest.fixture(scope="module")
+def work(tmp_path_factory):
+    build.build_tools()
+    d = tmp_path_factory.mktemp("cli")
+    oracle.write_bv_file(d / "a.bv", b"a", 10, oracle.tags_to_bv(np.ones(10, dtype=np.uint8)))
+    (d / "x.fa").write_text(">r\nACGT\n")
+    (d / "sets.txt").write_text("s:x.fa\n")
+    return d
+
+
+CASES = [
+    ("index_and_search", []), ("index_and_search", ["-h"]), ("index_and_search", ["-v"]), ("index_and_search", ["-z"]),
+    ("index_and_search", ["-i"]), ("index_and_search", ["-i", "sets.txt", "-s"]), ("index_and_search", ["-k"]),
+    ("index_and_search", ["-t"]), ("index_and_search", ["-i", "sets.txt"]), ("index_and_search", ["-s", "sets.txt"]),
+    ("index_and_search", ["-i", "nofile.txt", "-s", "nofile.txt", "-o", "o1", "-l", "o1"]),
+    ("index_and_search", ["-k", "31", "-t", "3", "-z"]),
+    ("filter_reads", []), ("filter_reads", ["-h"]), ("filter_reads", ["-v"]), ("filter_reads", ["-z"]),
+    ("filter_reads", ["nofile.fa", "-o", "x.bv"]),
+    ("bvop", []), ("bvop", ["-h"]), ("bvop", ["-v"]), ("bvop", ["-z"]), ("bvop", ["nofile.bv", "-i"]), ("bvop", ["a.bv", "-q"]),
+    ("extract_reads", []), ("extract_reads", ["-h"]), ("extract_reads", ["-v"]), ("extract_reads", ["-z"]),
+    ("extract_reads", ["x.fa"]), ("extract_reads", ["nofile.fa", "a.bv"]), ("extract_reads", ["x.fa", "nofile.bv"]),
+]
+
+
+@pytest.mark.parametrize("tool,args", CASES, ids=[f"{t}-{'_'.join(a) or 'noargs'}" for t, a in CASES])
+def test_cli_behaviour_before_the_gpu_is_needed(work, tool, args):
+    mine = subprocess.run([str(build.BIN / tool), *args], cwd=work, capture_output=True, timeout=60)
+    ref = subprocess.run([str(oracle.REF_DIR / tool), *args], cwd=work, capture_output=True, timeout=60)
+    assert ref.returncode >= 0, "the reference itself crashed on this case: not a comparison"
+    assert mine.returncode == ref.returncode
+    assert mine.stdout == ref.stdout
+    assert mine.stderr == ref.stderr
+
+
+def test_missing_option_values_are_clean_errors_where_the_reference_crashes(work):
+    """`filter_reads x.fa -l` and `bvop a.bv -a` read argv[argc] in the reference (segmentation fault); here exit 1"""
+    for tool, args in (("filter_reads", ["x.fa", "-l"]), ("bvop", ["a.bv", "-a"])):
+        r = subprocess.run([str(build.BIN / tool), *args], cwd=work, capture_output=True, timeout=60)
+        assert r.returncode == 1 and b"needs an argument" in r.stderr
