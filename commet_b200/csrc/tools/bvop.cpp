@@ -81,18 +81,23 @@ int main(int argc, char **argv)
 
     BitVec bv1;
     bv1.read(file_name1);
-    commet_ctx *ctx = nullptr;
-    if (commet_ctx_create(0, &ctx) != 0) die_gpu();
-
-    std::string comment;
-    bool do_nothing = false;
-    if (op == 'a' || op == 'o' || op == 'd') {
-        BitVec bv2;
+    // everything the host can check comes before the device is touched: the second vector is read and sized first
+    // (boolean_vector.h:420-423), and an invocation with nothing to compute never creates a context
+    BitVec bv2;
+    const bool binary = op == 'a' || op == 'o' || op == 'd';
+    if (binary) {
         bv2.read(file_name2);
-        if (bv2.n != bv1.n) {                            // boolean_vector.h:420-423
+        if (bv2.n != bv1.n) {
             std::cerr << "Error: the two vectors are not the same size -> exit\n";
             exit(1);
         }
+    }
+    commet_ctx *ctx = nullptr;
+    if ((binary || op == 'n' || print_info) && commet_ctx_create(0, &ctx) != 0) die_gpu();
+
+    std::string comment;
+    bool do_nothing = false;
+    if (binary) {
         int code = op == 'a' ? COMMET_BV_AND : op == 'o' ? COMMET_BV_OR : COMMET_BV_ANDNOT;
         if (commet_bvop(ctx, code, bv1.bytes.data(), bv2.bytes.data(), bv1.bytes.data(), bv1.bytes.size()) != 0) die_gpu();
         comment = file_name1 + (op == 'a' ? " AND " : op == 'o' ? " OR " : " AND (NOT ") + file_name2 +
@@ -111,7 +116,7 @@ int main(int argc, char **argv)
         std::cout << "\nReads:\n";
         std::cout << "  " << ones << " / " << bv1.n << " reads selected\n";
     }
-    commet_ctx_destroy(ctx);
+    if (ctx) commet_ctx_destroy(ctx);
     if (do_nothing) return 0;
 
     bv1.comment = comment;

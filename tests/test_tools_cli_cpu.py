@@ -18,6 +18,7 @@ def work(tmp_path_factory):
     build.build_tools()
     d = tmp_path_factory.mktemp("cli")
     oracle.write_bv_file(d / "a.bv", b"a", 10, oracle.tags_to_bv(np.ones(10, dtype=np.uint8)))
+    oracle.write_bv_file(d / "b.bv", b"b", 12, oracle.tags_to_bv(np.ones(12, dtype=np.uint8)))
     (d / "x.fa").write_text(">r\nACGT\n")
     (d / "sets.txt").write_text("s:x.fa\n")
     return d
@@ -32,6 +33,10 @@ CASES = [
     ("filter_reads", []), ("filter_reads", ["-h"]), ("filter_reads", ["-v"]), ("filter_reads", ["-z"]),
     ("filter_reads", ["nofile.fa", "-o", "x.bv"]),
     ("bvop", []), ("bvop", ["-h"]), ("bvop", ["-v"]), ("bvop", ["-z"]), ("bvop", ["nofile.bv", "-i"]), ("bvop", ["a.bv", "-q"]),
+    # the host-side checks of a binary operator come before the device is touched: size mismatch, missing second vector,
+    # and an invocation with nothing to compute (boolean_vector.h:420-423, src/bvop.cpp:133-160)
+    ("bvop", ["a.bv", "-a", "b.bv"]), ("bvop", ["a.bv", "-d", "b.bv", "-p", "out.bv"]), ("bvop", ["a.bv", "-o", "nofile.bv"]),
+    ("bvop", ["a.bv"]),
     ("extract_reads", []), ("extract_reads", ["-h"]), ("extract_reads", ["-v"]), ("extract_reads", ["-z"]),
     ("extract_reads", ["x.fa"]), ("extract_reads", ["nofile.fa", "a.bv"]), ("extract_reads", ["x.fa", "nofile.bv"]),
 ]
