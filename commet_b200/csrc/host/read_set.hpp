@@ -34,7 +34,18 @@ struct ReadSet {
     bool add_file(const std::string &fname, const std::string &bv_name)
     {
         SetFile sf;
-        if (!parse_reads_file(fname, sf.data, " -> ignore\n")) return false;
+        // file_manager.h:119-143: an unreadable file is reported by the first-byte probe ("file file" is the reference's
+        // wording), then again by the gzip probe, which exits; only a file of unknown format is ignored
+        bool readable;
+        {
+            std::ifstream probe(fname.c_str());
+            readable = probe.good();
+        }
+        if (!readable) std::cerr << "Cannot open file file " << fname << " -> ignore\n";
+        if (!parse_reads_file(fname, sf.data, " -> ignore\n")) {
+            if (!readable) exit(1);
+            return false;
+        }
         sf.fname = fname;
         sf.nb_reads = sf.data.nb_reads;
         if (bv_name.empty()) {

@@ -21,6 +21,8 @@ def work(tmp_path_factory):
     oracle.write_bv_file(d / "b.bv", b"b", 12, oracle.tags_to_bv(np.ones(12, dtype=np.uint8)))
     (d / "x.fa").write_text(">r\nACGT\n")
     (d / "sets.txt").write_text("s:x.fa\n")
+    (d / "missing.txt").write_text("s:nofile.fa\n")
+    (d / "badbv.txt").write_text("s:x.fa,b.bv\n")
     return d
 
 
@@ -30,6 +32,12 @@ CASES = [
     ("index_and_search", ["-t"]), ("index_and_search", ["-i", "sets.txt"]), ("index_and_search", ["-s", "sets.txt"]),
     ("index_and_search", ["-i", "nofile.txt", "-s", "nofile.txt", "-o", "o1", "-l", "o1"]),
     ("index_and_search", ["-k", "31", "-t", "3", "-z"]),
+    # FileManager::addFile: an unreadable read file is reported twice and ends the run; a vector of the wrong size too
+    # (file_manager.h:119-143, fasta_file.h:104-107) -- on the index side and on the search side
+    ("index_and_search", ["-i", "missing.txt", "-s", "sets.txt", "-o", "o2", "-l", "o2"]),
+    ("index_and_search", ["-i", "sets.txt", "-s", "missing.txt", "-o", "o3", "-l", "o3"]),
+    ("index_and_search", ["-i", "badbv.txt", "-s", "sets.txt", "-o", "o4", "-l", "o4"]),
+    ("index_and_search", ["-i", "sets.txt", "-s", "badbv.txt", "-o", "o5", "-l", "o5"]),
     ("filter_reads", []), ("filter_reads", ["-h"]), ("filter_reads", ["-v"]), ("filter_reads", ["-z"]),
     ("filter_reads", ["nofile.fa", "-o", "x.bv"]),
     ("bvop", []), ("bvop", ["-h"]), ("bvop", ["-v"]), ("bvop", ["-z"]), ("bvop", ["nofile.bv", "-i"]), ("bvop", ["a.bv", "-q"]),
