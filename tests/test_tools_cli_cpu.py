@@ -22,6 +22,9 @@ def work(tmp_path_factory):
     (d / "x.fa").write_text(">r\nACGT\n")
     (d / "sets.txt").write_text("s:x.fa\n")
     (d / "missing.txt").write_text("s:nofile.fa\n")
+    (d / "two.txt").write_text("a:x.fa\nb:x.fa\n")
+    (d / "empty.txt").write_text("\n\n")
+    (d / "afile").write_text("")
     (d / "badbv.txt").write_text("s:x.fa,b.bv\n")
     return d
 
@@ -38,6 +41,13 @@ CASES = [
     ("index_and_search", ["-i", "sets.txt", "-s", "missing.txt", "-o", "o3", "-l", "o3"]),
     ("index_and_search", ["-i", "badbv.txt", "-s", "sets.txt", "-o", "o4", "-l", "o4"]),
     ("index_and_search", ["-i", "sets.txt", "-s", "badbv.txt", "-o", "o5", "-l", "o5"]),
+    # output / log paths that exist and are not directories (src/index_and_search.cpp:178-191), more than one index
+    # set, a repeated -i, an index fof without any set
+    ("index_and_search", ["-i", "sets.txt", "-s", "sets.txt", "-o", "afile", "-l", "o6"]),
+    ("index_and_search", ["-i", "sets.txt", "-s", "sets.txt", "-o", "o7", "-l", "afile"]),
+    ("index_and_search", ["-i", "two.txt", "-s", "missing.txt", "-o", "o8", "-l", "o8"]),
+    ("index_and_search", ["-i", "sets.txt", "-i", "two.txt", "-s", "missing.txt", "-o", "o9", "-l", "o9"]),
+    ("index_and_search", ["-i", "empty.txt", "-s", "sets.txt", "-o", "o10", "-l", "o10"]),
     ("filter_reads", []), ("filter_reads", ["-h"]), ("filter_reads", ["-v"]), ("filter_reads", ["-z"]),
     ("filter_reads", ["nofile.fa", "-o", "x.bv"]),
     ("bvop", []), ("bvop", ["-h"]), ("bvop", ["-v"]), ("bvop", ["-z"]), ("bvop", ["nofile.bv", "-i"]), ("bvop", ["a.bv", "-q"]),
