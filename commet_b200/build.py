@@ -17,7 +17,7 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libcommet_b200.so"
 BIN = PKG / "bin"
-TOOLS = ("index_and_search", "filter_reads", "bvop", "commet_nxn", "extract_reads")
+TOOLS = ("index_and_search", "filter_reads", "bvop", "commet_nxn", "extract_reads", "compare_reads")
 HOST_ONLY = ("extract_reads",)          # pure I/O tools: no CUDA library behind them
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

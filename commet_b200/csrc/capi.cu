@@ -180,8 +180,7 @@ struct commet_reads {
 namespace {
 
 constexpr unsigned kGridBps = 8;       // blocks per SM of the streaming kernels' grids (see grid_for)
-constexpr int kScratch = 256;         // [0,128): 4 counters per query set; [128,256): misc
-constexpr int kMaxSets = 30;
+constexpr int kScratch = 256;         // [0,4): commet_search counters; [128,256): misc
 
 struct DevBuf {                       // scoped, stream-ordered device temporary from the context's arena
     void *p = nullptr;
@@ -575,6 +574,17 @@ extern "C" int commet_reads_clone(commet_ctx *c, const commet_reads *src, commet
         } else {
             cudaGetLastError();
         }
+    }
+    // the encode (and any kernel that still writes the source's planes) may be in flight on the source
+    // context's compute stream: the copy waits for it
+    {
+        cudaEvent_t done;
+        CK(cudaSetDevice(src->ctx->device));
+        CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));    // not from the source's pool: another thread owns it
+        CK(cudaEventRecord(done, src->ctx->stream));
+        CK(cudaSetDevice(c->device));
+        CK(cudaStreamWaitEvent(c->stream, done, 0));
+        CK(cudaEventDestroy(done));                 // released by the runtime once the recorded work has completed
     }
     commet_reads *r = nullptr;
     CKR(reads_alloc(c, src->n_reads, src->n_bases, &r));
@@ -1167,8 +1177,13 @@ static int chunk_loop(commet_ctx *c, int k, int t, uint64_t max_kmer, const std:
                       int n_sets, commet_reads *const *queries, uint32_t *const *d_tags,
                       uint64_t *searched, uint64_t *shared, uint64_t *stats)
 {
-    // scratch[4s..4s+3]: found total, searched in the last chunk, filter tests, k-mer lookups
-    CK(cudaMemsetAsync(c->scratch, 0, 128 * sizeof(unsigned long long), c->stream));
+    // cnt[4s..4s+3]: found total, searched in the last chunk, filter tests, k-mer lookups -- sized from n_sets (the
+    // reference takes any number of search sets, and Commet.py puts all the other samples into one -s file)
+    DevBuf cnt_buf(c);
+    const size_t n_cnt = 4 * (size_t)std::max(n_sets, 1);
+    if (cnt_buf.alloc(n_cnt * sizeof(unsigned long long)) != cudaSuccess) return fail("counter allocation failed");
+    unsigned long long *d_cnt = cnt_buf.as<unsigned long long>();
+    CK(cudaMemsetAsync(d_cnt, 0, n_cnt * sizeof(unsigned long long), c->stream));
     uint64_t n_chunks = 0, n_indexed = 0, n_kmers = 0;
     uint64_t cum = 0, open_reads = 0;
     bool began = false, dirty = false, pending_drop = false, queries_ready = false;
@@ -1199,8 +1214,8 @@ static int chunk_loop(commet_ctx *c, int k, int t, uint64_t max_kmer, const std:
         }
         CKR(t_search.begin(c->stream));
         for (int s = 0; s < n_sets; s++) {
-            CK(cudaMemsetAsync(c->scratch + 4 * s + 1, 0, sizeof(unsigned long long), c->stream));
-            CKR(search_launch(c, queries[s], k, t, d_tags[s], c->scratch + 4 * s));
+            CK(cudaMemsetAsync(d_cnt + 4 * s + 1, 0, sizeof(unsigned long long), c->stream));
+            CKR(search_launch(c, queries[s], k, t, d_tags[s], d_cnt + 4 * s));
         }
         CKR(t_search.end(c->stream));
         n_chunks++;
@@ -1259,8 +1274,8 @@ static int chunk_loop(commet_ctx *c, int k, int t, uint64_t max_kmer, const std:
     if (open_reads > 0) CKR(close_chunk());
     trace("last chunk: searches queued");
 
-    unsigned long long h[128];
-    CK(cudaMemcpyAsync(h, c->scratch, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<unsigned long long> h(n_cnt);
+    CK(cudaMemcpyAsync(h.data(), d_cnt, n_cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     trace("counters read back (sync)");
     uint64_t n_tests = 0, n_lookups = 0;
@@ -1283,7 +1298,7 @@ extern "C" int commet_index_and_search_staged(commet_ctx *c, int k, int t, uint6
                                               uint64_t *searched, uint64_t *shared, uint64_t *stats)
 {
     CKR(set_device(c));
-    if (n_sets < 0 || n_sets > kMaxSets) return fail("n_sets=%d unsupported (0..%d)", n_sets, kMaxSets);
+    if (n_sets < 0) return fail("n_sets=%d unsupported", n_sets);
     if (k < 1 || k > kMaxK) return fail("k=%d unsupported (1..%d)", k, kMaxK);
     std::vector<commet_reads *> parts(1, index);
     return chunk_loop(c, k, t, max_kmer, parts, n_sets, queries, d_tags, searched, shared, stats);
@@ -1298,7 +1313,7 @@ extern "C" int commet_index_and_search_resident(commet_ctx *c, int k, int t, uin
                                                 uint64_t *searched, uint64_t *shared, uint64_t *ones, uint64_t *stats)
 {
     CKR(set_device(c));
-    if (n_sets < 0 || n_sets > kMaxSets) return fail("n_sets=%d unsupported (0..%d)", n_sets, kMaxSets);
+    if (n_sets < 0) return fail("n_sets=%d unsupported", n_sets);
     if (k < 1 || k > kMaxK) return fail("k=%d unsupported (1..%d)", k, kMaxK);
     std::vector<uint32_t *> dt(n_sets, nullptr);
     int rc = 0;
@@ -1348,7 +1363,7 @@ extern "C" int commet_index_and_search(commet_ctx *c, int k, int t, uint64_t max
                                        uint64_t *shared, uint64_t *stats)
 {
     CKR(set_device(c));
-    if (n_sets < 0 || n_sets > kMaxSets) return fail("n_sets=%d unsupported (0..%d)", n_sets, kMaxSets);
+    if (n_sets < 0) return fail("n_sets=%d unsupported", n_sets);
     if (k < 1 || k > kMaxK) return fail("k=%d unsupported (1..%d)", k, kMaxK);
     if (ioffs[0] != 0) return fail("commet_index_and_search: ioffs[0] must be 0");
     std::vector<commet_reads *> parts;
@@ -1414,7 +1429,7 @@ static int filter_run(commet_ctx *c, uint64_t n, int64_t min_len, int64_t max_N,
     if (n_blocks > 0x7fffffffull) return fail("too many reads for one filter call");
     FilterParams fp;
     fp.min_len = min_len;
-    fp.max_N = max_N < 0 ? 2147483647LL : max_N;
+    fp.max_N = max_N == -1 ? 2147483647LL : max_N;      // -1: no limit; any other negative value drops every read (filter_reads.cpp:192)
     fp.min_shannon = min_shannon;
     fp.margin = 2e-5f;
     if (max_reads < -1) max_reads = 0;          // `selected < max_reads` is false at once: nothing kept

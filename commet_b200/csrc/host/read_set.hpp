@@ -41,6 +41,12 @@ struct ReadSet {
             std::ifstream probe(fname.c_str());
             readable = probe.good();
         }
+        if (!readable && !bv_name.empty()) {
+            // the two-argument addFile (file_manager.h:167-175, the form Commet.py's "file,bv" entries take): one
+            // message, the file is skipped and the run goes on
+            std::cerr << "Cannot open file " << fname << " -> ignore\n";
+            return false;
+        }
         if (!readable) std::cerr << "Cannot open file file " << fname << " -> ignore\n";
         if (!parse_reads_file(fname, sf.data, " -> ignore\n")) {
             if (!readable) exit(1);

@@ -141,7 +141,7 @@ int main(int argc, char **argv)
         // a cap that is never reached inside the examined prefix behaves like "no cap" there
         long cap = max_reads;
         if (commet_filter_reads(ctx, pf.seq.empty() ? &none : pf.seq.data(), pf.off.data(), n_eff, min_size,
-                                max_N == INT_MAX ? -1 : max_N, min_shannon, cap, part.data(), counters) != 0) {
+                                max_N == INT_MAX ? -1 : (max_N < 0 ? -2 : max_N), min_shannon, cap, part.data(), counters) != 0) {
             std::cerr << "filter_reads: " << commet_last_error() << "\n";
             return 1;
         }

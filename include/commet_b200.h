@@ -195,7 +195,8 @@ int commet_index_and_search_resident(commet_ctx *ctx, int k, int t, uint64_t max
 
 /* ---- stage 3: filter_reads --------------------------------------------------
  * The per-read selection of src/filter_reads.cpp:181-205: length < min_len ->
- * drop; #non-ACGTacgt > max_N -> drop (max_N<0: infinite); shannon_index
+ * drop; #non-ACGTacgt > max_N -> drop (max_N == -1: no limit; any other
+ * negative value drops every read, as the reference's signed compare does); shannon_index
  * (:265-306, float/double mixed precision reproduced exactly) < min_shannon
  * -> drop; stop after max_reads selected (<0: all) and clear every later bit
  * (untag_last_reads, include/read_file.h:76-81).  bv: n_reads/8+1 bytes out.

@@ -51,6 +51,26 @@ def test_commet_flow_bit_exact(bin_dir, tmp_path, case, config, kw):
     check_flow(tmp_path, res, GOLDEN[case])
 
 
+@pytest.mark.skipif(not (oracle.REF_DIR / "Commet.py").exists(), reason="oracle/_ref/Commet.py did not travel")
+@pytest.mark.parametrize("case,config,opts", [
+    ("abcde_3sets_k32", "ABCDE_bench/sets_config.txt", ["-k", "32"]),
+    ("abcde_5sets_k32", "ABCDE_bench/five_sets.txt", ["-k", "32"]),
+    ("dissymmetry_k33", "test_dissymmetry/fof.txt", ["-k", "33"]),
+    ("abcde_3sets_k21_filtered", "ABCDE_bench/sets_config.txt", ["-k", "21", "-t", "3", "-l", "100", "-e", "1.9", "-n", "0", "-m", "9000"]),
+])
+def test_unmodified_commet_py_over_the_drop_in_tools(bin_dir, tmp_path, case, config, opts):
+    """The seam itself (Commet.py:447,480-488): the reference's own orchestrator, byte for byte as shipped, run with
+    `-b commet_b200/bin` -- the command tests/golden/make_golden.py ran with `-b oracle/_ref` to record the goldens."""
+    import sys
+    fixtures.materialize(tmp_path)
+    r = subprocess.run([sys.executable, str(oracle.REF_DIR / "Commet.py"), config, "-b", str(bin_dir), *opts], cwd=tmp_path,
+                       capture_output=True, text=True)
+    out = tmp_path / "output_commet"
+    assert (out / "matrix_plain.csv").exists(), (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+    res = {n: (out / f"matrix_{n}.csv").read_text() for n in ("plain", "percentage", "normalized")}
+    check_flow(tmp_path, res, GOLDEN[case])
+
+
 @pytest.mark.parametrize("k", [20, 22, 33])
 def test_chunk_boundary_known_answer(bin_dir, tmp_path, k):
     fixtures.materialize(tmp_path)
@@ -169,6 +189,94 @@ def test_index_and_search_vs_reference_binary(bin_dir, tmp_path, seed):
         a = pat.search(lg.read_text()).group(0)
         b = pat.search((outs["gpu"] / lg.name).read_text()).group(0)
         assert a == b, (seed, lg.name)
+
+
+@pytest.mark.skipif(not (oracle.REF_DIR / "compare_reads").exists(), reason="oracle/_ref/compare_reads did not travel")
+@pytest.mark.parametrize("seed", range(6))
+def test_compare_reads_vs_reference_binary(bin_dir, tmp_path, seed):
+    """src/compare_reads.cpp:237-333: the three passes behind their own argv; stdout (minus the clock lines) and both
+    .bv files equal the reference's.  One chunk per index: with a lost read the reference's loop never ends (:248)."""
+    rng = np.random.default_rng(8000 + seed)
+    k = int(rng.integers(14, 25))
+    t = int(rng.integers(0, 4))
+    L = int(rng.integers(k, 4 * k))
+    dirt = dict(p_N=float(rng.choice([0, 0.02])), p_lower=float(rng.choice([0, 0.3])))
+    per_read = max(1, L - k + 1)
+    n_max = int(max(5, min(300, oracle.max_kmer(k) // (2 * per_read) - 2)))     # both sets stay below max_kmer
+    a_files = [H.make_ref_set(rng, int(rng.integers(3, n_max // 2 + 4)), max(1, L - 10), L + 10, **dirt) for _ in range(int(rng.integers(1, 3)))]
+    all_a = [r for f in a_files for r in f]
+    b_files = [H.make_query_set(rng, all_a, int(rng.integers(3, n_max // 2 + 4)), max(1, L - 10), L + 10, **dirt)
+               for _ in range(int(rng.integers(1, 3)))]
+    (tmp_path / "a.txt").write_text("setA:" + ";".join(_write_set(rng, tmp_path, "a", a_files, with_bv=bool(seed % 2))) + "\n")
+    (tmp_path / "b.txt").write_text("setB:" + ";".join(_write_set(rng, tmp_path, "b", b_files, with_bv=bool(seed % 3 == 0))) + "\n")
+    res = {}
+    for who, tool in (("ref", oracle.REF_DIR / "compare_reads"), ("gpu", bin_dir / "compare_reads")):
+        out = tmp_path / who
+        r = subprocess.run([str(tool), "-i", str(tmp_path / "a.txt"), "-s", str(tmp_path / "b.txt"), "-o", str(out), "-l", str(out),
+                            "-k", str(k), "-t", str(t)], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, (who, r.stderr)
+        text = [ln for ln in r.stdout.split("\n") if not re.match(r"(Index |Search|Total ) time", ln)]
+        res[who] = ({p.name: p.read_bytes() for p in out.glob("*.bv")}, text)
+    assert res["ref"][0].keys() == res["gpu"][0].keys() and len(res["ref"][0]) >= 2
+    assert res["ref"][0] == res["gpu"][0], (seed, k, t)
+    assert res["ref"][1] == res["gpu"][1], (seed, k, t)
+
+
+@needs_ref
+def test_unreadable_file_with_a_vector_is_skipped_and_the_run_goes_on(bin_dir, tmp_path):
+    """FileManager::addFile(file, bv) (file_manager.h:167-175, the form Commet.py's "file,bv" entries take): one message,
+    the file is skipped, the other files of the set are processed"""
+    rng = np.random.default_rng(77)
+    ref = H.make_ref_set(rng, 60, 50, 70)
+    qry = H.make_query_set(rng, ref, 40, 50, 70)
+    H.write_fasta(tmp_path / "r.fa", ref)
+    H.write_fasta(tmp_path / "q.fa", qry)
+    oracle.write_bv_file(tmp_path / "all_r.bv", b"x", len(ref), oracle.tags_to_bv(np.ones(len(ref), dtype=np.uint8)))
+    oracle.write_bv_file(tmp_path / "all_q.bv", b"x", len(qry), oracle.tags_to_bv(np.ones(len(qry), dtype=np.uint8)))
+    (tmp_path / "i.txt").write_text("I:nofile.fa,all_r.bv;r.fa,all_r.bv\n")
+    (tmp_path / "s.txt").write_text("S:q.fa,all_q.bv;gone.fa,all_q.bv\n")
+    res = {}
+    for who, tool in (("ref", oracle.REF_DIR / "index_and_search"), ("gpu", bin_dir / "index_and_search")):
+        r = subprocess.run([str(tool), "-i", "i.txt", "-s", "s.txt", "-o", who, "-l", who, "-k", "16"], cwd=tmp_path,
+                           capture_output=True, text=True)
+        res[who] = (r.returncode, r.stderr, {p.name: p.read_bytes() for p in (tmp_path / who).glob("*.bv")})
+    assert res["ref"] == res["gpu"]
+    assert res["ref"][0] == 0 and len(res["ref"][2]) == 1
+
+
+@needs_ref
+def test_negative_max_n_drops_every_read_that_passes_the_length_test(bin_dir, tmp_path):
+    """`number_of_N(read) > max_N` with a negative max_N is true for every read (src/filter_reads.cpp:192)"""
+    rng = np.random.default_rng(78)
+    H.write_fasta(tmp_path / "in.fa", H.make_ref_set(rng, 200, 20, 90, p_N=0.02))
+    res = {}
+    for who, tool in (("ref", oracle.REF_DIR / "filter_reads"), ("gpu", bin_dir / "filter_reads")):
+        r = subprocess.run([str(tool), "in.fa", "-l", "40", "-n", "-3", "-o", f"{who}.bv"], cwd=tmp_path, capture_output=True, text=True)
+        assert r.returncode == 0, (who, r.stderr)
+        res[who] = ((tmp_path / f"{who}.bv").read_bytes(), [ln for ln in r.stdout.split("\n") if not ln.startswith("Total  time")])
+    assert res["ref"] == res["gpu"]
+    assert "Number of selected reads = 0" in res["gpu"][1]
+
+
+@needs_ref
+def test_more_than_thirty_search_sets_in_one_invocation(bin_dir, tmp_path):
+    """Commet.py puts every other sample into one -s file; the reference takes any number of search sets"""
+    rng = np.random.default_rng(79)
+    ref = H.make_ref_set(rng, 300, 40, 60)      # several chunks at k=14
+    H.write_fasta(tmp_path / "r.fa", ref)
+    (tmp_path / "i.txt").write_text("I:r.fa\n")
+    lines = []
+    for s in range(37):
+        H.write_fasta(tmp_path / f"q{s}.fa", H.make_query_set(rng, ref, int(rng.integers(3, 30)), 40, 60))
+        lines.append(f"Q{s:02d}:q{s}.fa")
+    (tmp_path / "s.txt").write_text("\n".join(lines) + "\n")
+    res = {}
+    for who, tool in (("ref", oracle.REF_DIR / "index_and_search"), ("gpu", bin_dir / "index_and_search")):
+        r = subprocess.run([str(tool), "-i", "i.txt", "-s", "s.txt", "-o", who, "-l", who, "-k", "14", "-t", "1"], cwd=tmp_path,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, (who, r.stderr)
+        res[who] = {p.name: p.read_bytes() for p in (tmp_path / who).glob("*.bv")}
+    assert len(res["ref"]) == 37 and res["ref"] == res["gpu"]
 
 
 @needs_ref

@@ -9,7 +9,7 @@ import pytest
 from commet_b200 import build
 from oracle import oracle
 
-TOOLS = ("index_and_search", "filter_reads", "bvop", "extract_reads")
+TOOLS = ("index_and_search", "filter_reads", "bvop", "extract_reads", "compare_reads")
 pytestmark = pytest.mark.skipif(not all((oracle.REF_DIR / t).exists() for t in TOOLS), reason="oracle/_ref not built")
 
 
@@ -48,6 +48,13 @@ CASES = [
     ("index_and_search", ["-i", "two.txt", "-s", "missing.txt", "-o", "o8", "-l", "o8"]),
     ("index_and_search", ["-i", "sets.txt", "-i", "two.txt", "-s", "missing.txt", "-o", "o9", "-l", "o9"]),
     ("index_and_search", ["-i", "empty.txt", "-s", "sets.txt", "-o", "o10", "-l", "o10"]),
+    # compare_reads (src/compare_reads.cpp:82-183): same argv conventions, its own usage text and messages
+    ("compare_reads", []), ("compare_reads", ["-h"]), ("compare_reads", ["-v"]), ("compare_reads", ["-z"]),
+    ("compare_reads", ["-i"]), ("compare_reads", ["-i", "sets.txt", "-s"]), ("compare_reads", ["-k", "31", "-t", "3", "-z"]),
+    ("compare_reads", ["-i", "sets.txt", "-i", "two.txt", "-s", "sets.txt", "-s", "two.txt", "-o", "afile", "-l", "c1"]),
+    ("compare_reads", ["-i", "sets.txt", "-s", "sets.txt", "-o", "c2", "-l", "afile"]),
+    ("compare_reads", ["-i", "missing.txt", "-s", "sets.txt", "-o", "c3", "-l", "c3"]),
+    ("compare_reads", ["-i", "sets.txt", "-s", "badbv.txt", "-o", "c4", "-l", "c4"]),
     ("filter_reads", []), ("filter_reads", ["-h"]), ("filter_reads", ["-v"]), ("filter_reads", ["-z"]),
     ("filter_reads", ["nofile.fa", "-o", "x.bv"]),
     ("bvop", []), ("bvop", ["-h"]), ("bvop", ["-v"]), ("bvop", ["-z"]), ("bvop", ["nofile.bv", "-i"]), ("bvop", ["a.bv", "-q"]),
