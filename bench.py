@@ -323,19 +323,20 @@ def main():
     n_tag_words = (n // 8 + 1 + 3) // 4
     tags_d = torch.zeros(n_tag_words, dtype=torch.int32, device=dev)
 
-    counters_d = torch.zeros(4, dtype=torch.int64, device=dev)
-    peers = None
+    dd = None
     if world > 1:
-        # one-time: map every rank's filter into this process (CUDA IPC over NVLink peer memory)
+        # one-time: every rank's filter is mapped into every process (CUDA IPC over NVLink peer memory) by
+        # commet_dist_open; torch.distributed only serves the two callbacks of the library's loop (barrier, all-gather of
+        # a few bytes: the k-mer totals of the chunk plan)
         from commet_b200 import multi
-        be0 = multi.DeviceBackend(ctx, None, [], [], [])
 
         def all_gather_bytes(b):
-            out = [None] * world
-            dist.all_gather_object(out, b)
-            return out
-        be0.connect(k_arg, world, rank, all_gather_bytes)
-        peers = be0.peers
+            t_in = torch.frombuffer(bytearray(b), dtype=torch.uint8).to(dev)
+            out = torch.empty(world * len(b), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(out, t_in)
+            raw = out.cpu().numpy().tobytes()
+            return [raw[i * len(b):(i + 1) * len(b)] for i in range(world)]
+        dd = commet_b200.Dist(ctx, world, rank, k_arg, dist.barrier, all_gather_bytes)
         # this rank's shard of the reference set: blocks b = rank (mod world) of BLOCK consecutive reads -- what a
         # rank's loader delivers when every process parses only its own blocks of the files
         BLOCK = multi.DEFAULT_BLOCK
@@ -343,17 +344,6 @@ def main():
         n_loc = int(own.sum())
         ref_loc_d = ref_d.view(n, L)[own].reshape(-1).contiguous()
         offs_loc_d = torch.arange(0, n_loc + 1, dtype=torch.int64, device=dev) * L
-        gather_buf = torch.zeros(world, dtype=torch.int64, device=dev)
-
-        def all_gather(obj):
-            """multi.distributed_plan's exchange: one integer per rank on the fast path (one NCCL all-gather of
-            8 bytes), pickled per-read counts only when the reference set reaches max_kmer"""
-            if isinstance(obj, int):
-                dist.all_gather_into_tensor(gather_buf, torch.tensor([obj], dtype=torch.int64, device=dev))
-                return gather_buf.tolist()
-            out = [None] * world
-            dist.all_gather_object(out, obj)
-            return out
 
     def step_device():
         """one pass with inputs resident in HBM; returns info dict"""
@@ -367,15 +357,11 @@ def main():
             # the rank stages ITS shard of the reference set; every chunk's partial filters are merged by the
             # one-kernel OR all-reduce over peer memory; every rank probes its own query set
             idx = ctx.stage_device(ref_loc_d.data_ptr(), offs_loc_d.data_ptr(), n_loc, n_loc * L)
-            counters_d.zero_()
             torch.cuda.current_stream().synchronize()
-            be = multi.DeviceBackend(ctx, idx, [q], [tags_d.data_ptr()], [counters_d.data_ptr()])
-            be.peers, be.rank, be.k = peers, rank, k
-            r = multi.distributed_index_and_search(be, dist.barrier, all_gather, world, rank, k, t, n, BLOCK)
-            ctx.sync()
-            c = counters_d.tolist()
-            info = {"shared": [c[0]], "searched": [c[1]], "chunks": r["chunks"], "index_ns": 0, "search_ns": 0, "kmers": 0,
-                    "phases_ms": {key[:-2]: round(r[key] * 1e3, 3) for key in ("plan_s", "index_s", "merge_s", "barrier_s")}}
+            r = dd.index_and_search(t, idx, n, [q], [tags_d.data_ptr()], block=BLOCK)
+            info = {"shared": r["shared"], "searched": r["searched"], "chunks": r["chunks"], "index_ns": 0, "search_ns": r["search_ns"],
+                    "kmers": 0, "phases_ms": {key[:-2]: round(r[key] * 1e3, 3) for key in ("plan_s", "index_s", "merge_s", "barrier_s")}}
+            info["phases_ms"]["search"] = round(r["search_ns"] / 1e6, 3)
         idx.free()
         q.free()
         return info
@@ -443,17 +429,13 @@ def main():
             _, inf = ctx.index_and_search(k, t, (ref_h.numpy(), offs_h), [(qry_h.numpy(), offs_h)])
             return inf["shared"][0]
         tags_d.zero_()
-        counters_d.zero_()
         torch.cuda.current_stream().synchronize()
         idx = ctx.stage_async(ref_loc_h.numpy(), offs_loc_h)
         q = ctx.stage_async(qry_h.numpy(), offs_h)
-        be = multi.DeviceBackend(ctx, idx, [q], [tags_d.data_ptr()], [counters_d.data_ptr()])
-        be.peers, be.rank, be.k = peers, rank, k
-        multi.distributed_index_and_search(be, dist.barrier, all_gather, world, rank, k, t, n, BLOCK)
-        ctx.sync()
+        r = dd.index_and_search(t, idx, n, [q], [tags_d.data_ptr()], block=BLOCK)
         tags_h.copy_(tags_d.view(torch.uint8)[:n // 8 + 1])
         idx.free(); q.free()
-        return int(counters_d[0])
+        return r["shared"][0]
 
     for _ in range(max(1, args.warmup)):
         step_e2e()
@@ -473,6 +455,8 @@ def main():
            "h2d_bytes_per_step": int(world * (n * L + 8 * (n + 1)) + n * L + 8 * (n + world)),
            "d2h_bytes_per_step": int(world * (n // 8 + 1))}
 
+    if dd is not None:
+        dd.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -67,6 +67,16 @@ _SIGS = {
     "commet_peer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "commet_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "commet_index_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "commet_dist_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "commet_dist_index_and_search": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "commet_dist_close": (None, [C.c_void_p]),
+    "commet_group_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "commet_group_destroy": (None, [C.c_void_p]),
+    "commet_group_size": (C.c_int, [C.c_void_p]),
+    "commet_group_index_and_search": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
+                                                C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p]),
     "commet_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, _u64p, _u64p]),
     "commet_search_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "commet_index_and_search": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
@@ -145,6 +155,127 @@ def _as_stream(bases, offs):
     if offs.ndim != 1 or offs.size < 1:
         raise ValueError("offs must hold n_reads+1 offsets")
     return bases, offs
+
+
+_BARRIER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+_ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
+
+
+class _CommStruct(C.Structure):            # commet_comm (include/commet_b200.h)
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("user", C.c_void_p), ("barrier", _BARRIER_FN),
+                ("all_gather", _ALLGATHER_FN)]
+
+
+class Dist:
+    """commet_dist*: this rank's end of the multi-GPU chunk loop.  barrier() and all_gather_bytes(b) -> [bytes of every
+    rank] are the host language's collectives (torch.distributed in bench.py and the tests)."""
+
+    def __init__(self, ctx: "Context", world: int, rank: int, k: int, barrier, all_gather_bytes):
+        self.ctx, self.world, self.rank, self.k = ctx, world, rank, k
+        self._err = None
+
+        def _barrier(_user):
+            try:
+                barrier()
+                return 0
+            except Exception as e:              # an exception must not unwind through the C frames
+                self._err = e
+                return -1
+
+        def _all_gather(_user, p_in, p_out, nbytes):
+            try:
+                parts = all_gather_bytes(C.string_at(p_in, nbytes))
+                C.memmove(p_out, b"".join(parts), nbytes * world)
+                return 0
+            except Exception as e:
+                self._err = e
+                return -1
+
+        self._cbs = (_BARRIER_FN(_barrier), _ALLGATHER_FN(_all_gather))      # kept alive with the object
+        self._comm = _CommStruct(world, rank, None, *self._cbs)
+        h = C.c_void_p()
+        self._ck(ctx.lib.commet_dist_open(ctx.handle, C.byref(self._comm), k, C.byref(h)))
+        self.handle = h.value
+
+    def _ck(self, rc):
+        if rc != 0:
+            err, self._err = self._err, None
+            msg = self.ctx.lib.commet_last_error().decode()
+            raise CommetError(msg) from err
+
+    def index_and_search(self, t: int, shard: "ReadStream", n_global: int, queries, d_tags, block: int = 1 << 16,
+                         maxk: int | None = None) -> dict:
+        """collective: src/index_and_search.cpp:255-277 with the index set dealt block-cyclically over the ranks"""
+        maxk = max_kmer(self.k) if maxk is None else maxk
+        ns = len(queries)
+        qh = (C.c_void_p * max(ns, 1))(*[q.handle for q in queries])
+        th = (C.c_void_p * max(ns, 1))(*d_tags)
+        searched = np.zeros(max(ns, 1), dtype=np.uint64)
+        shared = np.zeros(max(ns, 1), dtype=np.uint64)
+        stats = np.zeros(11, dtype=np.uint64)
+        self._ck(self.ctx.lib.commet_dist_index_and_search(self.handle, t, maxk, shard.handle, n_global, block, ns,
+                                                           C.cast(qh, C.c_void_p), C.cast(th, C.c_void_p), _ptr(searched),
+                                                           _ptr(shared), _ptr(stats)))
+        return dict(chunks=int(stats[0]), indexed_here=int(stats[1]), plan_s=stats[2] * 1e-9, index_s=stats[3] * 1e-9,
+                    search_ns=int(stats[4]), merge_s=stats[5] * 1e-9, barrier_s=stats[6] * 1e-9, tests=int(stats[7]),
+                    lookups=int(stats[8]), last_chunk=(int(stats[9]), int(stats[10])),
+                    searched=[int(x) for x in searched[:ns]], shared=[int(x) for x in shared[:ns]])
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.commet_dist_close(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Group:
+    """commet_group*: several GPUs of THIS process behind the signature of Context.index_and_search"""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        if self.lib.commet_group_create(C.cast(devs, C.c_void_p), len(devices), C.byref(h)) != 0:
+            raise CommetError(self.lib.commet_last_error().decode())
+        self.handle = h.value
+
+    def index_and_search(self, k: int, t: int, index_stream, query_streams, maxk: int | None = None):
+        maxk = max_kmer(k) if maxk is None else maxk
+        ib, io = _as_stream(*index_stream)
+        qs = [_as_stream(b, o) for b, o in query_streams]
+        ns = len(qs)
+        tags = [np.zeros((o.size - 1) // 8 + 1, dtype=np.uint8) for _, o in qs]
+        qb = (C.c_void_p * max(ns, 1))(*[b.ctypes.data for b, _ in qs])
+        qo = (C.c_void_p * max(ns, 1))(*[o.ctypes.data for _, o in qs])
+        tg = (C.c_void_p * max(ns, 1))(*[t_.ctypes.data for t_ in tags])
+        nq = np.array([o.size - 1 for _, o in qs] or [0], dtype=np.uint64)
+        searched = np.zeros(max(ns, 1), dtype=np.uint64)
+        shared = np.zeros(max(ns, 1), dtype=np.uint64)
+        stats = np.zeros(8, dtype=np.uint64)
+        if self.lib.commet_group_index_and_search(self.handle, k, t, maxk, _ptr(ib), _ptr(io), io.size - 1, ns,
+                                                  C.cast(qb, C.c_void_p), C.cast(qo, C.c_void_p), _ptr(nq),
+                                                  C.cast(tg, C.c_void_p), _ptr(searched), _ptr(shared), _ptr(stats)) != 0:
+            raise CommetError(self.lib.commet_last_error().decode())
+        info = dict(chunks=int(stats[0]), indexed=int(stats[1]), index_ns=int(stats[3]), search_ns=int(stats[4]),
+                    tests=int(stats[5]), lookups=int(stats[6]), gpus=int(stats[7]),
+                    searched=[int(x) for x in searched[:ns]], shared=[int(x) for x in shared[:ns]])
+        return tags, info
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.commet_group_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class ReadStream:

@@ -11,8 +11,11 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -150,6 +153,11 @@ struct commet_ctx {
     uint32_t *recs = nullptr;         // region-sorted key records of the L2-blocked insert
     uint64_t recs_cap = 0;            // capacity in records
     unsigned long long *bins = nullptr;   // hist[512] | base[513] | cursor[512] | tile counter
+    int insert_form = 2;              // L2-blocked insert: 1 = histogram + scatter + apply, 2 = slab scatter + apply (kernels.cuh)
+    uint32_t *bins2 = nullptr;        // second form: fill[512] | tbase[513] | slab counter
+    uint32_t *slab_table = nullptr;   // second form: table[region][slab of the region] -> 1 + slab id
+    uint64_t slab_table_cap = 0;      // entries
+    unsigned s2_attr = 0;             // k_bin_scatter2<TW> instances whose shared-memory limit has been raised on this device
     Arena arena;                      // cached device temporaries (see Arena)
     // pinned bounce ring for H2D copies out of pageable host memory (see h2d_copy)
     uint8_t *bounce[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -273,6 +281,8 @@ extern "C" void commet_ctx_destroy(commet_ctx *c)
     if (c->scratch) cudaFree(c->scratch);
     if (c->recs) cudaFree(c->recs);
     if (c->bins) cudaFree(c->bins);
+    if (c->bins2) cudaFree(c->bins2);
+    if (c->slab_table) cudaFree(c->slab_table);
     for (Arena::Block &b : c->arena.blocks) cudaFree(b.p);
     for (int i = 0; i < 4; i++) {
         if (c->bounce[i]) cudaFreeHost(c->bounce[i]);
@@ -295,7 +305,9 @@ extern "C" void *commet_ctx_stream(commet_ctx *c) { return (void *)c->stream; }
 extern "C" int commet_ctx_count_probes(commet_ctx *c, int on) { c->count_probes = on != 0; return 0; }
 extern "C" int commet_ctx_binned_index(commet_ctx *c, int on)
 {
-    // 0: direct RED.OR; 1: keys sorted by region first (default); 16..30: region passes with 2^on-byte regions
+    // 0: direct RED.OR; 1: keys sorted by region first (default); 101 / 102: the same, first / second form of the
+    // L2-blocked insert (kernels.cuh) whatever the default is; 16..30: region passes with 2^on-byte regions
+    if (on == 101 || on == 102) c->insert_form = on - 100;
     c->binned_index = on != 0;
     c->region_passes = on >= 16 && on <= 30;
     if (c->region_passes) c->region_log2 = on;
@@ -837,8 +849,9 @@ static int index_range_binned(commet_ctx *c, commet_reads *r, uint64_t b0, uint6
 {
     const int k = c->k;
     const int n_bins = 1 << (k - kRecKeyBits);
-    if (!c->bins) {
-        CK(cudaMalloc(&c->bins, 2048 * sizeof(unsigned long long)));
+    if (!c->bins) CK(cudaMalloc(&c->bins, 2048 * sizeof(unsigned long long)));
+    if (!(c->s2_attr & 1u)) {                        // per device, once
+        c->s2_attr |= 1u;
         CK(cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         CK(cudaFuncSetAttribute(k_bin_count<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * 128 + 128) * 4));
     }
@@ -907,6 +920,100 @@ static int index_range_binned(commet_ctx *c, commet_reads *r, uint64_t b0, uint6
     return 0;
 }
 
+// The second form of the L2-blocked insert (kernels.cuh: k_bin_scatter2 / k_bin_plan2 / k_bin_apply2): no histogram
+// pass, records in slabs.  Same contract as index_range_binned.
+template <int TW>
+static void launch_scatter2(commet_ctx *c, commet_reads *r, uint64_t s0, uint64_t s1, int k, int n_bins, uint32_t *fill,
+                            uint32_t max_q, uint32_t *n_slabs, unsigned bps)
+{
+    const size_t sh = scatter2_smem_bytes(TW, n_bins);
+    if (!(c->s2_attr & (unsigned)TW)) {             // per device: the attribute belongs to the context's device
+        cudaFuncSetAttribute(k_bin_scatter2<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem_bytes(TW, kMaxBins));
+        c->s2_attr |= (unsigned)TW;
+    }
+    const uint64_t n_tiles = (((s1 + 31) >> 5) - (s0 >> 5) + TW - 1) / TW;
+    const unsigned g = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * bps);
+    k_bin_scatter2<TW><<<g, kS2Threads, sh, c->stream>>>(r->planes, s0, s1, k, n_bins, fill, c->slab_table, max_q, n_slabs, c->recs);
+}
+
+static int index_range_binned2(commet_ctx *c, commet_reads *r, uint64_t b0, uint64_t b1, uint64_t kmers_hint)
+{
+    const int k = c->k;
+    const int n_bins = 1 << (k - kRecKeyBits);
+    if (!c->bins) CK(cudaMalloc(&c->bins, 2048 * sizeof(unsigned long long)));
+    if (!c->bins2) CK(cudaMalloc(&c->bins2, 2048 * sizeof(uint32_t)));
+    uint32_t *fill = c->bins2, *tbase = c->bins2 + 512, *n_slabs = c->bins2 + 1030;
+    unsigned long long *tile_counter = c->bins + 1700;
+    const uint64_t positions = b1 - b0;
+    const uint64_t kmers = kmers_hint ? std::min(kmers_hint, positions) : positions;
+    // records of one launch: bounded by the 32-bit record counters and by what the device has room for (in slabs)
+    const uint64_t limit = 0xE0000000ull;
+    auto slabs_for = [&](uint64_t recs) { return (recs + kSlabRecs - 1) / kSlabRecs + (uint64_t)n_bins + 1; };
+    uint64_t bound = 4 * kmers, parts = 1;
+    uint64_t budget = c->recs_cap > ((uint64_t)n_bins + 1) * kSlabRecs ? c->recs_cap - ((uint64_t)n_bins + 1) * kSlabRecs : 0;   // records
+    bool forced = false;
+    if (const char *e = getenv("COMMET_B200_RECS_BUDGET")) {                   // tests: force sub-ranges
+        uint64_t v = strtoull(e, nullptr, 10);
+        if (v >= 4096) { budget = v; forced = true; }
+    }
+    if (!forced && slabs_for(bound) * kSlabRecs > c->recs_cap) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t room = (uint64_t)((free_b + c->recs_cap * 4) * 0.6) / 4;       // records
+        budget = room > ((uint64_t)n_bins + 1) * kSlabRecs ? room - ((uint64_t)n_bins + 1) * kSlabRecs : 0;
+        if (budget < kSlabRecs) return 1;                                            // no room: direct atomics
+    }
+    budget = std::min(budget, limit);
+    if (bound > budget) {
+        parts = (4 * positions + budget - 1) / budget;            // sub-ranges are cut by position: no per-part k-mer count
+        bound = 4 * ((positions + parts - 1) / parts + 32);
+    }
+    const uint64_t need = slabs_for(bound) * kSlabRecs;
+    if (c->recs_cap < need) {
+        if (c->recs) { cudaFree(c->recs); c->recs = nullptr; c->recs_cap = 0; }
+        if (cudaMalloc(&c->recs, need * sizeof(uint32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        c->recs_cap = need;
+    }
+    const uint32_t max_q = (uint32_t)((bound + kSlabRecs - 1) / kSlabRecs + 1);
+    const uint64_t table_entries = (uint64_t)n_bins * max_q;
+    if (c->slab_table_cap < table_entries) {
+        if (c->slab_table) { cudaFree(c->slab_table); c->slab_table = nullptr; c->slab_table_cap = 0; }
+        CK(cudaMalloc(&c->slab_table, table_entries * sizeof(uint32_t)));
+        c->slab_table_cap = table_entries;
+    }
+    const int tw = (int)env_or("COMMET_B200_S2_TW", 128);
+    const unsigned sbps = env_or("COMMET_B200_SCATTER_BPS", tw <= 64 ? 3 : 2);
+    int tile = 2048, bps = 8, pf = 1;
+    if (const char *e = getenv("COMMET_B200_APPLY_TILE")) tile = atoi(e);
+    if (const char *e = getenv("COMMET_B200_APPLY_BPS")) bps = atoi(e);
+    if (const char *e = getenv("COMMET_B200_APPLY_PREFETCH")) pf = atoi(e);
+    for (uint64_t p = 0; p < parts; p++) {
+        const uint64_t s0 = b0 + positions * p / parts, s1 = b0 + positions * (p + 1) / parts;
+        if (s1 <= s0) continue;
+        CK(cudaMemsetAsync(c->bins2, 0, 2048 * sizeof(uint32_t), c->stream));
+        CK(cudaMemsetAsync(c->slab_table, 0, table_entries * sizeof(uint32_t), c->stream));
+        if (tw <= 64) launch_scatter2<64>(c, r, s0, s1, k, n_bins, fill, max_q, n_slabs, sbps);
+        else if (tw <= 96) launch_scatter2<96>(c, r, s0, s1, k, n_bins, fill, max_q, n_slabs, sbps);
+        else launch_scatter2<128>(c, r, s0, s1, k, n_bins, fill, max_q, n_slabs, sbps);
+        const unsigned ga = c->sm_count * bps;
+        if (tile == 4096) {
+            k_bin_plan2<4096><<<1, 32, 0, c->stream>>>(fill, n_bins, tbase, tile_counter);
+            if (pf) k_bin_apply2<4096, true><<<ga, 256, 0, c->stream>>>(c->filter, c->recs, fill, tbase, c->slab_table, max_q, n_bins, tile_counter);
+            else k_bin_apply2<4096, false><<<ga, 256, 0, c->stream>>>(c->filter, c->recs, fill, tbase, c->slab_table, max_q, n_bins, tile_counter);
+        } else {
+            k_bin_plan2<2048><<<1, 32, 0, c->stream>>>(fill, n_bins, tbase, tile_counter);
+            if (pf) k_bin_apply2<2048, true><<<ga, 256, 0, c->stream>>>(c->filter, c->recs, fill, tbase, c->slab_table, max_q, n_bins, tile_counter);
+            else k_bin_apply2<2048, false><<<ga, 256, 0, c->stream>>>(c->filter, c->recs, fill, tbase, c->slab_table, max_q, n_bins, tile_counter);
+        }
+        c->launches += 3;
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
 static int index_range(commet_ctx *c, commet_reads *r, uint64_t first, uint64_t count, uint64_t kmers_hint)
 {
     if (c->k == 0) return fail("commet_index_add before commet_index_begin");
@@ -930,7 +1037,10 @@ static int index_range(commet_ctx *c, commet_reads *r, uint64_t first, uint64_t 
         return 0;
     }
     if (c->binned_index && c->k >= 28 && c->k - kRecKeyBits <= 9) {
-        int rc = index_range_binned(c, r, hb[0], hb[1], kmers_hint);
+        int form = c->insert_form;
+        if (const char *e = getenv("COMMET_B200_INSERT")) form = atoi(e);          // A/B (scripts/ab_index.py)
+        int rc = form == 2 ? index_range_binned2(c, r, hb[0], hb[1], kmers_hint)
+                                     : index_range_binned(c, r, hb[0], hb[1], kmers_hint);
         if (rc <= 0) return rc;
     }
     uint64_t positions = hb[1] - hb[0] + 32;
@@ -1651,3 +1761,6 @@ extern "C" int commet_bench_random_sectors(commet_ctx *c, uint64_t bytes, uint64
     if (ns) *ns = (double)ms * 1e6;
     return 0;
 }
+
+// ------------------------------------------------------------- multi-GPU ----
+#include "dist.inl"

@@ -1,0 +1,559 @@
+// Multi-GPU chunk loop (included at the end of capi.cu): src/index_and_search.cpp:255-277 with the index set dealt
+// block-cyclically over `world` ranks, one GPU each.  Block b of `block` consecutive reads of the set's valid-read
+// stream lives on rank b % world, so a rank parses, uploads and encodes only 1/world of the set and every chunk --
+// a contiguous range of global reads -- is a contiguous, evenly sized range of LOCAL reads on every rank.
+//
+//   plan   the stop rule of index_reads (index_reads.h:48-49,60) needs the k-mer counts of all reads in global order.
+//          The ranks exchange their local totals (8 bytes each); only if max_kmer is reached at all, their per-BLOCK
+//          totals (computed on the device), which they walk together; the read at which a chunk closes is resolved by
+//          the rank that owns its block from that block's per-read counts (one 256 KB download) and announced.
+//   chunk  every rank clears its filter and inserts ITS reads of the chunk; barrier; ONE kernel per rank ORs slice
+//          `rank` of every partial over NVLink peer memory and pushes the merged slice into every filter
+//          (k_merge_peers); barrier; every rank probes its own query reads.  Bloom insertion is commutative and
+//          idempotent: the merged filter is bit-identical to the single-GPU filter of the chunk.
+//
+// The ranks may be processes (one per GPU: the filters are mapped through CUDA IPC, the two collectives the loop needs
+// -- barrier and all-gather of a few bytes -- are callbacks the host language provides, e.g. over torch.distributed)
+// or threads of one process (commet_group_*: peer access, an in-process barrier).  commet_b200/multi.py keeps a
+// Python mirror of the plan for the CPU tests.
+
+namespace {
+
+struct PeerInfo {                   // what the ranks exchange in commet_dist_open
+    uint64_t pid;
+    int32_t device;
+    int32_t pad;
+    uint64_t ptr;                   // the filter's device address (meaningful inside the owning process)
+    uint8_t handle[COMMET_IPC_HANDLE_BYTES];
+};
+
+inline uint64_t local_index(uint64_t g, uint64_t world, uint64_t rank, uint64_t block)
+{
+    // number of reads with global index < g that live on `rank`
+    const uint64_t cycle = block * world, full = g / cycle, o = g % cycle;
+    const uint64_t lo = rank * block;
+    return full * block + (o <= lo ? 0 : std::min(o - lo, block));
+}
+
+struct Stopwatch {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    uint64_t lap_ns()
+    {
+        auto t1 = std::chrono::steady_clock::now();
+        uint64_t ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+        t0 = t1;
+        return ns;
+    }
+};
+
+}  // namespace
+
+struct commet_dist {
+    commet_ctx *ctx = nullptr;
+    commet_comm comm{};
+    int k = 0;
+    std::vector<void *> peers;          // peer filters as seen from this device (entry `rank`: null)
+    std::vector<char> via_ipc;          // opened with cudaIpcOpenMemHandle: closed in commet_dist_close
+};
+
+extern "C" int commet_dist_open(commet_ctx *c, const commet_comm *comm, int k, commet_dist **out)
+{
+    if (!c || !comm || !out) return fail("commet_dist_open: null argument");
+    if (comm->world < 1 || comm->world > kMaxPeers || comm->rank < 0 || comm->rank >= comm->world)
+        return fail("commet_dist_open: %d ranks (rank %d) unsupported (1..%d)", comm->world, comm->rank, kMaxPeers);
+    if (comm->world > 1 && (!comm->barrier || !comm->all_gather)) return fail("commet_dist_open: the communicator has no callbacks");
+    CKR(commet_index_begin(c, k));
+    commet_dist *d = new commet_dist;
+    d->ctx = c;
+    d->comm = *comm;
+    d->k = k;
+    d->peers.assign(comm->world, nullptr);
+    d->via_ipc.assign(comm->world, 0);
+    if (comm->world > 1) {
+        PeerInfo me{};
+        me.pid = (uint64_t)getpid();
+        me.device = c->device;
+        me.ptr = (uint64_t)(uintptr_t)c->filter;
+        int rc = commet_index_export(c, me.handle);
+        std::vector<PeerInfo> all(comm->world);
+        if (rc == 0 && comm->all_gather(comm->user, &me, all.data(), sizeof me) != 0) rc = fail("commet_dist_open: all_gather failed");
+        for (int p = 0; rc == 0 && p < comm->world; p++) {
+            if (p == comm->rank) continue;
+            if (all[p].pid == me.pid) {
+                // a thread of this process: the pointer is valid here; the other device must be accessible
+                if (all[p].device != c->device) {
+                    int can = 0;
+                    if (cudaDeviceCanAccessPeer(&can, c->device, all[p].device) != cudaSuccess || !can) {
+                        cudaGetLastError();
+                        rc = fail("device %d cannot access the memory of device %d", c->device, all[p].device);
+                        break;
+                    }
+                    cudaError_t pe = cudaDeviceEnablePeerAccess(all[p].device, 0);
+                    if (pe != cudaSuccess) cudaGetLastError();          // already enabled: fine
+                }
+                d->peers[p] = (void *)(uintptr_t)all[p].ptr;
+            } else {
+                rc = commet_peer_open(c, all[p].handle, &d->peers[p]);
+                if (rc == 0) d->via_ipc[p] = 1;
+            }
+        }
+        // everybody has mapped everybody (or failed) before anyone may free its filter
+        if (comm->barrier(comm->user) != 0 && rc == 0) rc = fail("commet_dist_open: barrier failed");
+        if (rc != 0) { commet_dist_close(d); return rc; }
+    }
+    *out = d;
+    return 0;
+}
+
+extern "C" void commet_dist_close(commet_dist *d)
+{
+    if (!d) return;
+    if (d->ctx) {
+        cudaSetDevice(d->ctx->device);
+        cudaStreamSynchronize(d->ctx->stream);
+        for (size_t p = 0; p < d->peers.size(); p++)
+            if (d->peers[p] && d->via_ipc[p]) cudaIpcCloseMemHandle(d->peers[p]);
+    }
+    delete d;
+}
+
+namespace {
+
+// per-block sums of the per-read k-mer counts of a local shard (block j of the shard = its j-th run of `block` reads)
+__global__ void __launch_bounds__(256)
+k_block_sums(const uint32_t *__restrict__ counts, uint64_t n, uint64_t block, unsigned long long *__restrict__ sums)
+{
+    const uint64_t j = blockIdx.x;
+    const uint64_t lo = j * block, hi = min(n, lo + block);
+    unsigned long long s = 0;
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s += counts[i];
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    __shared__ unsigned long long ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < 8; i++) t += ws[i];
+        sums[j] = t;
+    }
+}
+
+struct Resolved { uint64_t found, index, kmers; };      // found: 0 / 1; index: global read; kmers of the range
+
+// Chunk plan of the whole set from this rank's shard (see the header of this file).  plan: pairs (first, end).
+int dist_plan(commet_dist *d, commet_reads *shard, uint64_t n_global, uint64_t block, uint64_t max_kmer,
+              std::vector<uint64_t> &plan)
+{
+    commet_ctx *c = d->ctx;
+    const commet_comm &cm = d->comm;
+    const uint64_t world = (uint64_t)cm.world, rank = (uint64_t)cm.rank;
+    plan.clear();
+    const uint64_t n_local = local_index(n_global, world, rank, block);
+    if (shard->n_reads != n_local)
+        return fail("rank %d holds %llu reads, its blocks of %llu reads are %llu", cm.rank, (unsigned long long)shard->n_reads,
+                    (unsigned long long)n_global, (unsigned long long)n_local);
+    DevBuf counts(c);
+    unsigned long long total = 0;
+    CKR(count_kmers(c, shard, d->k, counts, &total));
+    std::vector<uint64_t> totals(world, 0);
+    uint64_t mine = total;
+    if (world > 1) { if (cm.all_gather(cm.user, &mine, totals.data(), sizeof mine) != 0) return fail("all_gather failed"); }
+    else totals[0] = mine;
+    if (n_global == 0) return 0;
+    uint64_t sum = 0;
+    for (uint64_t v : totals) sum += v;
+    if (sum < max_kmer) {                       // the limit is never reached: one chunk, nothing lost
+        plan.push_back(0);
+        plan.push_back(n_global);
+        return 0;
+    }
+    // per-block totals: n_global / block numbers in all
+    const uint64_t n_blocks = (n_global + block - 1) / block;
+    const uint64_t my_blocks = (n_local + block - 1) / block, slots = (n_blocks + world - 1) / world;
+    std::vector<uint64_t> mine_b(slots, 0), all_b(slots * world, 0);
+    if (my_blocks) {
+        DevBuf sums(c);
+        if (sums.alloc(my_blocks * sizeof(unsigned long long)) != cudaSuccess) return fail("allocation of block sums failed");
+        k_block_sums<<<(unsigned)my_blocks, 256, 0, c->stream>>>(counts.as<uint32_t>(), n_local, block, sums.as<unsigned long long>());
+        c->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(mine_b.data(), sums.p, my_blocks * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    if (world > 1) { if (cm.all_gather(cm.user, mine_b.data(), all_b.data(), slots * sizeof(uint64_t)) != 0) return fail("all_gather failed"); }
+    else all_b = mine_b;
+    std::vector<uint64_t> csT(n_blocks);          // inclusive prefix over the global blocks
+    {
+        uint64_t acc = 0;
+        for (uint64_t b = 0; b < n_blocks; b++) {
+            acc += all_b[(b % world) * slots + b / world];
+            csT[b] = acc;
+        }
+    }
+    std::vector<uint32_t> blk;                    // per-read counts of the one block being resolved
+    // reads [g0, g1) of ONE block, `cum` k-mers already in the open chunk: the read at which the chunk closes, if any
+    auto ask = [&](uint64_t g0, uint64_t g1, uint64_t cum, Resolved &ans) -> int {
+        const uint64_t owner = (g0 / block) % world;
+        Resolved r{0, 0, 0};
+        if (owner == rank) {
+            const uint64_t l0 = local_index(g0, world, rank, block), l1 = local_index(g1, world, rank, block);
+            blk.resize(l1 - l0);
+            if (l1 > l0) {
+                CK(cudaMemcpyAsync(blk.data(), counts.as<uint32_t>() + l0, (l1 - l0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+            }
+            uint64_t acc = 0;
+            for (uint64_t i = 0; i < l1 - l0; i++) {
+                acc += blk[i];
+                if (!r.found && cum + acc >= max_kmer) { r.found = 1; r.index = g0 + i; }
+            }
+            r.kmers = acc;
+        }
+        if (world > 1) {
+            std::vector<Resolved> all(world);
+            if (cm.all_gather(cm.user, &r, all.data(), sizeof r) != 0) return fail("all_gather failed");
+            ans = all[owner];
+        } else ans = r;
+        return 0;
+    };
+    uint64_t i = 0;
+    while (i < n_global) {
+        const uint64_t b = i / block;
+        Resolved a;
+        CKR(ask(i, std::min((b + 1) * block, n_global), 0, a));            // from read i to the end of its block
+        if (!a.found) {
+            // whole blocks after b: the first one in which the running count reaches max_kmer
+            const uint64_t target = (max_kmer - a.kmers) + csT[b];
+            const uint64_t b2 = (uint64_t)(std::lower_bound(csT.begin(), csT.end(), target) - csT.begin());
+            if (b2 >= n_blocks) {                                          // the limit is not reached again
+                plan.push_back(i);
+                plan.push_back(n_global);
+                break;
+            }
+            const uint64_t cum = a.kmers + csT[b2 - 1] - csT[b];
+            CKR(ask(b2 * block, std::min((b2 + 1) * block, n_global), cum, a));
+            if (!a.found) return fail("chunk plan: block %llu does not close the chunk it should", (unsigned long long)b2);
+        }
+        plan.push_back(i);
+        plan.push_back(a.index + 1);
+        i = a.index + 2;                                                   // read index+1 is fetched and lost (index_reads.h:60)
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_kmer, commet_reads *shard, uint64_t n_global,
+                                            uint64_t block, int n_sets, commet_reads *const *queries, uint32_t *const *d_tags,
+                                            uint64_t *searched, uint64_t *shared, uint64_t *stats)
+{
+    if (!d || !shard) return fail("commet_dist_index_and_search: null argument");
+    commet_ctx *c = d->ctx;
+    const commet_comm &cm = d->comm;
+    const int k = d->k;
+    CKR(set_device(c));
+    if (n_sets < 0) return fail("n_sets=%d unsupported", n_sets);
+    if (block == 0) return fail("commet_dist_index_and_search: block must be positive");
+    if (shard->sel) return fail("commet_dist_index_and_search: read selections are not supported on a sharded index set");
+    if (c->k != k || !c->filter) return fail("commet_dist_index_and_search: the context's filter was re-created since commet_dist_open");
+    const uint64_t world = (uint64_t)cm.world, rank = (uint64_t)cm.rank;
+    Stopwatch sw;
+    uint64_t ns_plan = 0, ns_index = 0, ns_merge = 0, ns_wait = 0;
+    std::vector<uint64_t> plan;
+    if (max_kmer == 0) {
+        // nothing is ever inserted (index_reads.h:48: 0 < 0 is false) and every call loses one read: n_global searches
+        // of an empty filter tag nothing; one of them gives the same vectors and counters
+        if (n_global) { plan.push_back(0); plan.push_back(0); }
+    } else {
+        CKR(dist_plan(d, shard, n_global, block, max_kmer, plan));
+    }
+    ns_plan = sw.lap_ns();
+    DevBuf cnt_buf(c);
+    const size_t n_cnt = 4 * (size_t)std::max(n_sets, 1);
+    if (cnt_buf.alloc(n_cnt * sizeof(unsigned long long)) != cudaSuccess) return fail("counter allocation failed");
+    unsigned long long *d_cnt = cnt_buf.as<unsigned long long>();
+    CK(cudaMemsetAsync(d_cnt, 0, n_cnt * sizeof(unsigned long long), c->stream));
+    for (int s = 0; s < n_sets; s++) CKR(prepare(c, queries[s], k));
+    const uint64_t clear_bytes = std::max<uint64_t>((commet_filter_bytes(k) + 255) & ~255ull, 256);
+    uint64_t indexed_here = 0;
+    SegTimer t_search;
+    for (size_t ci = 0; ci + 1 < plan.size(); ci += 2) {
+        CK(cudaMemsetAsync(c->filter, 0, clear_bytes, c->stream));
+        const uint64_t lo = local_index(plan[ci], world, rank, block), hi = local_index(plan[ci + 1], world, rank, block);
+        sw.lap_ns();
+        if (hi > lo) {
+            CKR(index_range(c, shard, lo, hi - lo, 0));
+            indexed_here += hi - lo;
+        }
+        if (world > 1) {
+            CK(cudaStreamSynchronize(c->stream));          // my partial filter is complete on the device ...
+            ns_index += sw.lap_ns();
+            if (cm.barrier(cm.user) != 0) return fail("barrier failed");      // ... and so is everybody else's
+            ns_wait += sw.lap_ns();
+            CKR(commet_index_merge(c, d->peers.data(), cm.world, cm.rank));
+            CK(cudaStreamSynchronize(c->stream));          // my merged slice has landed in every filter ...
+            ns_merge += sw.lap_ns();
+            if (cm.barrier(cm.user) != 0) return fail("barrier failed");      // ... and so has everybody else's
+            ns_wait += sw.lap_ns();
+        }
+        CKR(t_search.begin(c->stream));
+        for (int s = 0; s < n_sets; s++) {
+            CK(cudaMemsetAsync(d_cnt + 4 * s + 1, 0, sizeof(unsigned long long), c->stream));
+            CKR(search_launch(c, queries[s], k, t, d_tags[s], d_cnt + 4 * s));
+        }
+        CKR(t_search.end(c->stream));
+    }
+    std::vector<unsigned long long> h(n_cnt);
+    CK(cudaMemcpyAsync(h.data(), d_cnt, n_cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (world == 1) ns_index += sw.lap_ns();
+    // nobody clears or frees its filter while a peer may still be merging into / out of it
+    if (world > 1 && cm.barrier(cm.user) != 0) return fail("barrier failed");
+    uint64_t n_tests = 0, n_lookups = 0;
+    for (int s = 0; s < n_sets; s++) {
+        if (shared) shared[s] = h[4 * s];
+        if (searched) searched[s] = h[4 * s + 1];
+        n_tests += h[4 * s + 2];
+        n_lookups += h[4 * s + 3];
+    }
+    if (stats) {
+        stats[0] = max_kmer == 0 ? n_global : plan.size() / 2;
+        stats[1] = indexed_here;
+        stats[2] = ns_plan;
+        stats[3] = ns_index;
+        stats[4] = (uint64_t)(t_search.total_ms() * 1e6);
+        stats[5] = ns_merge;
+        stats[6] = ns_wait;
+        stats[7] = n_tests;
+        stats[8] = n_lookups;
+        stats[9] = plan.size() >= 2 ? plan[plan.size() - 2] : 0;       // the last chunk (global reads): what the filter holds now
+        stats[10] = plan.size() >= 2 ? plan[plan.size() - 1] : 0;
+    }
+    return 0;
+}
+
+// ------------------------------------------------- several GPUs of ONE process ----
+// commet_index_and_search over G devices: a thread per device runs the loop above on its block-cyclic shard of the
+// index set and on its slice of every query set (reads [n r / G, n (r+1) / G) cut at multiples of 32, so that the
+// slices' tag words are disjoint byte ranges of the set's vector).  The contexts live as long as the group.
+struct commet_group {
+    std::vector<commet_ctx *> ctx;
+    // in-process collectives
+    std::mutex m;
+    std::condition_variable cv;
+    int arrived = 0;
+    uint64_t generation = 0;
+    bool failed = false;                // a rank gave up: the others must not wait for it
+    std::vector<uint8_t> buf;
+};
+
+namespace {
+
+struct GroupRank { commet_group *g; int rank; };
+
+int group_barrier(void *user)
+{
+    GroupRank *gr = static_cast<GroupRank *>(user);
+    commet_group *g = gr->g;
+    std::unique_lock<std::mutex> lk(g->m);
+    const uint64_t gen = g->generation;
+    if (++g->arrived == (int)g->ctx.size()) {
+        g->arrived = 0;
+        g->generation++;
+        g->cv.notify_all();
+    } else {
+        g->cv.wait(lk, [&] { return g->generation != gen || g->failed; });
+    }
+    return g->failed ? -1 : 0;
+}
+
+int group_all_gather(void *user, const void *in, void *out, uint64_t bytes)
+{
+    GroupRank *gr = static_cast<GroupRank *>(user);
+    commet_group *g = gr->g;
+    const size_t world = g->ctx.size();
+    {
+        std::lock_guard<std::mutex> lk(g->m);
+        if (g->buf.size() < world * bytes) g->buf.resize(world * bytes);
+    }
+    if (group_barrier(user) != 0) return -1;        // the buffer has its size and nobody still reads the previous exchange
+    memcpy(g->buf.data() + (size_t)gr->rank * bytes, in, bytes);
+    if (group_barrier(user) != 0) return -1;
+    memcpy(out, g->buf.data(), world * bytes);
+    return group_barrier(user);
+}
+
+}  // namespace
+
+extern "C" int commet_group_create(const int *devices, int n_dev, commet_group **out)
+{
+    if (!devices || !out || n_dev < 1 || n_dev > kMaxPeers) return fail("commet_group_create: 1..%d devices", kMaxPeers);
+    commet_group *g = new commet_group;
+    g->ctx.assign(n_dev, nullptr);
+    std::vector<std::string> errs(n_dev);
+    std::vector<std::thread> th;
+    for (int r = 0; r < n_dev; r++)
+        th.emplace_back([&, r]() { if (commet_ctx_create(devices[r], &g->ctx[r]) != 0) errs[r] = commet_last_error(); });
+    for (auto &t : th) t.join();
+    for (int r = 0; r < n_dev; r++)
+        if (!g->ctx[r]) {
+            std::string e = errs[r];
+            commet_group_destroy(g);
+            return fail("%s", e.c_str());
+        }
+    *out = g;
+    return 0;
+}
+
+extern "C" void commet_group_destroy(commet_group *g)
+{
+    if (!g) return;
+    for (commet_ctx *c : g->ctx) commet_ctx_destroy(c);
+    delete g;
+}
+
+extern "C" int commet_group_size(const commet_group *g) { return g ? (int)g->ctx.size() : 0; }
+
+extern "C" int commet_group_index_and_search(commet_group *g, int k, int t, uint64_t max_kmer, const uint8_t *ibases,
+                                             const uint64_t *ioffs, uint64_t n_index, int n_sets,
+                                             const uint8_t *const *qbases, const uint64_t *const *qoffs,
+                                             const uint64_t *n_query, uint8_t *const *tags, uint64_t *searched,
+                                             uint64_t *shared, uint64_t *stats)
+{
+    if (!g || !ioffs) return fail("commet_group_index_and_search: null argument");
+    if (n_sets < 0) return fail("n_sets=%d unsupported", n_sets);
+    if (k < 1 || k > kMaxK) return fail("k=%d unsupported (1..%d)", k, kMaxK);
+    const int world = (int)g->ctx.size();
+    if (world == 1)
+        return commet_index_and_search(g->ctx[0], k, t, max_kmer, ibases, ioffs, n_index, n_sets, qbases, qoffs, n_query, tags,
+                                       searched, shared, stats);
+    uint64_t block = 1 << 16;
+    if (const char *e = getenv("COMMET_B200_DIST_BLOCK")) block = std::max<uint64_t>(strtoull(e, nullptr, 10), 1);      // tests
+    std::vector<std::string> errs(world);
+    std::vector<std::vector<uint64_t>> r_searched(world, std::vector<uint64_t>(n_sets, 0)), r_shared(world, std::vector<uint64_t>(n_sets, 0));
+    std::vector<std::vector<uint64_t>> r_stats(world, std::vector<uint64_t>(16, 0));
+    std::vector<GroupRank> ranks(world);
+    auto body = [&](int r) -> int {
+        commet_ctx *c = g->ctx[r];
+        CKR(set_device(c));
+        // ---- this rank's shard of the index set: its blocks, contiguous on the device ------------------------------
+        const uint64_t n_local = local_index(n_index, (uint64_t)world, (uint64_t)r, block);
+        std::vector<uint64_t> loffs(n_local + 1, 0);
+        {
+            uint64_t l = 0;
+            for (uint64_t b = (uint64_t)r; b * block < n_index; b += (uint64_t)world) {
+                const uint64_t g0 = b * block, g1 = std::min(n_index, g0 + block);
+                for (uint64_t i = g0; i < g1; i++, l++) loffs[l + 1] = loffs[l] + (ioffs[i + 1] - ioffs[i]);
+            }
+        }
+        commet_reads *shard = nullptr;
+        CKR(reads_alloc(c, n_local, loffs[n_local], &shard));
+        struct Cleanup {
+            std::vector<commet_reads *> rs; std::vector<void *> bufs; commet_ctx *c; commet_dist *d = nullptr;
+            ~Cleanup() { commet_dist_close(d); for (auto *x : rs) commet_reads_free(x); for (void *p : bufs) c->arena.free(p); }
+        } cl;
+        cl.c = c;
+        cl.rs.push_back(shard);
+        {
+            const uint64_t padded = shard->n_words * 32;
+            if (c->arena.alloc((void **)&shard->ascii, padded ? padded : 32) != cudaSuccess) return fail("device allocation of %llu staging bytes failed", (unsigned long long)padded);
+            if (padded > shard->n_bases) CK(cudaMemsetAsync(shard->ascii + shard->n_bases, 0, padded - shard->n_bases, c->stream));
+            cudaEvent_t ready;
+            CKR(take_event(c, &ready));
+            CK(cudaEventRecord(ready, c->stream));
+            CK(cudaStreamWaitEvent(c->copy_stream, ready, 0));
+            c->ev_pool.push_back(ready);
+            CKR(h2d_copy(c, shard->offs, loffs.data(), (n_local + 1) * sizeof(uint64_t), false));
+            const bool pinned = n_index == 0 || queueable(ibases);
+            uint64_t l = 0;
+            for (uint64_t b = (uint64_t)r; b * block < n_index; b += (uint64_t)world) {
+                const uint64_t g0 = b * block, g1 = std::min(n_index, g0 + block);
+                CKR(h2d_copy(c, shard->ascii + loffs[l], ibases + ioffs[g0], ioffs[g1] - ioffs[g0], pinned));
+                l += g1 - g0;
+            }
+            cudaEvent_t e;
+            CKR(take_event(c, &e));
+            CK(cudaEventRecord(e, c->copy_stream));
+            shard->chunk_ev.push_back(e);
+            shard->chunk_words = std::max<uint64_t>(shard->n_words, 1);      // one encode over the whole shard
+        }
+        // ---- this rank's slice of every query set --------------------------------------------------------------------
+        std::vector<commet_reads *> q(n_sets, nullptr);
+        std::vector<uint32_t *> dt(n_sets, nullptr);
+        std::vector<uint64_t> a0(n_sets), a1(n_sets);
+        for (int s = 0; s < n_sets; s++) {
+            const uint64_t n = n_query[s];
+            a0[s] = (n * (uint64_t)r / (uint64_t)world) & ~31ull;
+            a1[s] = r + 1 == world ? n : ((n * (uint64_t)(r + 1) / (uint64_t)world) & ~31ull);
+            CKR(reads_upload_async(c, qbases[s] + qoffs[s][a0[s]], qoffs[s] + a0[s], a1[s] - a0[s], &q[s]));
+            cl.rs.push_back(q[s]);
+            const uint64_t nw = tag_words(a1[s] - a0[s]);
+            if (c->arena.alloc((void **)&dt[s], nw * 4) != cudaSuccess) return fail("tag allocation failed");
+            cl.bufs.push_back(dt[s]);
+            CK(cudaMemsetAsync(dt[s], 0, nw * 4, c->stream));
+        }
+        // ---- the loop ---------------------------------------------------------------------------------------------------
+        commet_comm cm;
+        cm.world = world;
+        cm.rank = r;
+        cm.user = &ranks[r];
+        cm.barrier = group_barrier;
+        cm.all_gather = group_all_gather;
+        CKR(commet_dist_open(c, &cm, k, &cl.d));
+        CKR(commet_dist_index_and_search(cl.d, t, max_kmer, shard, n_index, block, n_sets, q.data(), dt.data(), r_searched[r].data(),
+                                         r_shared[r].data(), r_stats[r].data()));
+        for (int s = 0; s < n_sets; s++) {
+            const uint64_t m = a1[s] - a0[s];
+            const uint64_t bytes = r + 1 == world ? (n_query[s] / 8 + 1) - a0[s] / 8 : m / 8;
+            if (bytes) CK(cudaMemcpyAsync(tags[s] + a0[s] / 8, dt[s], bytes, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        return 0;
+    };
+    // a rank that fails marks the group: the others' collectives return an error instead of waiting for it
+    g->failed = false;
+    g->arrived = 0;
+    std::vector<std::thread> th;
+    std::vector<int> rcs(world, 0);
+    for (int r = 0; r < world; r++) {
+        ranks[r] = GroupRank{g, r};
+        th.emplace_back([&, r]() {
+            rcs[r] = body(r);
+            if (rcs[r] != 0) {
+                errs[r] = commet_last_error();
+                std::lock_guard<std::mutex> lk(g->m);       // release the ranks waiting for this one
+                g->failed = true;
+                g->cv.notify_all();
+            }
+        });
+    }
+    for (auto &x : th) x.join();
+    for (int r = 0; r < world; r++)          // the rank that failed first has the message that matters
+        if (rcs[r] != 0 && errs[r].find("barrier failed") == std::string::npos && errs[r].find("all_gather failed") == std::string::npos)
+            return fail("GPU %d: %s", g->ctx[r]->device, errs[r].c_str());
+    for (int r = 0; r < world; r++)
+        if (rcs[r] != 0) return fail("GPU %d: %s", g->ctx[r]->device, errs[r].c_str());
+    for (int s = 0; s < n_sets; s++) {
+        if (searched) searched[s] = 0;
+        if (shared) shared[s] = 0;
+        for (int r = 0; r < world; r++) {
+            if (searched) searched[s] += r_searched[r][s];
+            if (shared) shared[s] += r_shared[r][s];
+        }
+    }
+    if (stats) {
+        // same layout as commet_index_and_search: chunks, indexed, k-mers (not counted here), index ns, search ns (device
+        // time of the slowest rank), tests, lookups, GPUs
+        for (int i = 0; i < 8; i++) stats[i] = 0;
+        stats[0] = r_stats[0][0];
+        for (int r = 0; r < world; r++) {
+            stats[1] += r_stats[r][1];
+            stats[3] = std::max(stats[3], r_stats[r][3] + r_stats[r][5] + r_stats[r][6]);
+            stats[4] = std::max(stats[4], r_stats[r][4]);
+            stats[5] += r_stats[r][7];
+            stats[6] += r_stats[r][8];
+        }
+        stats[7] = (uint64_t)world;
+    }
+    return 0;
+}

@@ -6,6 +6,7 @@
 
 #include <chrono>
 #include <cstdlib>
+#include <algorithm>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -42,8 +43,48 @@ struct PassResult {
     double index_s = 0, search_s = 0, total_s = 0;
 };
 
-// One chunk loop (src/index_and_search.cpp:255-277) on the GPU: `index` against every set of `queries`.
-inline PassResult run_pass(commet_ctx *ctx, int k, int t, uint64_t max_kmer, ReadSet &index,
+// The GPU(s) a tool runs on.  COMMET_B200_GPUS = N asks for the first N visible devices, "all" for every one; unset:
+// one GPU, or every visible one when the sets hold at least 2e9 bases (what makes dealing the index set over the
+// box worth the extra contexts).  COMMET_B200_DEVICES = "0,0,1" names the devices rank by rank (tests: several ranks
+// may share a GPU).  More than one device -> commet_group_* (the index set dealt over the GPUs, the partial filters
+// merged over NVLink); otherwise a plain context on device 0.
+struct Engine {
+    commet_ctx *ctx = nullptr;
+    commet_group *group = nullptr;
+
+    bool open(uint64_t total_bases)
+    {
+        std::vector<int> devices;
+        if (const char *e = getenv("COMMET_B200_DEVICES")) {
+            for (const char *p = e; *p;) {
+                devices.push_back(atoi(p));
+                while (*p && *p != ',') p++;
+                if (*p == ',') p++;
+            }
+        } else {
+            int want = 1;
+            const int visible = commet_device_count();
+            const char *e2 = getenv("COMMET_B200_GPUS");
+            if (e2 && std::string(e2) == "all") want = visible;
+            else if (e2 && atoi(e2) > 0) want = atoi(e2);
+            else if (total_bases >= 2000000000ull) want = visible;
+            want = std::max(1, std::min(std::min(want, visible), 8));
+            for (int i = 0; i < want; i++) devices.push_back(i);
+        }
+        if (devices.size() > 1) return commet_group_create(devices.data(), (int)devices.size(), &group) == 0;
+        return commet_ctx_create(devices.empty() ? 0 : devices[0], &ctx) == 0;
+    }
+    void close()
+    {
+        if (group) commet_group_destroy(group);
+        if (ctx) commet_ctx_destroy(ctx);
+        group = nullptr;
+        ctx = nullptr;
+    }
+};
+
+// One chunk loop (src/index_and_search.cpp:255-277) on the GPU(s): `index` against every set of `queries`.
+inline PassResult run_pass(Engine &eng, int k, int t, uint64_t max_kmer, ReadSet &index,
                            std::vector<ReadSet *> &queries, bool banners, const char *tool = "index_and_search")
 {
     PassResult res;
@@ -65,9 +106,13 @@ inline PassResult run_pass(commet_ctx *ctx, int k, int t, uint64_t max_kmer, Rea
     }
     uint64_t stats[8] = {0};
     auto t0 = std::chrono::steady_clock::now();
-    int rc = commet_index_and_search(ctx, k, t, max_kmer, index.bases.empty() ? &none : index.bases.data(),
-                                     index.offs.data(), index.n_valid(), (int)ns, qb.data(), qo.data(), nq.data(),
-                                     tp.data(), res.searched.data(), res.shared.data(), stats);
+    const uint8_t *ib = index.bases.empty() ? &none : index.bases.data();
+    int rc = eng.group ? commet_group_index_and_search(eng.group, k, t, max_kmer, ib, index.offs.data(), index.n_valid(), (int)ns,
+                                                       qb.data(), qo.data(), nq.data(), tp.data(), res.searched.data(),
+                                                       res.shared.data(), stats)
+                       : commet_index_and_search(eng.ctx, k, t, max_kmer, ib, index.offs.data(), index.n_valid(), (int)ns,
+                                                 qb.data(), qo.data(), nq.data(), tp.data(), res.searched.data(),
+                                                 res.shared.data(), stats);
     if (rc != 0) {
         std::cerr << tool << ": " << commet_last_error() << "\n";
         exit(1);

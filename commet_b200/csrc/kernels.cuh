@@ -591,6 +591,253 @@ k_bin_apply(uint32_t *__restrict__ filter, const uint32_t *__restrict__ recs,
     }
 }
 
+// ------------------------------- stage 1, L2-blocked variant, second form ----
+// Same idea (records partitioned by filter region, then applied region after region), without the histogram
+// pass and with half the shared-memory traffic and instructions per record:
+//   * no k_bin_count: a region's records live in SLABS of 2^kSlabLog2 records handed out on demand.  A tile's
+//     run for region b reserves `cnt` places with one atomicAdd on fill[b] (the region's virtual record stream);
+//     the block whose reservation covers the first place of a slab allocates it (atomicAdd on the slab counter)
+//     and publishes its id in table[b][slab]; blocks whose runs land in a slab they did not open wait for the
+//     id.  The opener has already executed its atomicAdd -- it is resident and publishes before it waits for
+//     anything itself -- so the wait always ends.
+//   * a tile's plane words are loaded once into shared memory; the keys are generated twice from there (first
+//     only their regions, for the per-region counts; then in full, taking their place in the region-sorted tile
+//     from a shared-memory cursor) instead of being carried in registers across the scan: no per-record
+//     register state, so tiles can be larger (longer runs per region) and more blocks fit an SM.
+//   * copy-out by region run: a warp copies whole runs (coalesced), no per-record region lookup.
+//   * k_bin_apply2 takes tiles that never span two regions (per-region tile ranges from fill[]), so the inner
+//     loop has no region walk, and all index arithmetic inside a tile is 32-bit.
+constexpr int kSlabLog2 = 18;                        // records per slab (1 MiB)
+constexpr uint32_t kSlabRecs = 1u << kSlabLog2;
+constexpr int kS2Threads = 512;
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// dynamic shared memory of k_bin_scatter2<TW>: stage[TW*128] | planes[TW+2] (uint4) | 6 arrays of n_bins u32 | wsum[16]
+__host__ __device__ inline size_t scatter2_smem_bytes(int tw, int n_bins)
+{
+    return (size_t)tw * 128 * 4 + (size_t)(tw + 2) * 16 + (size_t)6 * n_bins * 4 + 16 * 4;
+}
+
+// fill[b]: records reserved for region b so far; table[b * max_q + q]: 1 + id of the q-th slab of region b
+// (0: not opened yet); n_slabs: slabs handed out.  All zeroed by the host before the launch.
+template <int TW>
+__global__ void __launch_bounds__(kS2Threads, (TW <= 64 ? 3 : 2))
+k_bin_scatter2(const uint4 *__restrict__ planes, uint64_t b0, uint64_t b1, int k, int n_bins,
+               uint32_t *__restrict__ fill, uint32_t *__restrict__ table, uint32_t max_q,
+               uint32_t *__restrict__ n_slabs, uint32_t *__restrict__ recs)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw);
+    uint4 *pl = reinterpret_cast<uint4 *>(smem_raw + (size_t)TW * 128 * 4);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(pl + TW + 2);
+    uint32_t *cur = cnt + n_bins, *start = cur + n_bins, *gpos = start + n_bins, *sid0 = gpos + n_bins,
+             *sid1 = sid0 + n_bins, *wsum = sid1 + n_bins;
+    constexpr int kWarps = kS2Threads / 32;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t pol = ld_policy_evict_first();
+    const uint64_t w_first = b0 >> 5, w_end = (b1 + 31) >> 5;
+    const uint64_t n_tiles = (w_end - w_first + TW - 1) / TW;
+    const int top = 32 - (k - kRecKeyBits);
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t w0 = w_first + tile * TW;
+        // ---- the tile's plane words (+2 of halo), W restricted to [b0, b1) -----------------------------
+        for (uint32_t i = tid; i < (uint32_t)TW + 2; i += kS2Threads) {
+            const uint64_t wi = w0 + i;
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            if (wi < w_end + 2) {                       // planes carry 4 zero words past the end
+                q = ld_nc_u4(planes + wi);
+                q.w = (wi < w_end && i < (uint32_t)TW) ? w_in_range(q.w, wi, b0, b1) : 0u;
+            }
+            pl[i] = q;
+        }
+        for (uint32_t i = tid; i < (uint32_t)n_bins; i += kS2Threads) cnt[i] = 0;
+        __syncthreads();
+        // ---- pass A: regions only -> per-region counts -----------------------------------------------------
+#pragma unroll 2
+        for (int wl = (int)warp; wl < TW; wl += kWarps) {
+            const uint4 q0 = pl[wl];
+            if (!((q0.w >> lane) & 1u)) continue;
+            const uint4 q1 = pl[wl + 1];
+            const uint32_t ba = __brev(__funnelshift_r(q0.x, q1.x, lane)) >> top;
+            const uint32_t bb = __brev(__funnelshift_r(q0.y, q1.y, lane)) >> top;
+            atomicAdd(&cnt[ba], 1u);
+            atomicAdd(&cnt[bb], 1u);
+            atomicAdd(&cnt[ba ^ bb], 1u);
+            atomicAdd(&cnt[ba | bb], 1u);
+        }
+        __syncthreads();
+        // ---- scan over the regions (one per thread), reservation in the regions' record streams, slabs ---------
+        {
+            const uint32_t c = (int)tid < n_bins ? cnt[tid] : 0u;
+            uint32_t incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += v;
+            }
+            if (lane == 31) wsum[warp] = incl;
+            __syncthreads();
+            uint32_t off = 0;
+            for (uint32_t w = 0; w < warp; w++) off += wsum[w];
+            if ((int)tid < n_bins) {
+                const uint32_t excl = off + incl - c;
+                start[tid] = excl;
+                cur[tid] = excl;
+                if (c) {
+                    const uint32_t g = atomicAdd(&fill[tid], c);
+                    gpos[tid] = g;
+                    const uint32_t qa = g >> kSlabLog2, qb = (g + c - 1) >> kSlabLog2;
+                    uint32_t *row = table + (size_t)tid * max_q;
+                    uint32_t ida = 0, idb = 0;
+                    // open the slabs whose first place this run covers -- before waiting for anything
+                    if ((g & (kSlabRecs - 1)) == 0) { ida = atomicAdd(n_slabs, 1u) + 1; st_release_u32(row + qa, ida); }
+                    if (qb != qa) { idb = atomicAdd(n_slabs, 1u) + 1; st_release_u32(row + qb, idb); }
+                    while (ida == 0) ida = ld_acquire_u32(row + qa);
+                    sid0[tid] = ida - 1;
+                    sid1[tid] = qb != qa ? idb - 1 : ida - 1;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- pass B: full records, placed region-sorted through the cursors ----------------------------------------
+#pragma unroll 2
+        for (int wl = (int)warp; wl < TW; wl += kWarps) {
+            const uint4 q0 = pl[wl];
+            if (!((q0.w >> lane) & 1u)) continue;
+            const uint4 q1 = pl[wl + 1], q2 = pl[wl + 2];
+            const BinKeys q = bin_keys(window64(q0.x, q1.x, q2.x, lane), window64(q0.y, q1.y, q2.y, lane), k);
+#pragma unroll
+            for (int j = 0; j < 4; j++) stage[atomicAdd(&cur[q.bin[j]], 1u)] = q.rec[j];
+        }
+        __syncthreads();
+        // ---- copy-out: a warp per region run ----------------------------------------------------------------
+        for (int b = (int)warp; b < n_bins; b += kWarps) {
+            const uint32_t c = cnt[b];
+            if (c == 0) continue;
+            const uint32_t s = start[b], g = gpos[b], qa = g >> kSlabLog2;
+            const size_t base0 = (size_t)sid0[b] << kSlabLog2, base1 = (size_t)sid1[b] << kSlabLog2;
+            for (uint32_t i = lane; i < c; i += 32) {
+                const uint32_t v = g + i;
+                st_stream_u32(recs + (((v >> kSlabLog2) == qa ? base0 : base1) + (v & (kSlabRecs - 1))), stage[s + i], pol);
+            }
+        }
+        __syncthreads();                   // stage / cnt / planes are rewritten by the next tile
+    }
+}
+
+// per-region tile ranges of k_bin_apply2: tbase[b] = first tile of region b, tbase[n_bins] = number of tiles
+template <int TILE>
+__global__ void k_bin_plan2(const uint32_t *__restrict__ fill, int n_bins, uint32_t *__restrict__ tbase,
+                            unsigned long long *__restrict__ tile_counter)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int b = 0; b < n_bins; b++) {
+            tbase[b] = acc;
+            acc += (fill[b] + TILE - 1) / TILE;
+        }
+        tbase[n_bins] = acc;
+        *tile_counter = 0;
+    }
+}
+
+// Tiles are taken in order from a global counter (region-major), every tile lies inside one region and one slab
+// (TILE divides the slab size): the inner loop is load, mask, RED.
+template <int TILE, bool PREFETCH>
+__global__ void __launch_bounds__(256)
+k_bin_apply2(uint32_t *__restrict__ filter, const uint32_t *__restrict__ recs, const uint32_t *__restrict__ fill,
+             const uint32_t *__restrict__ tbase, const uint32_t *__restrict__ table, uint32_t max_q, int n_bins,
+             unsigned long long *__restrict__ tile_counter)
+{
+    constexpr int U = TILE / (256 * 4);                    // 16-byte loads per thread per tile
+    static_assert((kSlabRecs % TILE) == 0, "a tile must not span two slabs");
+    __shared__ uint32_t sbase[kMaxBins + 1];
+    __shared__ uint32_t sfill[kMaxBins];
+    __shared__ uint32_t s_next;
+    __shared__ int s_bin;
+    for (int i = threadIdx.x; i <= n_bins; i += blockDim.x) sbase[i] = tbase[i];
+    for (int i = threadIdx.x; i < n_bins; i += blockDim.x) sfill[i] = fill[i];
+    __syncthreads();
+    const uint32_t n_tiles = sbase[n_bins];
+    const uint64_t pol = ld_policy_evict_first();
+    auto bin_of = [&](uint32_t t) {                        // last region with tbase <= t (regions without tiles are skipped)
+        int lo = 0, hi = n_bins - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (sbase[mid] <= t) lo = mid; else hi = mid - 1;
+        }
+        return lo;
+    };
+    if (threadIdx.x == 0) {
+        unsigned long long tl = atomicAdd(tile_counter, 1ull);
+        s_next = tl < n_tiles ? (uint32_t)tl : n_tiles;
+        s_bin = tl < n_tiles ? bin_of((uint32_t)tl) : 0;
+    }
+    __syncthreads();
+    uint32_t tl = s_next;
+    int bin = s_bin;
+    while (tl < n_tiles) {
+        __syncthreads();                                   // everybody holds tl/bin: the slots may be overwritten
+        unsigned long long nxt = 0;
+        if (threadIdx.x == 0) nxt = atomicAdd(tile_counter, 1ull);      // consumed after this tile
+        const uint32_t lt = tl - sbase[bin];                          // tile inside the region
+        const uint32_t v0 = lt * TILE;                                // first record of the tile in the region's stream
+        const uint32_t n_here = min((uint32_t)TILE, sfill[bin] - v0);
+        const uint32_t slab = table[(size_t)bin * max_q + (v0 >> kSlabLog2)] - 1u;
+        const uint4 *src = reinterpret_cast<const uint4 *>(recs + (((size_t)slab << kSlabLog2) + (v0 & (kSlabRecs - 1))));
+        uint4 v[U];
+#pragma unroll
+        for (int it = 0; it < U; it++) {
+            const uint32_t e = (it * 256 + threadIdx.x) * 4;
+            v[it] = make_uint4(0u, 0u, 0u, 0u);
+            if (e < n_here) v[it] = ld_stream_u4(src + (it * 256 + threadIdx.x), pol);      // slabs are whole: the tail of a vector is readable
+        }
+        if (PREFETCH && bin + 1 < n_bins) {
+            // the tiles of region b pull region b+1 into L2 ahead of its first RED, each tile an equal slice, as
+            // sequential line prefetches -- unless b+1 receives too few records to touch most of its lines
+            const uint32_t nf = sfill[bin + 1];
+            if (nf >= (1u << (kRegionLog2 - 8))) {                              // >= half a record per line
+                const uint32_t n_t = sbase[bin + 1] - sbase[bin];
+                const uint32_t lines = 1u << (kRegionLog2 - 7);
+                const uint32_t l0 = (uint32_t)((uint64_t)lines * lt / n_t), l1 = (uint32_t)((uint64_t)lines * (lt + 1) / n_t);
+                const char *nxt_region = reinterpret_cast<const char *>(filter) + ((uint64_t)(bin + 1) << kRegionLog2);
+                for (uint32_t l = l0 + threadIdx.x; l < l1; l += 256)
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(nxt_region + ((uint64_t)l << 7)));
+            }
+        }
+        uint32_t *region = filter + ((uint64_t)bin << (kRegionLog2 - 2));
+#pragma unroll
+        for (int it = 0; it < U; it++) {
+            const uint32_t e = (it * 256 + threadIdx.x) * 4;
+            const uint32_t r[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                if (e + x < n_here) {
+                    const uint32_t key_low = r[x] & kRecMask;
+                    atomicOr(region + (key_low >> 3), key_bit((uint64_t)key_low, (int)(r[x] >> kRecKeyBits)));
+                }
+            }
+        }
+        if (threadIdx.x == 0) {
+            s_next = nxt < n_tiles ? (uint32_t)nxt : n_tiles;
+            s_bin = nxt < n_tiles ? bin_of((uint32_t)nxt) : 0;
+        }
+        __syncthreads();
+        tl = s_next;
+        bin = s_bin;
+    }
+}
+
 // --------------------------------- stage 1, region-pass variant (no sort) ----
 // The region of a key is its TOP bits = the k-mer's FIRST R bases, so "which k-mers of this 32-position
 // word fall into region r" is a bit-parallel pattern match on the plane words: R funnel-shift + LOP3 pairs

@@ -138,8 +138,8 @@ int main(int argc, char **argv)
     B.build_stream(true);
     const uint64_t nb_reads_A = A.n_valid(), nb_reads_B = B.n_valid();
 
-    commet_ctx *ctx = nullptr;
-    if (commet_ctx_create(0, &ctx) != 0) {
+    Engine ctx;
+    if (!ctx.open(A.bases.size() + B.bases.size())) {
         std::cerr << "compare_reads: " << commet_last_error() << "\n";
         return 1;
     }
@@ -179,6 +179,6 @@ int main(int argc, char **argv)
     print_times(r3);
     std::cout << " " << 100 * (float)r3.shared[0] / (float)nb_reads_B << "%\n";
 
-    commet_ctx_destroy(ctx);
+    ctx.close();
     return 0;
 }

@@ -148,8 +148,10 @@ int main(int argc, char **argv)
     const uint64_t nb_reads_A = index_set.n_valid();
     const uint64_t nb_reads_B = search_sets[0]->n_valid();
 
-    commet_ctx *ctx = nullptr;
-    if (commet_ctx_create(0, &ctx) != 0) {
+    uint64_t total_bases = index_set.bases.size();
+    for (auto &s : search_sets) total_bases += s->bases.size();
+    Engine ctx;
+    if (!ctx.open(total_bases)) {
         std::cerr << "index_and_search: " << commet_last_error() << "\n";
         return 1;
     }
@@ -218,7 +220,7 @@ int main(int argc, char **argv)
         log_file.close();
     }
 
-    commet_ctx_destroy(ctx);
+    ctx.close();
 
     // ---- outputs, :397-399 ------------------------------------------------------
     for (auto &s : search_sets) s->save_bv(out_path, index_specs.begin()->first);

@@ -148,6 +148,53 @@ int commet_peer_open(commet_ctx *ctx, const uint8_t handle[COMMET_IPC_HANDLE_BYT
 int commet_peer_close(commet_ctx *ctx, void *d_filter);
 int commet_index_merge(commet_ctx *ctx, void *const *d_filters, int n_ranks, int rank);
 
+/* ---- multi-GPU: the chunk loop of src/index_and_search.cpp:255-277 with the index set dealt over the ranks ----
+ * One rank = one GPU.  Block b of `block` consecutive reads of the index set's valid-read stream lives on rank
+ * b % world: a rank stages only its own blocks (its SHARD, reads in global order), and every chunk is a contiguous
+ * range of local reads on every rank.  Per chunk every rank inserts its reads into its own filter, the partial
+ * filters are merged by commet_index_merge, and every rank probes its own query streams.  The stop rule of
+ * index_reads (include/index_reads.h:48-49,60) is evaluated on k-mer counts the ranks exchange: totals, then
+ * per-block totals, then the one read that closes each chunk -- the plan equals commet_chunk_plan's on the whole set.
+ *
+ * The ranks may be processes or threads; the two collectives the loop needs are callbacks (return 0 on success):
+ * barrier(user) returns once every rank has called it; all_gather(user, in, out, bytes) gives every rank the
+ * `bytes`-byte contributions of all ranks in rank order (out: world * bytes).  Filters of ranks in other processes
+ * are mapped through CUDA IPC, those of threads of this process through peer access. */
+typedef struct commet_comm {
+    int world, rank;
+    void *user;
+    int (*barrier)(void *user);
+    int (*all_gather)(void *user, const void *in, void *out, uint64_t bytes);
+} commet_comm;
+typedef struct commet_dist commet_dist;
+/* collective: allocates the context's filter for k and maps every peer's.  The context must not get another
+ * filter (commet_index_begin / commet_index_and_search* with another k) while the handle is open. */
+int commet_dist_open(commet_ctx *ctx, const commet_comm *comm, int k, commet_dist **out);
+/* collective.  shard: this rank's blocks of the index set (n_global reads in all); queries / d_tags / searched /
+ * shared: this rank's own query streams, as in commet_index_and_search_staged.  stats[11]: chunks, reads indexed
+ * by this rank, then host nanoseconds spent in the plan, the inserts, [4] = device ns of the searches, the merges,
+ * the barriers; filter tests and k-mer lookups (with commet_ctx_count_probes); first and end read of the last
+ * chunk (what the filter holds when the call returns). */
+int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_kmer, commet_reads *shard, uint64_t n_global,
+                                 uint64_t block, int n_sets, commet_reads *const *queries, uint32_t *const *d_tags,
+                                 uint64_t *searched, uint64_t *shared, uint64_t *stats);
+void commet_dist_close(commet_dist *d);
+
+/* The same over several GPUs of ONE process, behind the signature of commet_index_and_search: a thread per
+ * device stages its shard of the index set and its slice of every query set (contiguous reads, cut at multiples
+ * of 32) from the host buffers, runs the loop above and writes its byte range of every tag vector.  What the
+ * drop-in index_and_search executable calls when COMMET_B200_GPUS asks for more than one GPU.  stats[8] as
+ * commet_index_and_search (stats[2], the k-mer count, is 0; stats[7] = GPUs used). */
+typedef struct commet_group commet_group;
+int commet_group_create(const int *devices, int n_dev, commet_group **out);
+void commet_group_destroy(commet_group *g);
+int commet_group_size(const commet_group *g);
+int commet_group_index_and_search(commet_group *g, int k, int t, uint64_t max_kmer, const uint8_t *ibases,
+                                  const uint64_t *ioffs, uint64_t n_index, int n_sets,
+                                  const uint8_t *const *qbases, const uint64_t *const *qoffs,
+                                  const uint64_t *n_query, uint8_t *const *tags, uint64_t *searched,
+                                  uint64_t *shared, uint64_t *stats);
+
 /* ---- stage 2: search_reads ------------------------------------------------
  * include/search_reads.h:34-87 against the context's current filter: for
  * every read whose bit in `tags` is 0 (FileManager skips tagged reads,

@@ -1,0 +1,7 @@
+#!/bin/bash
+# round 2, call b: new tool tests + insert second form (parity, then A/B timing on C2)
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fullsize.py -q -m gpu -x -k "l2_blocked or k33 or sorted_insert or chunk_loop" > gpurun_out/r02b_insert_tests.txt 2>&1; echo "insert tests rc=$?"; tail -5 gpurun_out/r02b_insert_tests.txt
+timeout 600 python -m pytest tests/test_gpu_tools.py -q -m gpu -k "commet_py or compare_reads or unreadable or negative_max or thirty" > gpurun_out/r02b_tool_tests.txt 2>&1; echo "tool tests rc=$?"; tail -5 gpurun_out/r02b_tool_tests.txt
+timeout 900 python scripts/ab_index.py COMMET_B200_INSERT=1 COMMET_B200_INSERT=2,COMMET_B200_S2_TW=128 COMMET_B200_S2_TW=96 COMMET_B200_S2_TW=64 COMMET_B200_S2_TW=128,COMMET_B200_APPLY_TILE=4096 COMMET_B200_APPLY_TILE=2048,COMMET_B200_APPLY_BPS=6 COMMET_B200_APPLY_BPS=8,COMMET_B200_APPLY_PREFETCH=0 > gpurun_out/r02b_ab.txt 2>&1; echo "ab rc=$?"; cat gpurun_out/r02b_ab.txt

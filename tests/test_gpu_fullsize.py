@@ -95,19 +95,21 @@ def test_c2_filter_sorted_insert_equals_direct_and_oracle_keys(env):
     F = oracle.filter_bytes(K)
     torch.cuda.synchronize()
     idx = ctx.stage_device(e["ref"].data_ptr(), e["offs"].data_ptr(), N, N * L)
-    ctx.binned_index(1)
+    ctx.binned_index(102)                 # second form of the L2-blocked insert (slabs, no histogram pass): the default
     ctx.index_reads(idx, K)
     ctx.sync()
     sorted_f = torch.as_tensor(_DevMem(ctx.filter_ptr, F), device=e["dev"]).clone()
     torch.cuda.synchronize()              # the copy runs on torch's stream: it must land before the context clears the filter
-    ctx.binned_index(0)
     try:
-        ctx.index_reads(idx, K)
-        ctx.sync()
+        for mode in (101, 0):             # first form (histogram + scatter + apply), then direct RED.OR
+            ctx.binned_index(mode)
+            ctx.index_reads(idx, K)
+            ctx.sync()
+            other_f = torch.as_tensor(_DevMem(ctx.filter_ptr, F), device=e["dev"])
+            assert torch.equal(sorted_f, other_f), mode
+            del other_f
     finally:
-        ctx.binned_index(1)
-    direct_f = torch.as_tensor(_DevMem(ctx.filter_ptr, F), device=e["dev"])
-    assert torch.equal(sorted_f, direct_f)
+        ctx.binned_index(102)
     # at most one bit per key; a, b, c keys are uniform over 2^33 positions (~6.54e8 distinct each), d = a|b is not
     ones = ctx.nb_one_device(ctx.filter_ptr, 8 * (F - 1))
     kmers = N * (L - K + 1)
@@ -292,3 +294,66 @@ def test_c4_shape_many_chunks_eight_query_sets(env):
     for s in range(8):
         assert np.array_equal(tags[s], oracle.tags_to_bv(exp_tags[s])), s
         assert 0.4 < info["shared"][s] / n_q < 0.7
+
+
+def _write_fasta_fixed(path, bases_2d):
+    """>%08d headers, one sequence line per read, written as one numpy array (10 M reads: ~1.1 GB, seconds)"""
+    n, length = bases_2d.shape
+    rows = np.empty((n, 1 + 8 + 1 + length + 1), dtype=np.uint8)
+    rows[:, 0] = ord(">")
+    idx = np.arange(n, dtype=np.int64)
+    for d in range(8):
+        rows[:, 1 + d] = (idx // 10 ** (7 - d)) % 10 + 48
+    rows[:, 9] = 10
+    rows[:, 10:10 + length] = bases_2d
+    rows[:, -1] = 10
+    rows.tofile(path)
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref did not travel")
+def test_c2_whole_vector_equals_the_reference_binary(env, tmp_path):
+    """C2 at full size through the executables: `commet_b200/bin/index_and_search` on the two 10 M x 100 bp FASTA files
+    against the reference's own index_and_search (oracle/_ref) on the same files -- every bit of the 10 M-read vector.
+    The reference is single-threaded (about 3 minutes of indexing + 2 of search here), so it is run as several
+    processes over contiguous parts of the query file, each indexing the whole reference file; part sizes are multiples
+    of 8 reads, so each part's payload is a byte range of the whole vector."""
+    import os
+    import subprocess
+    from commet_b200 import build
+    build.build_tools()
+    e, torch = env, env["torch"]
+    ref = e["ref"].view(N, L).cpu().numpy()
+    qry = e["qry"].view(N, L).cpu().numpy()
+    _write_fasta_fixed(tmp_path / "ref.fa", ref)
+    (tmp_path / "ref.txt").write_text("ref:ref.fa\n")
+    procs = max(1, min(8, (os.cpu_count() or 2) // 2))
+    per = ((N + procs - 1) // procs + 7) // 8 * 8
+    parts = [(s, min(N, s + per)) for s in range(0, N, per)]
+    cmds = []
+    for i, (s, t) in enumerate(parts):
+        _write_fasta_fixed(tmp_path / f"q{i}.fa", qry[s:t])
+        (tmp_path / f"q{i}.txt").write_text(f"q{i}:q{i}.fa\n")
+        cmds.append([str(oracle.REF_DIR / "index_and_search"), "-i", "ref.txt", "-s", f"q{i}.txt", "-o", f"ref_out{i}", "-l",
+                     f"ref_out{i}", "-k", str(K), "-t", str(T)])
+    running = [subprocess.Popen(c, cwd=tmp_path, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for c in cmds]
+    # meanwhile: the drop-in tool on the whole query file
+    _write_fasta_fixed(tmp_path / "qry.fa", qry)
+    (tmp_path / "qry.txt").write_text("qry:qry.fa\n")
+    r = subprocess.run([str(build.BIN / "index_and_search"), "-i", "ref.txt", "-s", "qry.txt", "-o", "gpu_out", "-l", "gpu_out",
+                        "-k", str(K), "-t", str(T)], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    comment, n, mine = oracle.read_bv_file(tmp_path / "gpu_out" / "qry.fa_in_ref.bv")
+    assert n == N and comment == b"qry.fa in ref"
+    assert all(p.wait(timeout=1500) == 0 for p in running)
+    shared = 0
+    for i, (s, t) in enumerate(parts):
+        _, n_i, theirs = oracle.read_bv_file(tmp_path / f"ref_out{i}" / f"q{i}.fa_in_ref.bv")
+        assert n_i == t - s
+        whole = (t - s) // 8
+        assert np.array_equal(mine[s // 8:s // 8 + whole], theirs[:whole]), f"part {i}: payload differs from the reference's"
+        if (t - s) % 8:                                          # only the last part can end inside a byte
+            assert mine[s // 8 + whole] == theirs[whole]
+        shared += int(np.unpackbits(theirs, bitorder="little")[:t - s].sum())
+    assert 0.4 < shared / N < 0.6
+    log = (tmp_path / "gpu_out" / "qry_in_ref.log").read_text()
+    assert f"[indexed {N}, searched {N}, shared {shared}]" in log

@@ -50,13 +50,13 @@ def test_index_filter_bit_exact(ctx, k, dirt):
 
 
 @pytest.mark.parametrize("k,budget", [(28, None), (29, None), (31, None), (28, "5000"), (30, "100000")])
-@pytest.mark.parametrize("mode", [1, 26, 22])
+@pytest.mark.parametrize("mode", [101, 102, 26, 22])
 def test_index_l2_blocked_path_bit_exact(ctx, k, budget, mode, monkeypatch):
     """Filters larger than L2 are fed region by region -- by sorting key records by region first (mode 1, also
     when the record buffer forces several sub-ranges) or by region passes over the stream (modes 26 and 22 = 64 MiB
     and 4 MiB regions, i.e. few and many passes): same bits as the oracle and as the direct RED.OR path."""
     if budget:
-        if mode != 1:
+        if mode < 100:
             pytest.skip("the record budget only concerns the sorted path")
         monkeypatch.setenv("COMMET_B200_RECS_BUDGET", budget)
     rng = np.random.default_rng(k)
@@ -77,7 +77,7 @@ def test_index_l2_blocked_path_bit_exact(ctx, k, budget, mode, monkeypatch):
         ctx.index_reads(rs, k, 5, 3000)
         assert np.array_equal(ctx.filter_download(k), direct)
     finally:
-        ctx.binned_index(1)
+        ctx.binned_index(102)
 
 
 @pytest.mark.parametrize("k", [3, 9, 12, 17, 21])
@@ -121,24 +121,24 @@ def test_search_against_reference_built_filter(ctx, seed):
 
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7, 27, 31, 32, 33, 34, 35])
 def test_search_small_and_large_k(ctx, k):
-    """k below the probe batch (the k-jump after a hit lands inside the batch that found it) and k up to the 61-base
-    limit, t = 0..3, reads shorter than k, both the one-pass two-strand scan and the reference-order scan
-    (probe counting on) against the oracle (k <= 24; above that the two scans are compared with each other).  Low-complexity references keep small-k filters from saturating."""
+    """k below the probe batch (the k-jump after a hit lands inside the batch that found it) and k up to 35 (a 16 GiB
+    filter), t = 0..3, reads shorter than k, both the one-pass two-strand scan and the reference-order scan (probe
+    counting on) against the oracle at EVERY k -- its 2^(k-1)-byte filter is calloc'ed, so only the touched pages
+    exist.  Low-complexity references keep small-k filters from saturating."""
     rng = np.random.default_rng(300 + k)
     L = max(3 * k, 12)
     alphabet = np.frombuffer(b"AC" if k < 8 else b"ACGT", dtype=np.uint8)
     ref = [alphabet[rng.integers(0, len(alphabet), size=int(rng.integers(max(1, k - 2), L)))].tobytes() for _ in range(40 if k < 28 else 300)]
     qry = H.make_query_set(rng, ref, 300, max(1, k - 3), L, frac_shared=0.5, sub_rate=0.05, p_N=0.03)
     for t in range(0, 4):
-        if k <= 24:
-            exp_tags, exp = oracle.index_and_search(k, t, H.to_stream(ref), [H.to_stream(qry)], 1 << 60)
+        exp_tags, exp = oracle.index_and_search(k, t, H.to_stream(ref), [H.to_stream(qry)], 1 << 60)
         for count in (False, True):
             ctx.count_probes(count)
             tags, info = ctx.index_and_search(k, t, H.to_stream(ref), [H.to_stream(qry)], 1 << 60)
-            if k <= 24:
-                assert np.array_equal(tags[0], oracle.tags_to_bv(exp_tags[0])), (k, t, count)
-                assert info["shared"] == exp["shared"]
+            assert np.array_equal(tags[0], oracle.tags_to_bv(exp_tags[0])), (k, t, count)
+            assert info["shared"] == exp["shared"]
             if count:
+                assert info["tests"] == exp["tests"] and info["lookups"] == exp["lookups"], (k, t)
                 ref_order = tags[0].copy()
             else:
                 one_pass = tags[0].copy()

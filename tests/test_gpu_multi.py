@@ -93,21 +93,23 @@ def _worker_distributed(rank, world, port, k, t, maxk, seed, block, n_dev, out_d
         tags = torch.zeros((nq // 8 + 1 + 3) // 4, dtype=torch.int32, device=f"cuda:{dev}")
         counters = torch.zeros(4, dtype=torch.int64, device=f"cuda:{dev}")
         torch.cuda.synchronize()
-        be = multi.DeviceBackend(ctx, idx, [q], [tags.data_ptr()], [counters.data_ptr()])
 
         def all_gather(obj):
             out = [None] * world
             dist.all_gather_object(out, obj)
             return out
-        be.connect(k, world, rank, all_gather)
-        info = multi.distributed_index_and_search(be, dist.barrier, all_gather, world, rank, k, t, len(ref), block, maxk)
+        # the product loop: commet_dist_* in the library, torch.distributed only behind its two callbacks
+        d = commet_b200.Dist(ctx, world, rank, k, dist.barrier, all_gather)
+        info = d.index_and_search(t, idx, len(ref), [q], [tags.data_ptr()], block=block, maxk=maxk)
+        counters[0], counters[1] = info["shared"][0], info["searched"][0]
+        info["plan"] = [info["last_chunk"]]
         ctx.sync()
         filt = ctx.filter_download(k)
         dist.barrier()
-        be.disconnect()
+        d.close()
         np.save(Path(out_dir) / f"tags{rank}.npy", tags.cpu().numpy().view(np.uint8)[:nq // 8 + 1])
         np.save(Path(out_dir) / f"meta{rank}.npy", np.array([info["chunks"], info["indexed_here"], int(counters[0]), int(counters[1]),
-                                                            idx.n_reads]))
+                                                            idx.n_reads, info["plan"][-1][0], info["plan"][-1][1]]))
         np.save(Path(out_dir) / f"filt{rank}.npy", filt)
         ctx.close()
     finally:
@@ -144,13 +146,16 @@ def test_sharded_index_merge_search_two_gpus(tmp_path, k, t, maxk, seed):
 
 
 @pytest.mark.skipif(_n_gpus() < 1, reason="needs a GPU")
-@pytest.mark.parametrize("k,t,maxk,block,seed", [(16, 2, None, 64, 1), (20, 2, 60000, 100, 2), (29, 2, 90000, 7, 3)])
-def test_distributed_reference_set_two_ranks(tmp_path, k, t, maxk, block, seed):
-    """Two ranks (two GPUs when the box has them, else both on one GPU), each holding only its block-cyclic shard of
-    the reference set, uploaded with commet_reads_upload_async: global chunk plan from exchanged k-mer counts,
-    one-kernel merge over IPC-mapped filters, tags of the single-process oracle."""
+@pytest.mark.parametrize("world,k,t,maxk,block,seed", [(2, 16, 2, None, 64, 1), (2, 20, 2, 60000, 100, 2), (2, 29, 2, 90000, 7, 3),
+                                                       (3, 20, 2, 60000, 33, 4), (4, 20, 1, 50000, 50, 5), (4, 29, 2, 90000, 16, 6),
+                                                       (8, 16, 2, None, 64, 7), (8, 20, 2, 60000, 25, 8)])
+def test_distributed_reference_set_ranks(tmp_path, world, k, t, maxk, block, seed):
+    """2, 3, 4 and 8 ranks (one GPU each while the box has them, else sharing GPUs: the IPC mapping is per process), each
+    holding only its block-cyclic shard of the reference set, uploaded with commet_reads_upload_async: global chunk
+    plan from exchanged k-mer counts, one-kernel merge k_merge_peers<world> over IPC-mapped filters, tags of the
+    single-process oracle; the merged filter of the last chunk is the same on every rank and equal to the oracle's
+    filter of that chunk."""
     import torch.multiprocessing as mp
-    world = 2
     mp.spawn(_worker_distributed, args=(world, _free_port(), k, t, maxk, seed, block, min(_n_gpus(), world), str(tmp_path)),
              nprocs=world, join=True)
     rng = np.random.default_rng(seed)
@@ -160,12 +165,50 @@ def test_distributed_reference_set_two_ranks(tmp_path, k, t, maxk, block, seed):
     indexed = held = 0
     for r in range(world):
         tags = np.load(tmp_path / f"tags{r}.npy")
-        chunks, indexed_here, shared, searched, n_local = np.load(tmp_path / f"meta{r}.npy").tolist()
+        chunks, indexed_here, shared, searched, n_local, c0, c1 = np.load(tmp_path / f"meta{r}.npy").tolist()
         assert np.array_equal(tags, oracle.tags_to_bv(e_tags[r])), f"rank {r}: tags differ from the oracle"
         assert chunks == e["chunks"] and shared == e["shared"][r] and searched == e["searched"][r]
         indexed += indexed_here
         held += n_local
     assert indexed == e["indexed"] and held == len(ref)
-    assert np.array_equal(np.load(tmp_path / "filt0.npy"), np.load(tmp_path / "filt1.npy"))
+    f0 = np.load(tmp_path / "filt0.npy")
+    for r in range(1, world):
+        assert np.array_equal(f0, np.load(tmp_path / f"filt{r}.npy")), f"rank {r}: merged filter differs from rank 0's"
+    # the single-rank filter of the last chunk (reads [c0, c1) of the global stream), built by the oracle
+    bases, offs = H.to_stream(ref)
+    offs = np.asarray(offs, dtype=np.uint64)
+    exp = np.zeros(oracle.filter_bytes(k), dtype=np.uint8)
+    sub = offs[c0:c1 + 1]
+    oracle.index_chunk(exp, k, np.asarray(bases)[int(sub[0]):int(sub[-1])], (sub - sub[0]).astype(np.uint64), 0, 1 << 62)
+    assert np.array_equal(f0, exp)
+    if maxk:
+        assert e["chunks"] >= 2
+
+
+@pytest.mark.skipif(_n_gpus() < 1, reason="needs a GPU")
+@pytest.mark.parametrize("world,k,t,maxk,block,seed", [(2, 16, 2, None, 64, 11), (2, 20, 2, 60000, 100, 12), (3, 29, 2, 90000, 7, 13),
+                                                       (4, 20, 0, 50000, 33, 14), (8, 18, 3, 40000, 16, 15), (5, 3, 1, None, 9, 16)])
+def test_group_of_one_process_equals_the_oracle(monkeypatch, world, k, t, maxk, block, seed):
+    """commet_group_index_and_search: a thread per device (the ranks share GPUs when the box has fewer), host buffers in,
+    tag vectors out -- the signature of commet_index_and_search.  Several query sets of different sizes (slices cut at
+    multiples of 32 reads, sets smaller than that land on the last rank), chunk boundaries inside blocks."""
+    import commet_b200
+    monkeypatch.setenv("COMMET_B200_DIST_BLOCK", str(block))
+    rng = np.random.default_rng(seed)
+    ref = H.make_ref_set(rng, 3000, max(1, k - 5), 120, p_N=0.01)
+    queries = [H.make_query_set(rng, ref, n, max(1, k - 5), 120, p_N=0.01) for n in (1500, 17, 333, 64)]
+    e_tags, e = oracle.index_and_search(k, t, H.to_stream(ref), [H.to_stream(q) for q in queries], maxk)
+    n_dev = _n_gpus()
+    g = commet_b200.Group([r % n_dev for r in range(world)])
+    try:
+        for _ in range(2):                       # the group's contexts are reused by the next call
+            tags, info = g.index_and_search(k, t, H.to_stream(ref), [H.to_stream(q) for q in queries], maxk)
+            for s in range(len(queries)):
+                assert np.array_equal(tags[s], oracle.tags_to_bv(e_tags[s])), (s, world)
+            assert info["chunks"] == e["chunks"] and info["indexed"] == e["indexed"]
+            assert info["shared"] == e["shared"] and info["searched"] == e["searched"]
+            assert info["gpus"] == world
+    finally:
+        g.close()
     if maxk:
         assert e["chunks"] >= 2

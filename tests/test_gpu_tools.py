@@ -280,6 +280,38 @@ def test_more_than_thirty_search_sets_in_one_invocation(bin_dir, tmp_path):
 
 
 @needs_ref
+@pytest.mark.parametrize("devices,full", [("0,0", False), ("0,0,0", True), ("0,0,0,0", False)])
+def test_index_and_search_tool_over_several_ranks(bin_dir, tmp_path, devices, full):
+    """COMMET_B200_DEVICES / COMMET_B200_GPUS: the drop-in tool deals the index set over the GPUs (commet_group_*); files
+    and logs are those of the reference binary, also for the three passes of -f"""
+    import os
+    rng = np.random.default_rng(500 + len(devices))
+    ref_files = [H.make_ref_set(rng, 900, 40, 110, p_N=0.01) for _ in range(2)]
+    all_ref = [r for f in ref_files for r in f]
+    (tmp_path / "index.txt").write_text("R:" + ";".join(_write_set(rng, tmp_path, "idx", ref_files, with_bv=True)) + "\n")
+    lines = []
+    for s in range(1 if full else 3):
+        files = [H.make_query_set(rng, all_ref, int(rng.integers(40, 700)), 40, 110, p_N=0.01) for _ in range(2)]
+        lines.append(f"Q{s}:" + ";".join(_write_set(rng, tmp_path, f"q{s}", files, with_bv=bool(s % 2))))
+    (tmp_path / "query.txt").write_text("\n".join(lines) + "\n")
+    outs = {}
+    for who, tool, env in (("ref", oracle.REF_DIR / "index_and_search", {}), ("gpu", bin_dir / "index_and_search",
+                                                                           {"COMMET_B200_DEVICES": devices, "COMMET_B200_DIST_BLOCK": "50"})):
+        out = tmp_path / who
+        r = subprocess.run([str(tool), "-i", str(tmp_path / "index.txt"), "-s", str(tmp_path / "query.txt"), "-o", str(out),
+                            "-l", str(out), "-k", "16", "-t", "2", *(["-f"] if full else [])], capture_output=True, text=True,
+                           env={**os.environ, **env})
+        assert r.returncode == 0, (who, r.stderr)
+        outs[who] = out
+    a = {p.name: p.read_bytes() for p in outs["ref"].glob("*.bv")}
+    b = {p.name: p.read_bytes() for p in outs["gpu"].glob("*.bv")}
+    assert a == b and len(a) >= 2
+    pat = re.compile(r"\[indexed \d+, searched \d+, shared \d+\](\n[0-9.eE+-]+%)?")
+    for lg in outs["ref"].glob("*.log"):
+        assert pat.search(lg.read_text()).group(0) == pat.search((outs["gpu"] / lg.name).read_text()).group(0), lg.name
+
+
+@needs_ref
 @pytest.mark.parametrize("seed", range(20))
 def test_filter_reads_vs_reference_binary(bin_dir, tmp_path, seed):
     rng = np.random.default_rng(4000 + seed)
