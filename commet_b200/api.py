@@ -95,10 +95,13 @@ _SIGS = {
                                             C.c_int64, C.c_void_p, C.c_void_p]),
     "commet_filter_reads_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_float,
                                           C.c_int64, C.c_void_p, C.c_void_p]),
+    "commet_reads_from_device_filtered": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64,
+                                                    C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "commet_bvop": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "commet_bv_popcount": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, _u64p]),
     "commet_bvop_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "commet_bv_popcount_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, _u64p]),
+    "commet_bv_popcount_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "commet_bench_random_sectors": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
 }
 
@@ -550,6 +553,16 @@ class Context:
                                                   C.c_float(min_shannon), max_reads, _ptr(d_bv), _ptr(cnt)))
         return dict(rm_length=int(cnt[0]), rm_N=int(cnt[1]), rm_shannon=int(cnt[2]), selected=int(cnt[3]))
 
+    def stage_device_filtered(self, d_bases: int, d_offs: int, n_reads: int, n_bases: int, d_bv: int, min_len=0, max_N=-1,
+                              min_shannon=0.0, max_reads=-1):
+        """staging and selection fused: (staged stream, counters) from one pass over the device-resident ASCII bases"""
+        cnt = np.zeros(4, dtype=np.uint64)
+        h = C.c_void_p()
+        self._ck(self.lib.commet_reads_from_device_filtered(self.handle, _ptr(d_bases), _ptr(d_offs), n_reads, n_bases, min_len,
+                                                            max_N, C.c_float(min_shannon), max_reads, _ptr(d_bv), _ptr(cnt),
+                                                            C.byref(h)))
+        return ReadStream(self, h.value), dict(rm_length=int(cnt[0]), rm_N=int(cnt[1]), rm_shannon=int(cnt[2]), selected=int(cnt[3]))
+
     # -- stage 4 --------------------------------------------------------------
     def bvop(self, op: int, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:
         """BooleanVector::full_and/or/and_not/not over all payload bytes."""
@@ -576,6 +589,15 @@ class Context:
         ones = C.c_uint64(0)
         self._ck(self.lib.commet_bv_popcount_dev(self.handle, _ptr(d_bv), n_bits, C.byref(ones)))
         return int(ones.value)
+
+    def nb_one_device_batch(self, d_bvs, n_bits) -> list:
+        """nb_one of several device-resident vectors: one read-back and one synchronisation for all"""
+        n = len(d_bvs)
+        ptrs = (C.c_void_p * max(n, 1))(*d_bvs)
+        bits = np.asarray(n_bits, dtype=np.uint64)
+        ones = np.zeros(max(n, 1), dtype=np.uint64)
+        self._ck(self.lib.commet_bv_popcount_batch_dev(self.handle, C.cast(ptrs, C.c_void_p), _ptr(bits), n, _ptr(ones)))
+        return [int(x) for x in ones[:n]]
 
     # -- measurement ------------------------------------------------------------
     def random_sector_rate(self, nbytes: int, n_ops: int, atomic: bool = False) -> float:

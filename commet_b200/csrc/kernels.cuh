@@ -631,10 +631,10 @@ __host__ __device__ inline size_t scatter2_smem_bytes(int tw, int n_bins)
 // fill[b]: records reserved for region b so far; table[b * max_q + q]: 1 + id of the q-th slab of region b
 // (0: not opened yet); n_slabs: slabs handed out.  All zeroed by the host before the launch.
 template <int TW>
-__global__ void __launch_bounds__(kS2Threads, (TW <= 64 ? 3 : 2))
+__global__ void __launch_bounds__(kS2Threads, (TW <= 96 ? 3 : 2))
 k_bin_scatter2(const uint4 *__restrict__ planes, uint64_t b0, uint64_t b1, int k, int n_bins,
                uint32_t *__restrict__ fill, uint32_t *__restrict__ table, uint32_t max_q,
-               uint32_t *__restrict__ n_slabs, uint32_t *__restrict__ recs)
+               uint32_t *__restrict__ n_slabs, uint32_t max_slabs, uint32_t *__restrict__ recs)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw);
@@ -700,8 +700,18 @@ k_bin_scatter2(const uint4 *__restrict__ planes, uint64_t b0, uint64_t b1, int k
                     uint32_t *row = table + (size_t)tid * max_q;
                     uint32_t ida = 0, idb = 0;
                     // open the slabs whose first place this run covers -- before waiting for anything
-                    if ((g & (kSlabRecs - 1)) == 0) { ida = atomicAdd(n_slabs, 1u) + 1; st_release_u32(row + qa, ida); }
-                    if (qb != qa) { idb = atomicAdd(n_slabs, 1u) + 1; st_release_u32(row + qb, idb); }
+                    // (a pool that is too small for the records -- the host sizes it from an upper bound -- is reported through
+                    // n_slabs[1]; the records then land in slab 0: in bounds, and the call fails)
+                    if ((g & (kSlabRecs - 1)) == 0) {
+                        ida = atomicAdd(n_slabs, 1u) + 1;
+                        if (ida > max_slabs) { n_slabs[1] = 1; ida = 1; }
+                        st_release_u32(row + qa, ida);
+                    }
+                    if (qb != qa) {
+                        idb = atomicAdd(n_slabs, 1u) + 1;
+                        if (idb > max_slabs) { n_slabs[1] = 1; idb = 1; }
+                        st_release_u32(row + qb, idb);
+                    }
                     while (ida == 0) ida = ld_acquire_u32(row + qa);
                     sid0[tid] = ida - 1;
                     sid1[tid] = qb != qa ? idb - 1 : ida - 1;
@@ -721,14 +731,21 @@ k_bin_scatter2(const uint4 *__restrict__ planes, uint64_t b0, uint64_t b1, int k
         }
         __syncthreads();
         // ---- copy-out: a warp per region run ----------------------------------------------------------------
+        // (runs are ~100 records: the per-run overhead matters as much as the loop body -- no unrolling, one pointer
+        // per slab; a run continues in a second slab once in 2^kSlabLog2 records)
         for (int b = (int)warp; b < n_bins; b += kWarps) {
             const uint32_t c = cnt[b];
             if (c == 0) continue;
-            const uint32_t s = start[b], g = gpos[b], qa = g >> kSlabLog2;
-            const size_t base0 = (size_t)sid0[b] << kSlabLog2, base1 = (size_t)sid1[b] << kSlabLog2;
-            for (uint32_t i = lane; i < c; i += 32) {
-                const uint32_t v = g + i;
-                st_stream_u32(recs + (((v >> kSlabLog2) == qa ? base0 : base1) + (v & (kSlabRecs - 1))), stage[s + i], pol);
+            const uint32_t off = gpos[b] & (kSlabRecs - 1);
+            const uint32_t n0 = min(c, kSlabRecs - off);                 // records that fit in the first slab
+            const uint32_t *src = stage + start[b];
+            uint32_t *dst = recs + (((size_t)sid0[b] << kSlabLog2) + off);
+#pragma unroll 1
+            for (uint32_t i = lane; i < n0; i += 32) st_stream_u32(dst + i, src[i], pol);
+            if (n0 < c) {
+                dst = recs + ((size_t)sid1[b] << kSlabLog2) - n0;
+#pragma unroll 1
+                for (uint32_t i = n0 + lane; i < c; i += 32) st_stream_u32(dst + i, src[i], pol);
             }
         }
         __syncthreads();                   // stage / cnt / planes are rewritten by the next tile
@@ -835,6 +852,134 @@ k_bin_apply2(uint32_t *__restrict__ filter, const uint32_t *__restrict__ recs, c
         __syncthreads();
         tl = s_next;
         bin = s_bin;
+    }
+}
+
+// k_bin_apply2 with the record tiles brought in by the bulk-copy engine (cp.async.bulk, completion on an mbarrier)
+// into a ring of shared-memory stages instead of by LDG.  In k_bin_apply2 a tile's loads are issued by the same LSU
+// pipe that is draining thousands of queued RED lane-operations: the loads wait behind them, the warps wait for
+// the loads (ncu: 43 long-scoreboard + 35 barrier stall cycles per issue, 150 G RED/s against a 218 G/s ceiling).
+// Here one thread claims tiles and issues one bulk copy per tile (and one bulk L2 prefetch for the slice of the
+// next region the tile is responsible for); all threads only read records from shared memory and issue REDs.
+// A stage is released through an "empty" mbarrier (256 arrivals), so warps drift apart by up to STAGES tiles
+// instead of meeting at a block barrier per tile.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(bytes) : "memory");
+}
+
+template <int TILE, int STAGES, bool PREFETCH>
+__global__ void __launch_bounds__(256)
+k_bin_apply3(uint32_t *__restrict__ filter, const uint32_t *__restrict__ recs, const uint32_t *__restrict__ fill,
+             const uint32_t *__restrict__ tbase, const uint32_t *__restrict__ table, uint32_t max_q, int n_bins,
+             unsigned long long *__restrict__ tile_counter)
+{
+    constexpr int U = TILE / (256 * 4);                    // 16-byte vectors per thread per tile
+    static_assert((kSlabRecs % TILE) == 0, "a tile must not span two slabs");
+    extern __shared__ __align__(16) unsigned char smem_raw[];        // STAGES tiles of TILE records (bulk copies need 16-byte alignment)
+    __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
+    __shared__ uint32_t s_bin[STAGES], s_n[STAGES];
+    __shared__ uint32_t sbase[kMaxBins + 1];
+    __shared__ uint32_t sfill[kMaxBins];
+    for (int i = threadIdx.x; i <= n_bins; i += blockDim.x) sbase[i] = tbase[i];
+    for (int i = threadIdx.x; i < n_bins; i += blockDim.x) sfill[i] = fill[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t n_tiles = sbase[n_bins];
+    const uint64_t pol = ld_policy_evict_first();
+    // thread 0: claim the next tile and start its copy into stage s (or mark the stage as the end of the work)
+    auto produce = [&](int s) {
+        const unsigned long long tl64 = atomicAdd(tile_counter, 1ull);
+        if (tl64 >= n_tiles) {
+            s_n[s] = 0;
+            mbar_arrive(&full[s]);
+            return;
+        }
+        const uint32_t tl = (uint32_t)tl64;
+        int lo = 0, hi = n_bins - 1;                       // last region with tbase <= tl (regions without tiles are skipped)
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (sbase[mid] <= tl) lo = mid; else hi = mid - 1;
+        }
+        const int bin = lo;
+        const uint32_t lt = tl - sbase[bin], v0 = lt * TILE;
+        const uint32_t slab = table[(size_t)bin * max_q + (v0 >> kSlabLog2)] - 1u;
+        s_bin[s] = (uint32_t)bin;
+        s_n[s] = min((uint32_t)TILE, sfill[bin] - v0);
+        mbar_arrive_expect_tx(&full[s], TILE * 4);
+        bulk_g2s(smem_raw + (size_t)s * TILE * 4, recs + (((size_t)slab << kSlabLog2) + (v0 & (kSlabRecs - 1))), TILE * 4, &full[s], pol);
+        if (PREFETCH && bin + 1 < n_bins && sfill[bin + 1] >= (1u << (kRegionLog2 - 8))) {
+            // the tiles of region b pull region b+1 into L2 ahead of its first RED, each tile an equal slice
+            const uint32_t n_t = sbase[bin + 1] - sbase[bin];
+            const uint32_t lines = 1u << (kRegionLog2 - 7);
+            const uint32_t l0 = (uint32_t)((uint64_t)lines * lt / n_t), l1 = (uint32_t)((uint64_t)lines * (lt + 1) / n_t);
+            if (l1 > l0)
+                bulk_prefetch_l2(reinterpret_cast<const char *>(filter) + ((uint64_t)(bin + 1) << kRegionLog2) + ((uint64_t)l0 << 7), (l1 - l0) << 7);
+        }
+    };
+    if (threadIdx.x == 0)
+        for (int s = 0; s < STAGES; s++) produce(s);
+    for (uint32_t it = 0;; it++) {
+        const int s = (int)(it % STAGES);
+        const uint32_t round = it / STAGES;
+        mbar_wait(&full[s], round & 1u);
+        const uint32_t n_here = s_n[s];
+        if (n_here == 0) break;                            // tiles are claimed in order: every later stage is empty too
+        uint32_t *region = filter + ((uint64_t)s_bin[s] << (kRegionLog2 - 2));
+        const uint4 *src = reinterpret_cast<const uint4 *>(smem_raw + (size_t)s * TILE * 4);
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) v[u] = src[u * 256 + threadIdx.x];
+        mbar_arrive(&empty[s]);                            // this thread's records are in registers
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t e = (u * 256 + threadIdx.x) * 4;
+            const uint32_t r[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                if (e + x < n_here) {
+                    const uint32_t key_low = r[x] & kRecMask;
+                    atomicOr(region + (key_low >> 3), key_bit((uint64_t)key_low, (int)(r[x] >> kRecKeyBits)));
+                }
+            }
+        }
+        if (threadIdx.x == 0) {
+            mbar_wait(&empty[s], round & 1u);              // every thread has taken its records out of the stage
+            produce(s);
+        }
     }
 }
 
@@ -1449,40 +1594,46 @@ k_filter(const uint4 *__restrict__ planes, const uint64_t *__restrict__ offs, ui
     if (threadIdx.x < 4) block_totals[4 * (uint64_t)blockIdx.x + threadIdx.x] = tot[threadIdx.x];
 }
 
-// The same selection FUSED INTO THE READ-STAGING PASS (north_star stage 3): the ASCII bases are read once
-// with 16-byte vector loads and nothing but the selection bits is written -- no bit-planes.  A group of 8
-// lanes owns one read (8 x 16 B = 128 B per step, the common read length), so a warp works on 4 reads at a
-// time and on 128 consecutive reads (4 words of the bit vector) in all; a block covers the same 1024 reads
-// as k_filter and produces the same outputs (bits, class bytes, block totals, undecided records).
-// `bases` must be 16-byte aligned and readable up to the next multiple of 16 bytes.
-__device__ __forceinline__ unsigned long long count_acgt16(uint4 v, uint32_t valid)   // valid: bit i = byte i counts
+// The staging pass and the selection in ONE kernel (north_star stage 3): every ASCII base is read once (two 16-byte
+// vector loads per 32-base word); its H/L/V bits are computed as k_encode does; the per-read A/C/G/T/other counts
+// are popcounts of those bits restricted to the read's range -- no per-byte counting at all; with PLANES the bits
+// are also stored as the stream's bit-planes, so a set that is filtered AND indexed is read from HBM once.
+// A group of 4 lanes owns a read and sweeps it 128 bytes at a time (lane g takes the 32-byte words w0+g, w0+g+4, ...
+// of the stream, aligned to the stream, not to the read); a word is STORED by the read that contains its first byte
+// (each word has exactly one such read), the words at the two ends of a read are also computed by its neighbours.
+// A warp works on 8 reads at a time and on 128 consecutive reads (4 words of the bit vector) in all; a block covers
+// the same 1024 reads as k_filter and produces the same outputs (bits, class bytes, block totals, undecided records).
+// `bases`: 16-byte aligned, readable up to `readable` bytes (a multiple of 16 >= the last offset = n_bases).
+__device__ __forceinline__ void encode32(uint4 q0, uint4 q1, uint32_t &H, uint32_t &L, uint32_t &V)
 {
-    uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    unsigned long long acc = 0;
+    const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    H = L = V = 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        uint32_t m = (valid >> (4 * i)) & 0xFu;
-        uint32_t bm = (m & 1u) | ((m & 2u) << 7) | ((m & 4u) << 14) | ((m & 8u) << 21);     // 0x01 per valid byte
-        uint32_t x = w[i] | 0x20202020u;                                                    // fold case
-        acc += (unsigned long long)__popc(__vcmpeq4(x, 0x61616161u) & bm)
-             | ((unsigned long long)__popc(__vcmpeq4(x, 0x63636363u) & bm) << 16)
-             | ((unsigned long long)__popc(__vcmpeq4(x, 0x67676767u) & bm) << 32)
-             | ((unsigned long long)__popc(__vcmpeq4(x, 0x74747474u) & bm) << 48);
+    for (int j = 0; j < 8; j++) {
+        const uint32_t c = w[j];
+        const uint32_t h = (c >> 2) & 0x01010101u;                 // A,C ->0  G,T ->1
+        const uint32_t l = ((c >> 1) ^ (c >> 2)) & 0x01010101u;    // A,G ->0  C,T ->1
+        const uint32_t x = c | 0x20202020u;                         // fold case
+        const uint32_t v = (__vcmpeq4(x, 0x61616161u) | __vcmpeq4(x, 0x63636363u) |
+                            __vcmpeq4(x, 0x67676767u) | __vcmpeq4(x, 0x74747474u)) & 0x01010101u;
+        H |= gather4(h) << (4 * j);
+        L |= gather4(l) << (4 * j);
+        V |= gather4(v) << (4 * j);
     }
-    return acc;
 }
 
+template <bool PLANES>
 __global__ void __launch_bounds__(256, 4)
-k_filter_ascii(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offs, uint64_t n_reads,
-               FilterParams fp, uint32_t *__restrict__ bv, uint64_t n_bv_words, uint8_t *__restrict__ classes,
-               unsigned int *__restrict__ block_totals, BorderRec *__restrict__ border,
+k_stage_filter(const uint8_t *__restrict__ bases, uint64_t readable, uint64_t n_bases, const uint64_t *__restrict__ offs, uint64_t n_reads,
+               uint4 *__restrict__ planes, FilterParams fp, uint32_t *__restrict__ bv, uint64_t n_bv_words,
+               uint8_t *__restrict__ classes, unsigned int *__restrict__ block_totals, BorderRec *__restrict__ border,
                unsigned int border_cap, unsigned int *__restrict__ n_border)
 {
     __shared__ unsigned int tot[4];
     if (threadIdx.x < 4) tot[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, gl = lane & 7;
-    const uint32_t gmask = 0xFFu << (8 * grp);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 2, gl = lane & 3;
+    const uint32_t gmask = 0xFu << (4 * grp);
     const uint64_t r0 = (uint64_t)blockIdx.x * kFilterBlock + (uint64_t)warp * 128;
     unsigned int wtot[4] = {0, 0, 0, 0};                      // rm_len, rm_N, rm_shannon, selected (lane 0)
     // lane i owns read rbase + i: its offsets (coalesced, fetched one word of the bit vector ahead), its class, its bit
@@ -1494,55 +1645,44 @@ k_filter_ascii(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ o
         nx_o = nx_e = 0;
         if (j < 3 && my_r + 32 < n_reads) { nx_o = offs[my_r + 32]; nx_e = offs[my_r + 33]; }
         unsigned int mine[4] = {0, 0, 0, 0};
-        // counting: 4 double steps; in each a group of 8 lanes sweeps two reads, 128 bytes at a time, with the first
-        // 16-byte load of both reads in flight before either is counted
-        for (int it2 = 0; it2 < 4; it2++) {
-            uint64_t o[2], e[2], c0[2];
-            bool act[2];
-            uint4 v[2];
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int src = 8 * it2 + 4 * u + grp;
-                o[u] = __shfl_sync(0xffffffffu, my_o, src);
-                e[u] = __shfl_sync(0xffffffffu, my_e, src);
-                act[u] = (long long)(e[u] - o[u]) >= fp.min_len && e[u] > o[u];      // uniform inside the group only
-                c0[u] = (o[u] & ~15ull) + 16 * gl;
-                v[u] = make_uint4(0u, 0u, 0u, 0u);
-                if (act[u] && c0[u] < e[u]) v[u] = ld_nc_u4(reinterpret_cast<const uint4 *>(bases + c0[u]));
+        for (int st = 0; st < 4; st++) {                       // 8 reads per step: read 8*st + grp of the 32
+            const int src = 8 * st + (int)grp;
+            const uint64_t o = __shfl_sync(0xffffffffu, my_o, src), e = __shfl_sync(0xffffffffu, my_e, src);
+            unsigned int cnt[4] = {0, 0, 0, 0};
+            // without planes a read that fails the length test is not read at all (filter_reads.cpp:189 comes first)
+            if (e > o && (PLANES || (long long)(e - o) >= fp.min_len)) {
+                for (uint64_t w = (o >> 5) + gl; (w << 5) < e; w += 4) {
+                    const uint64_t c = w << 5;
+                    const uint4 q0 = ld_nc_u4(reinterpret_cast<const uint4 *>(bases + c));
+                    uint4 q1 = make_uint4(0u, 0u, 0u, 0u);
+                    if (c + 16 < readable) q1 = ld_nc_u4(reinterpret_cast<const uint4 *>(bases + c + 16));
+                    uint32_t H, L, V;
+                    encode32(q0, q1, H, L, V);
+                    uint32_t m = ~0u;
+                    if (c < o) m &= ~0u << (o - c);
+                    if (c + 32 > e) m &= ~0u >> (c + 32 - e);
+                    if (PLANES && c >= o) {
+                        // nothing is valid past the end of the stream, whatever bytes lie there
+                        planes[w] = make_uint4(H, L, c + 32 > n_bases ? (V & (~0u >> (c + 32 - n_bases))) : V, 0u);
+                    }
+                    const uint32_t vm = V & m;
+                    cnt[0] += __popc(~H & ~L & vm);
+                    cnt[1] += __popc(~H & L & vm);
+                    cnt[2] += __popc(H & ~L & vm);
+                    cnt[3] += __popc(H & L & vm);
+                }
             }
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                unsigned int cnt[4] = {0, 0, 0, 0};
-                if (act[u]) {
-                    unsigned long long acc = 0;                      // four 16-bit counters, flushed before overflow
-                    int pending = 0;
-                    for (uint64_t c = c0[u]; c < e[u]; c += 128) {
-                        uint4 x = c == c0[u] ? v[u] : ld_nc_u4(reinterpret_cast<const uint4 *>(bases + c));
-                        uint32_t valid = 0xFFFFu;
-                        if (c < o[u]) valid &= 0xFFFFu << (o[u] - c);
-                        if (c + 16 > e[u]) valid &= 0xFFFFu >> (c + 16 - e[u]);
-                        acc += count_acgt16(x, valid);
-                        if (++pending == 4000) {
-                            for (int q = 0; q < 4; q++) cnt[q] += (unsigned int)((acc >> (16 * q)) & 0xFFFFu);
-                            acc = 0;
-                            pending = 0;
-                        }
-                    }
+            for (int q = 0; q < 4; q++) {                       // the reduction names the group's own lanes only
+                cnt[q] += __shfl_xor_sync(gmask, cnt[q], 1);
+                cnt[q] += __shfl_xor_sync(gmask, cnt[q], 2);
+            }
+            __syncwarp();
+            // hand the counts of read 8*st + g to its owner lane
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {                    // the reduction names the group's own lanes only
-                        cnt[q] += (unsigned int)((acc >> (16 * q)) & 0xFFFFu);
-                        cnt[q] += __shfl_xor_sync(gmask, cnt[q], 1);
-                        cnt[q] += __shfl_xor_sync(gmask, cnt[q], 2);
-                        cnt[q] += __shfl_xor_sync(gmask, cnt[q], 4);
-                    }
-                }
-                __syncwarp();
-                // hand the counts of read 8*it2 + 4*u + g to its owner lane
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    unsigned int t = __shfl_sync(0xffffffffu, cnt[q], 8 * (lane & 3));
-                    if ((int)(lane >> 2) == 2 * it2 + u) mine[q] = t;
-                }
+            for (int q = 0; q < 4; q++) {
+                const unsigned int t = __shfl_sync(0xffffffffu, cnt[q], 4 * (lane & 7));
+                if ((int)(lane >> 3) == st) mine[q] = t;
             }
         }
         // classification: one read per lane (the Shannon term is the expensive part; all 32 lanes work)
@@ -1555,7 +1695,7 @@ k_filter_ascii(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ o
                 cnt[4] = (unsigned int)len - (cnt[0] + cnt[1] + cnt[2] + cnt[3]);
                 cls = classify_counts(len, cnt, fp);
                 if (cls == 4) {
-                    unsigned int slot = atomicAdd(n_border, 1u);
+                    const unsigned int slot = atomicAdd(n_border, 1u);
                     if (slot < border_cap) {
                         BorderRec br;
                         br.read = my_r;
@@ -1808,6 +1948,161 @@ k_merge_peers(PeerFilters pf, int me, uint64_t v0, uint64_t v1)
             if (p == me) pf.f[p][i] = acc;
             else st_peer_u4(pf.f[p] + i, acc);
         }
+    }
+}
+
+// ------------------------------- multi-GPU: owner-applied insert + slice all-gather ----
+// Merging whole partial filters moves 2 (G-1)/G F bytes per GPU and direction (reduce-scatter + all-gather of the OR).
+// The reduce-scatter half is avoidable: what a rank contributes to a slice of the filter is not a dense slice but
+// the RECORDS of its reads that fall into it -- (G-1)/G of 16 bytes per k-mer instead of (G-1)/G F.  So the filter's
+// regions are dealt to the ranks (rank r owns regions [r n_bins/G, (r+1) n_bins/G) = slice r of the filter); every rank
+// scatters the records of ITS reads into its own slabs, as on one GPU; then every owner applies the records of ITS
+// regions from ALL ranks' slabs -- the record tiles of the peers are read straight out of their memory over NVLink by
+// the apply kernel itself (no copy pass, the link transfer overlaps the RED.OR) -- and sweeps only its own F/G bytes
+// through L2; finally every rank pulls the finished slices of the others (k_gather_slices).
+struct PeerInsert {
+    const uint32_t *recs[kMaxPeers];      // slab pools
+    const uint32_t *fill[kMaxPeers];      // records per region
+    const uint32_t *table[kMaxPeers];     // slab tables
+    uint32_t max_q[kMaxPeers];            // row length of each table
+};
+struct OwnerTile {
+    const uint32_t *src;                  // the tile's records (peer or local memory)
+    uint32_t n;                           // records in the tile; bit 31: the records are in peer memory
+    uint32_t bin;                         // region (global index)
+    uint32_t rt, rn;                      // tile index inside the region, tiles of the region (all sources)
+    uint32_t next_fill;                   // records of the next owned region (decides whether it is prefetched)
+    uint32_t pad;
+};
+
+// pairs e = i * world + s (owned region i, source rank s), region-major: fills[e], tbase[e] (first tile), tbase[n_pairs]
+template <int TILE>
+__global__ void __launch_bounds__(512)
+k_owner_fills(PeerInsert pi, int world, int b_first, int n_pairs, uint32_t *__restrict__ fills, uint32_t *__restrict__ tbase,
+              unsigned long long *__restrict__ tile_counter)
+{
+    __shared__ uint32_t wsum[16];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t f = 0;
+    if ((int)tid < n_pairs) f = pi.fill[tid % world][b_first + tid / world];
+    const uint32_t c = (f + TILE - 1) / TILE;
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t off = 0;
+    for (uint32_t w = 0; w < warp; w++) off += wsum[w];
+    if ((int)tid < n_pairs) {
+        fills[tid] = f;
+        tbase[tid] = off + incl - c;
+        if ((int)tid == n_pairs - 1) tbase[n_pairs] = off + incl;
+    }
+    if (tid == 0) *tile_counter = 0;
+}
+
+// one thread per tile: where its records are (the slab id is looked up in the source's table, over NVLink for a peer)
+template <int TILE>
+__global__ void __launch_bounds__(256)
+k_owner_tiles(PeerInsert pi, int world, int me, int b_first, int n_pairs, const uint32_t *__restrict__ fills,
+              const uint32_t *__restrict__ tbase, OwnerTile *__restrict__ tiles)
+{
+    const uint32_t n_tiles = tbase[n_pairs];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
+        int lo = 0, hi = n_pairs - 1;                      // last pair with tbase <= t (pairs without tiles are skipped)
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (tbase[mid] <= t) lo = mid; else hi = mid - 1;
+        }
+        const int e = lo, i = e / world, s = e % world, bin = b_first + i;
+        const uint32_t lt = t - tbase[e], v0 = lt * TILE;
+        const uint32_t slab = pi.table[s][(size_t)bin * pi.max_q[s] + (v0 >> kSlabLog2)] - 1u;
+        OwnerTile o;
+        o.src = pi.recs[s] + (((size_t)slab << kSlabLog2) + (v0 & (kSlabRecs - 1)));
+        o.n = min((uint32_t)TILE, fills[e] - v0) | (s != me ? 0x80000000u : 0u);
+        o.bin = (uint32_t)bin;
+        o.rt = t - tbase[i * world];
+        o.rn = tbase[(i + 1) * world] - tbase[i * world];
+        uint32_t nf = 0;
+        if ((i + 1) * world < n_pairs)
+            for (int q = 0; q < world; q++) nf += fills[(i + 1) * world + q];
+        o.next_fill = nf;
+        o.pad = 0;
+        tiles[t] = o;
+    }
+}
+
+template <int TILE, bool PREFETCH>
+__global__ void __launch_bounds__(256)
+k_owner_apply(uint32_t *__restrict__ filter, const OwnerTile *__restrict__ tiles, const uint32_t *__restrict__ tbase, int n_pairs,
+              int b_last, unsigned long long *__restrict__ tile_counter)
+{
+    constexpr int U = TILE / (256 * 4);
+    __shared__ unsigned long long s_next;
+    const uint32_t n_tiles = tbase[n_pairs];
+    const uint64_t pol = ld_policy_evict_first();
+    if (threadIdx.x == 0) s_next = atomicAdd(tile_counter, 1ull);
+    __syncthreads();
+    unsigned long long tl = s_next;
+    while (tl < n_tiles) {
+        __syncthreads();                                   // everybody holds tl: the slot may be overwritten
+        unsigned long long nxt = 0;
+        if (threadIdx.x == 0) nxt = atomicAdd(tile_counter, 1ull);      // consumed after this tile
+        const OwnerTile o = tiles[tl];
+        const uint32_t n_here = o.n & 0x7FFFFFFFu;
+        const bool remote = (o.n >> 31) != 0;
+        const uint4 *src = reinterpret_cast<const uint4 *>(o.src);
+        uint4 v[U];
+#pragma unroll
+        for (int it = 0; it < U; it++) {
+            const uint32_t e = (it * 256 + threadIdx.x) * 4;
+            v[it] = make_uint4(0u, 0u, 0u, 0u);
+            if (e < n_here) v[it] = remote ? ld_peer_u4(src + (it * 256 + threadIdx.x)) : ld_stream_u4(src + (it * 256 + threadIdx.x), pol);
+        }
+        if (PREFETCH && (int)o.bin < b_last && o.next_fill >= (1u << (kRegionLog2 - 8))) {
+            const uint32_t lines = 1u << (kRegionLog2 - 7);
+            const uint32_t l0 = (uint32_t)((uint64_t)lines * o.rt / o.rn), l1 = (uint32_t)((uint64_t)lines * (o.rt + 1) / o.rn);
+            const char *nxt_region = reinterpret_cast<const char *>(filter) + ((uint64_t)(o.bin + 1) << kRegionLog2);
+            for (uint32_t l = l0 + threadIdx.x; l < l1; l += 256)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(nxt_region + ((uint64_t)l << 7)));
+        }
+        uint32_t *region = filter + ((uint64_t)o.bin << (kRegionLog2 - 2));
+#pragma unroll
+        for (int it = 0; it < U; it++) {
+            const uint32_t e = (it * 256 + threadIdx.x) * 4;
+            const uint32_t r[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                if (e + x < n_here) {
+                    const uint32_t key_low = r[x] & kRecMask;
+                    atomicOr(region + (key_low >> 3), key_bit((uint64_t)key_low, (int)(r[x] >> kRecKeyBits)));
+                }
+            }
+        }
+        if (threadIdx.x == 0) s_next = nxt;
+        __syncthreads();
+        tl = s_next;
+    }
+}
+
+// every rank pulls the finished slices of the other owners into its own filter: G-1 peer loads in flight per thread
+template <int G>
+__global__ void __launch_bounds__(256)
+k_gather_slices(PeerFilters pf, int me, uint64_t n_slice)         // n_slice: 16-byte vectors per slice
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint4 *mine = pf.f[me];
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slice; i += stride) {
+        uint4 part[G];
+#pragma unroll
+        for (int p = 0; p < G; p++)
+            if (p != me) part[p] = ld_peer_u4(pf.f[p] + (uint64_t)p * n_slice + i);
+#pragma unroll
+        for (int p = 0; p < G; p++)
+            if (p != me) mine[(uint64_t)p * n_slice + i] = part[p];
     }
 }
 

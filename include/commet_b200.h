@@ -268,6 +268,13 @@ int commet_filter_reads_dev(commet_ctx *ctx, const uint8_t *d_bases, const uint6
                             int64_t min_len, int64_t max_N, float min_shannon, int64_t max_reads,
                             uint32_t *d_bv, uint64_t *counters);
 
+/* the staging pass and the selection in ONE pass over ASCII bases already on the device: the stream's bit-planes
+ * (as commet_reads_from_device) and the selection bits (as commet_filter_reads_dev) from a single read of the bases.
+ * Same alignment contract as commet_filter_reads_dev. */
+int commet_reads_from_device_filtered(commet_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offs, uint64_t n_reads,
+                                      uint64_t n_bases, int64_t min_len, int64_t max_N, float min_shannon,
+                                      int64_t max_reads, uint32_t *d_bv, uint64_t *counters, commet_reads **out);
+
 /* ---- stage 4: bvop ------------------------------------------------------------
  * BooleanVector::full_and/or/and_not/not (include/boolean_vector.h:418-462)
  * over ALL n_bytes = n/8+1 payload bytes (padding bits included), and nb_one
@@ -279,6 +286,8 @@ int commet_bv_popcount(commet_ctx *ctx, const uint8_t *bv, uint64_t n_bits, uint
 int commet_bvop_dev(commet_ctx *ctx, int op, const void *d_a, const void *d_b, void *d_out,
                     uint64_t n_bytes);
 int commet_bv_popcount_dev(commet_ctx *ctx, const void *d_bv, uint64_t n_bits, uint64_t *ones);
+/* nb_one of n device-resident vectors with one read-back and one synchronisation for all of them */
+int commet_bv_popcount_batch_dev(commet_ctx *ctx, const void *const *d_bvs, const uint64_t *n_bits, int n, uint64_t *ones);
 
 /* ---- measurement helpers (bench.py / profiles) ---------------------------------
  * random 32-byte-sector gather / atomic-OR ceilings over a `bytes`-sized

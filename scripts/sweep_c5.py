@@ -5,7 +5,10 @@ bandwidth-bound sweep with device-resident inputs.  GPU box only:
 
 filter_reads: SURVEY 8(d) mix -- lengths uniform in 50..150, 5 % low-complexity reads (homopolymer / dinucleotide),
 5 % of reads with 1..10 N, options -l 66 -n 2 -e 1.5.  Reads are generated on the device per batch (seeded) and
-streamed through stage (encode) + filter; a 1e9-read run is `--batches 63`.
+streamed through three paths: selection only (k_stage_filter<false>: the ASCII bases read once, bits out), staging and
+selection fused (k_stage_filter<true>: bases read once, bit-planes AND bits out), and the two-kernel path (k_encode,
+then k_filter over the planes); a 1e9-read run is `--batches 63`.  Each path is timed as a CALL (with its counter
+read-backs and synchronisations) -- the kernels alone are in the ncu launch list of the same command.
 Algorithmic bytes: 1 B/base in (ASCII) for stage+filter; bvop AND = 3 B per payload byte, popcount = 1 B.
 One batch is checked against the CPU oracle on a 200k-read prefix (bit-exact) before timing.
 """
@@ -67,13 +70,16 @@ def main():
 
     # ---- filter_reads ------------------------------------------------------------------------------------
     opts = dict(min_len=66, max_N=2, min_shannon=1.5)
-    t_stage = t_filter = t_fused = 0.0
+    t_stage = t_filter = t_fused = t_both = 0.0
     n_bases = n_reads = selected = 0
     for b in range(args.batches):
         bases, offs = make_batch(args.reads, 7000 + b, dev)
         n, nb = args.reads, int(offs[-1])
+        if bases.numel() % 16:                               # the fused kernels read whole 16-byte vectors
+            bases = torch.cat([bases, torch.zeros(16 - bases.numel() % 16, dtype=torch.uint8, device=dev)])
         d_bv = torch.zeros((n // 8 + 1 + 3) // 4, dtype=torch.int32, device=dev)
         d_bv2 = torch.zeros_like(d_bv)
+        d_bv3 = torch.zeros_like(d_bv)
         torch.cuda.synchronize()
         if b == 0:      # parity on a prefix, through the same entry points
             from oracle import oracle
@@ -87,8 +93,10 @@ def main():
             ctx.filter_reads_staged(rs, d_bv.data_ptr(), **opts)
             rs.free()
             ctx.filter_reads_device(bases.data_ptr(), offs.data_ptr(), n, d_bv2.data_ptr(), **opts)
+            rs, _ = ctx.stage_device_filtered(bases.data_ptr(), offs.data_ptr(), n, nb, d_bv3.data_ptr(), **opts)
+            rs.free()
             ctx.sync()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         with torch.cuda.stream(ext):
             ev[0].record()
         rs = ctx.stage_device(bases.data_ptr(), offs.data_ptr(), n, nb)
@@ -98,26 +106,38 @@ def main():
         with torch.cuda.stream(ext):
             ev[2].record()
         cnt_f = ctx.filter_reads_device(bases.data_ptr(), offs.data_ptr(), n, d_bv2.data_ptr(), **opts)
+        rs.free()                                              # its planes go back to the context's cache: the fused pass takes them
         with torch.cuda.stream(ext):
             ev[3].record()
+        rs3, cnt_b = ctx.stage_device_filtered(bases.data_ptr(), offs.data_ptr(), n, nb, d_bv3.data_ptr(), **opts)
+        with torch.cuda.stream(ext):
+            ev[4].record()
         ctx.sync()
         torch.cuda.synchronize()
-        assert cnt_f == cnt and torch.equal(d_bv, d_bv2), "fused and staged selections differ"
+        assert cnt_f == cnt and torch.equal(d_bv, d_bv2), "selection-only pass and staged selection differ"
+        assert cnt_b == cnt and torch.equal(d_bv, d_bv3), "fused staging+selection and staged selection differ"
         t_stage += ev[0].elapsed_time(ev[1]) * 1e-3
         t_filter += ev[1].elapsed_time(ev[2]) * 1e-3
         t_fused += ev[2].elapsed_time(ev[3]) * 1e-3
+        t_both += ev[3].elapsed_time(ev[4]) * 1e-3
         n_bases += nb
         n_reads += n
         selected += cnt["selected"]
-        rs.free()
-        del bases, offs, d_bv, d_bv2
+        rs3.free()
+        del bases, offs, d_bv, d_bv2, d_bv3
     tot = t_stage + t_filter
-    out["filter_reads_fused"] = {
+    out["filter_reads_selection_only"] = {
         "reads": n_reads, "bases": n_bases, "selected": selected, "options": "-l 66 -n 2 -e 1.5", "ms": t_fused * 1e3,
         "reads_per_s": n_reads / t_fused, "algorithmic_GBps": n_bases / t_fused / 1e9, "frac_of_hbm_peak": n_bases / t_fused / 1e9 / peak,
-        "note": "commet_filter_reads_dev: k_filter_ascii reads the ASCII once (1 B/base + 8 B/read of offsets) and writes 1 bit + 1 class "
-                "byte per read; includes the undecided-read round trip, the cutoff kernel and the counter read-back"}
-    out["filter_reads_staged"] = {
+        "note": "commet_filter_reads_dev: k_stage_filter<false> reads the ASCII once (1 B/base + 8 B/read of offsets) and writes 1 bit + 1 "
+                "class byte per read; the call includes the undecided-read round trip, the cutoff kernel and the counter read-back"}
+    out["filter_reads_fused_with_staging"] = {
+        "reads": n_reads, "bases": n_bases, "selected": selected, "options": "-l 66 -n 2 -e 1.5", "ms": t_both * 1e3,
+        "reads_per_s": n_reads / t_both, "algorithmic_GBps": n_bases / t_both / 1e9, "frac_of_hbm_peak": n_bases / t_both / 1e9 / peak,
+        "traffic_GBps": 1.5 * n_bases / t_both / 1e9, "traffic_frac_of_hbm_peak": 1.5 * n_bases / t_both / 1e9 / peak,
+        "note": "commet_reads_from_device_filtered: k_stage_filter<true> reads the ASCII once and writes the bit-planes (0.5 B/base) AND "
+                "the selection bits: a set that is filtered and indexed is read from HBM once; traffic = 1.5 B/base"}
+    out["filter_reads_two_kernels"] = {
         "reads": n_reads, "bases": n_bases, "selected": selected, "options": "-l 66 -n 2 -e 1.5",
         "stage_ms": t_stage * 1e3, "filter_ms": t_filter * 1e3,
         "reads_per_s": n_reads / tot, "algorithmic_GBps": n_bases / tot / 1e9, "frac_of_hbm_peak": n_bases / tot / 1e9 / peak,
@@ -163,6 +183,15 @@ def main():
     ms = (time.perf_counter() - t0) / args.reps * 1e3
     res["popcount"] = {"ms": ms, "algorithmic_GBps": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak,
                        "note": "includes the 8-byte D2H of the count and a stream sync per call"}
+    nvec = 16
+    t0 = time.perf_counter()
+    for _ in range(args.reps):
+        many = ctx.nb_one_device_batch([o.data_ptr()] * nvec, [args.bits] * nvec)
+    ms = (time.perf_counter() - t0) / args.reps / nvec * 1e3
+    assert many == [ones] * nvec
+    res["popcount_batched"] = {"ms_per_vector": ms, "vectors_per_call": nvec, "algorithmic_GBps": nbytes / ms / 1e6,
+                               "frac_of_hbm_peak": nbytes / ms / 1e6 / peak,
+                               "note": "commet_bv_popcount_batch_dev: one kernel per vector, one read-back and one sync per call"}
     out["bvop"] = {"bits": args.bits, "payload_bytes": nbytes, **res,
                    "note": "one 1e9-bit vector = 125 MB: a binary op touches 375 MB (> 126 MB L2)"}
     print(json.dumps(out, indent=1))

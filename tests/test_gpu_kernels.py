@@ -320,7 +320,7 @@ def test_filter_reads(ctx, seed):
     if rng.random() < 0.5: kw["max_reads"] = int(rng.choice([0, 1, n // 3, n, n + 5, 1024, 1023, 1025]))
     stream = H.to_stream(reads)
     exp_bv, exp_cnt = oracle.filter_reads(*stream, **kw)
-    bv, cnt = ctx.filter_reads(*stream, **kw)               # fused with the staging pass (k_filter_ascii)
+    bv, cnt = ctx.filter_reads(*stream, **kw)               # one pass over the ASCII bases, no bit-planes (k_stage_filter<false>)
     assert cnt == exp_cnt, (seed, kw)
     assert np.array_equal(bv, exp_bv), (seed, kw)
     import torch                                             # the same selection on an already staged stream (k_filter)
@@ -330,7 +330,47 @@ def test_filter_reads(ctx, seed):
     cnt2 = ctx.filter_reads_staged(rs, d_bv.data_ptr(), **kw)
     assert cnt2 == exp_cnt, (seed, kw)
     assert np.array_equal(d_bv.cpu().numpy().view(np.uint8)[:n // 8 + 1], exp_bv), (seed, kw)
+    # staging and selection in ONE pass (k_stage_filter<true>): the same bits, and bit-planes that index like k_encode's
+    bases_d = torch.zeros((len(stream[0]) + 15) // 16 * 16 + 16, dtype=torch.uint8, device="cuda:0")
+    bases_d[:len(stream[0])] = torch.as_tensor(stream[0], device="cuda:0")
+    if seed % 3 == 0:
+        bases_d[len(stream[0]):] = ord("A")                   # bytes past the end of the stream are not bases
+    offs_d = torch.as_tensor(stream[1].astype(np.int64), device="cuda:0")
+    d_bv3 = torch.zeros_like(d_bv)
+    torch.cuda.synchronize()
+    rs3, cnt3 = ctx.stage_device_filtered(bases_d.data_ptr(), offs_d.data_ptr(), n, len(stream[0]), d_bv3.data_ptr(), **kw)
+    assert cnt3 == exp_cnt, (seed, kw)
+    assert np.array_equal(d_bv3.cpu().numpy().view(np.uint8)[:n // 8 + 1], exp_bv), (seed, kw)
+    k = int(rng.integers(1, 25))
+    ctx.index_reads(rs, k)
+    f_encode = ctx.filter_download(k)
+    ctx.index_reads(rs3, k)
+    assert np.array_equal(ctx.filter_download(k), f_encode), (seed, k)
+    assert np.array_equal(ctx.kmer_counts(rs3, k), ctx.kmer_counts(rs, k))
     rs.free()
+    rs3.free()
+
+
+@pytest.mark.parametrize("cap", ["64", None])
+def test_filter_reads_more_undecided_reads_than_the_record_buffer(ctx, cap, monkeypatch):
+    """dinucleotide repeats have H = 1.0 exactly: with -e 1 every one of them sits on the threshold and is re-decided on
+    the host from its exact counts.  More of them than the device buffer holds (2^20; 64 here for the small case) run the
+    pass again with a buffer of the size asked for -- the reference has no such limit."""
+    rng = np.random.default_rng(99)
+    n = 3000 if cap else (1 << 20) + 50_000
+    if cap:
+        monkeypatch.setenv("COMMET_B200_BORDER_CAP", cap)
+    pats = [np.frombuffer(p, dtype=np.uint8) for p in (b"AC", b"GT", b"TA", b"CG", b"AG")]
+    reads = []
+    for i in range(n):
+        L = 2 * int(rng.integers(5, 20))
+        reads.append(np.tile(pats[i % 5], L // 2).tobytes() if i % 7 else H.random_read(rng, L).tobytes())
+    stream = H.to_stream(reads)
+    for kw in (dict(min_shannon=1.0), dict(min_shannon=1.0, min_len=20, max_reads=n // 2)):
+        exp_bv, exp_cnt = oracle.filter_reads(*stream, **kw)
+        bv, cnt = ctx.filter_reads(*stream, **kw)
+        assert cnt == exp_cnt and np.array_equal(bv, exp_bv), kw
+    assert exp_cnt["selected"] > 0
 
 
 def test_filter_reads_long_reads(ctx):

@@ -212,3 +212,84 @@ def test_group_of_one_process_equals_the_oracle(monkeypatch, world, k, t, maxk, 
         g.close()
     if maxk:
         assert e["chunks"] >= 2
+
+
+# ---- C4 twin: BASELINE.json configs[3] at a size the oracle can follow ----------------------------------------
+C4_TWIN = dict(n_ref=2_000_000, n_sets=8, nq=50_000, L=150, k=27, t=2)      # 2.5e8 k-mers = 16 chunks at k=27, 15 reads lost
+
+
+def _c4_worker(rank, world, port, n_dev, out_dir):
+    import faulthandler
+    faulthandler.enable()
+    import importlib.util
+    import torch
+    import torch.distributed as dist
+    import commet_b200
+    spec = importlib.util.spec_from_file_location("bench_c4", ROOT / "scripts" / "bench_c4.py")
+    bench_c4 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench_c4)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dev_i = rank % n_dev
+        torch.cuda.set_device(dev_i)
+        dev = torch.device("cuda", dev_i)
+        ctx = commet_b200.Context(dev_i)
+
+        def all_gather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        p = C4_TWIN
+        keep = {}
+        info, res = bench_c4.run_c4(torch, ctx, dev, world, rank, dist.barrier, all_gather, p["n_ref"], p["n_sets"], p["nq"], p["L"],
+                                    p["k"], p["t"], keep=keep)
+        np.save(Path(out_dir) / f"shard{rank}.npy", keep["shard"])
+        for s, (shared, tg) in res.items():
+            np.save(Path(out_dir) / f"query{s}.npy", keep[f"query{s}"])
+            np.save(Path(out_dir) / f"tags{s}.npy", tg.cpu().numpy().view(np.uint8)[:p["nq"] // 8 + 1])
+            np.save(Path(out_dir) / f"meta{s}.npy", np.array([info["chunks"], shared, info["searched"][list(res).index(s)]]))
+        np.save(Path(out_dir) / f"indexed{rank}.npy", np.array([info["indexed_here"]]))
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+_c4_oracle_cache = {}
+
+
+@pytest.mark.skipif(_n_gpus() < 1, reason="needs a GPU")
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_c4_twin_every_vector_equals_the_oracle(tmp_path, world):
+    """The C4 workload of scripts/bench_c4.py (same generator, same library loop) at 1/250 of the reference set and
+    k=27, so that the stop rule still cuts it into 16 chunks: every query set's vector, the chunk count, the lost reads
+    and the counters equal the oracle's, with the reference set on one rank and dealt over 2 and 4 ranks."""
+    import torch.multiprocessing as mp
+    from commet_b200 import multi
+    p = C4_TWIN
+    mp.spawn(_c4_worker, args=(world, _free_port(), min(_n_gpus(), world), str(tmp_path)), nprocs=world, join=True)
+    # the global reference stream from the ranks' shards (block b lives on rank b % world)
+    L, n_ref, block = p["L"], p["n_ref"], multi.DEFAULT_BLOCK
+    ref = np.empty(n_ref * L, dtype=np.uint8)
+    shards = [np.load(tmp_path / f"shard{r}.npy") for r in range(world)]
+    for b in range((n_ref + block - 1) // block):
+        g0, g1 = b * block, min(n_ref, (b + 1) * block)
+        r = b % world
+        l0 = multi.local_index(g0, world, r, block)
+        ref[g0 * L:g1 * L] = shards[r][l0 * L:(l0 + g1 - g0) * L]
+    queries = [np.load(tmp_path / f"query{s}.npy").reshape(-1) for s in range(p["n_sets"])]
+    key = hash(ref[::997].tobytes())
+    if key not in _c4_oracle_cache:                  # the generator does not depend on the number of ranks
+        offs = np.arange(n_ref + 1, dtype=np.uint64) * L
+        qoffs = np.arange(p["nq"] + 1, dtype=np.uint64) * L
+        _c4_oracle_cache[key] = oracle.index_and_search(p["k"], p["t"], (ref, offs), [(q, qoffs) for q in queries])
+    e_tags, e = _c4_oracle_cache[key]
+    assert e["chunks"] == 16
+    indexed = sum(int(np.load(tmp_path / f"indexed{r}.npy")[0]) for r in range(world))
+    assert indexed == e["indexed"] == n_ref - 15
+    for s in range(p["n_sets"]):
+        chunks, shared, searched = np.load(tmp_path / f"meta{s}.npy").tolist()
+        assert np.array_equal(np.load(tmp_path / f"tags{s}.npy"), oracle.tags_to_bv(e_tags[s])), f"set {s}: vector differs from the oracle's"
+        assert chunks == e["chunks"] and shared == e["shared"][s] and searched == e["searched"][s]
+        assert 0.4 < shared / p["nq"] < 0.8
