@@ -160,10 +160,11 @@ class ClockSampler:
 
 
 def bind_to_gpu_numa_node(index: int):
-    """BENCH_NUMA_BIND=1 (opt-in, A/B for the N=8 end-to-end leg): run this rank on the CPUs of its GPU's NUMA node and
-    prefer that node's memory, so that the pinned buffers its H2D copies read from are local to the GPU's PCIe root.
-    Returns what was done (for the JSON line) or None."""
-    if os.environ.get("BENCH_NUMA_BIND", "0") in ("", "0"):
+    """Run this rank on the CPUs of its GPU's NUMA node and prefer that node's memory, so that the pinned buffers its H2D
+    copies read from are local to the GPU's PCIe root.  On by default when there is more than one rank (BENCH_NUMA_BIND=0
+    turns it off; A/B in profiles/).  Returns what was done (for the JSON line) or None."""
+    dflt = "1" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "0"
+    if os.environ.get("BENCH_NUMA_BIND", dflt) in ("", "0"):
         return None
     try:
         import ctypes
@@ -263,6 +264,150 @@ def cpu_baseline(ref_b, qry_b, length, k, t, sample: int, procs: int = 1):
 
 
 # ----------------------------------------------------------------------------
+# cheap extra legs of the N=1 line (BASELINE.json configs other than the headline one): each is a few seconds, parity for
+# each is in tests/ (named per leg); a leg that fails reports its error instead of taking the line down
+# ----------------------------------------------------------------------------
+def extra_legs(torch, ctx, dev, ext, args, ref_d, qry_d, offs_d, ref_h, qry_h, shared_c2):
+    import commet_b200
+    from commet_b200 import build
+    n, L, k, t = args.reads, args.length, args.k, args.t
+    peak, _ = measured_peaks()
+    out = {}
+
+    def leg(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as e:                       # noqa: BLE001
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    def tool_e2e():
+        """C2 through the drop-in executable: FASTA parse, H2D, kernels, D2H and the .bv write inside the clock (SURVEY 8d's
+        end-to-end scope); the FASTA files are written to a tmpfs first (not timed).  Parity: tests/test_gpu_fullsize.py::
+        test_c2_whole_vector_equals_the_reference_binary."""
+        build.build_tools()
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+        with tempfile.TemporaryDirectory(prefix="commet_tool_", dir=base) as td:
+            td = Path(td)
+            for name, arr in (("ref", ref_h), ("qry", qry_h)):
+                rows = np.empty((n, 1 + 8 + 1 + L + 1), dtype=np.uint8)
+                rows[:, 0] = ord(">")
+                idx = np.arange(n, dtype=np.int64)
+                for d in range(8):
+                    rows[:, 1 + d] = (idx // 10 ** (7 - d)) % 10 + 48
+                rows[:, 9] = 10
+                rows[:, 10:10 + L] = arr.numpy().reshape(n, L)
+                rows[:, -1] = 10
+                rows.tofile(td / f"{name}.fa")
+                (td / f"{name}.txt").write_text(f"{name}:{td}/{name}.fa\n")
+                del rows
+            best = None
+            for _ in range(2):
+                t0 = time.perf_counter()
+                r = subprocess.run([str(build.BIN / "index_and_search"), "-i", str(td / "ref.txt"), "-s", str(td / "qry.txt"), "-o",
+                                    str(td / "out"), "-l", str(td / "out"), "-k", str(k), "-t", str(t)], capture_output=True, text=True)
+                wall = time.perf_counter() - t0
+                if r.returncode != 0:
+                    raise RuntimeError(r.stderr[-300:])
+                best = wall if best is None else min(best, wall)
+            log = (td / "out" / "qry_in_ref.log").read_text()
+            assert f"shared {shared_c2}]" in log, log
+            return {"value": n / best, "unit": UNIT, "seconds": round(best, 3), "fasta_bytes": int(2 * n * (L + 11)),
+                    "scope": "process start + CUDA context + FASTA parse (2 files) + H2D + kernels + D2H + .bv and .log write; best of 2"}
+
+    def k27():
+        """the L2-resident variant of C2: k=27, 64 MiB filter, 48 chunks.  Parity: test_search_small_and_large_k,
+        test_index_and_search_chunk_loop (multi-chunk), the C4 twin at k=27."""
+        tags = torch.zeros((n // 8 + 1 + 3) // 4, dtype=torch.int32, device=dev)
+        res = None
+        for it in range(2):
+            ctx.count_probes(it == 1)
+            tags.zero_()
+            torch.cuda.synchronize()
+            q = ctx.stage_device(qry_d.data_ptr(), offs_d.data_ptr(), n, n * L)
+            idx = ctx.stage_device(ref_d.data_ptr(), offs_d.data_ptr(), n, n * L)
+            info = ctx.index_and_search_staged(27, t, idx, [q], [tags.data_ptr()])
+            ctx.sync()
+            idx.free(); q.free()
+            if it == 0:
+                res = info
+        ctx.count_probes(False)
+        ceil = random_sector_ceiling(1 << 26)
+        ach = info["tests"] * 32 / (res["search_ns"] / 1e9) / 1e9
+        return {"chunks": res["chunks"], "index_ms": res["index_ns"] / 1e6, "search_ms": res["search_ns"] / 1e6,
+                "query_reads_per_s": n / ((res["index_ns"] + res["search_ns"]) / 1e9), "n_probes": info["tests"],
+                "probes_per_s": info["tests"] / (res["search_ns"] / 1e9), "achieved_GBps": ach, "l2_random_sector_ceiling_GBps": ceil,
+                "frac_of_l2_random_sector_ceiling": ach / ceil if ceil else None}
+
+    def c5():
+        """bandwidth-bound vector operators at 1e9 bits and the selection over the C2 query set (-l 66 -n 2 -e 1.5).
+        Parity: test_c5_vector_identities_at_1e9_bits, test_c5_filter_reads_constructed_classes_10m, test_filter_reads."""
+        bits = 1_000_000_000
+        nbytes = bits // 8 + 1
+        g = torch.Generator(device=dev)
+        g.manual_seed(7)
+        pad = (nbytes + 15) // 16 * 16
+        a = torch.randint(0, 256, (pad,), dtype=torch.uint8, generator=g, device=dev)
+        b = torch.randint(0, 256, (pad,), dtype=torch.uint8, generator=g, device=dev)
+        o = torch.empty_like(a)
+        torch.cuda.synchronize()
+        ctx.bvop_device(commet_b200.BV_AND, a.data_ptr(), b.data_ptr(), o.data_ptr(), nbytes)
+        ctx.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            e0.record()
+        for _ in range(5):
+            ctx.bvop_device(commet_b200.BV_AND, a.data_ptr(), b.data_ptr(), o.data_ptr(), nbytes)
+        with torch.cuda.stream(ext):
+            e1.record()
+        ctx.sync()
+        ms_and = e0.elapsed_time(e1) / 5
+        t0 = time.perf_counter()
+        ones = ctx.nb_one_device_batch([o.data_ptr()] * 8, [bits] * 8)
+        ms_pop = (time.perf_counter() - t0) / 8 * 1e3
+        d_bv = torch.zeros((n // 8 + 1 + 3) // 4, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        rs = ctx.stage_device(qry_d.data_ptr(), offs_d.data_ptr(), n, n * L)
+        ctx.filter_reads_staged(rs, d_bv.data_ptr(), min_len=66, max_N=2, min_shannon=1.5)
+        rs.free()
+        ctx.sync()
+        with torch.cuda.stream(ext):
+            e0.record()
+        rs = ctx.stage_device(qry_d.data_ptr(), offs_d.data_ptr(), n, n * L)
+        cnt = ctx.filter_reads_staged(rs, d_bv.data_ptr(), min_len=66, max_N=2, min_shannon=1.5)
+        with torch.cuda.stream(ext):
+            e1.record()
+        ctx.sync()
+        rs.free()
+        ms_f = e0.elapsed_time(e1)
+        return {"bvop_and_1e9_bits": {"ms": ms_and, "GBps": 3 * nbytes / ms_and / 1e6, "frac_of_hbm_peak": 3 * nbytes / ms_and / 1e6 / peak},
+                "popcount_1e9_bits_batched": {"ms": ms_pop, "GBps": nbytes / ms_pop / 1e6, "frac_of_hbm_peak": nbytes / ms_pop / 1e6 / peak,
+                                               "ones": ones[0]},
+                "stage_and_filter_reads": {"reads": n, "bases": n * L, "ms": ms_f, "reads_per_s": n / (ms_f / 1e3),
+                                           "GBps_of_ascii": n * L / ms_f / 1e6, "frac_of_hbm_peak": n * L / ms_f / 1e6 / peak,
+                                           "selected": cnt["selected"],
+                                           "scope": "k_encode + k_filter over the planes + cutoff, the call with its read-backs (CUDA events)"}}
+
+    def c4_small():
+        """C4 at 1/25 of the reference set (20 M reads x 150 bp, 3 chunks at k=33) against 8 query sets of 2 M reads: the multi-chunk,
+        multi-set loop in this line; full size (500 M reads, 59 chunks) at 1/2/4/8 GPUs is profiles/r02_c4_full_n*.json.
+        Parity: tests/test_gpu_multi.py::test_c4_twin_every_vector_equals_the_oracle."""
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("bench_c4", ROOT / "scripts" / "bench_c4.py")
+        bench_c4 = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bench_c4)
+        info, res = bench_c4.run_c4(torch, ctx, dev, 1, 0, torch.cuda.synchronize, lambda b: [b], 20_000_000, 8, 2_000_000, 150, 33, 2)
+        return {"ref_reads": 20_000_000, "query_sets": 8, "query_reads_per_set": 2_000_000, "read_len": 150, "chunks": info["chunks"],
+                "seconds": round(info["seconds"], 3), "query_reads_per_s": 8 * 2_000_000 / info["seconds"],
+                "index_s": round(info["index_s"], 3), "search_s": round(info["search_ns"] * 1e-9, 3), "shared_set0": int(res[0][0])}
+
+    leg("tool_e2e_c2", tool_e2e)
+    leg("k27_l2_resident", k27)
+    leg("c5", c5)
+    leg("c4_small", c4_small)
+    return out
+
+
+# ----------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -277,6 +422,7 @@ def main():
                     help="reads per set of the bounded CPU sample (2 M: ~20 s for one reference process at C2, so that the "
                          "fixed cost of zeroing the 4 GiB filter is amortised as it is at full size)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (tool-level end to end, k=27, C5, small C4) of the N=1 line")
     ap.add_argument("--direct-index", action="store_true", help="disable the L2-blocked insert (A/B)")
     ap.add_argument("--index-mode", type=int, default=None, help="commet_ctx_binned_index mode (A/B): 0 direct, 1 "
                     "sorted records (default), 16..30 region passes with 2^mode-byte regions")
@@ -362,6 +508,7 @@ def main():
             info = {"shared": r["shared"], "searched": r["searched"], "chunks": r["chunks"], "index_ns": 0, "search_ns": r["search_ns"],
                     "kmers": 0, "phases_ms": {key[:-2]: round(r[key] * 1e3, 3) for key in ("plan_s", "index_s", "merge_s", "barrier_s")}}
             info["phases_ms"]["search"] = round(r["search_ns"] / 1e6, 3)
+            info["dist_mode"] = r["mode"]
         idx.free()
         q.free()
         return info
@@ -473,6 +620,7 @@ def main():
     }
     if "phases_ms" in info:
         line["phases_ms_rank0"] = info["phases_ms"]
+        line["dist_mode"] = info.get("dist_mode")
     if numa is not None:
         line["numa_bind_rank0"] = numa
     if world == 1 and srch_ms > 0 and probes:
@@ -498,6 +646,8 @@ def main():
                            "n_lookups": probes["lookups"], "probes_per_s": probes["tests"] / (srch_ms / 1e3)}
     if not args.no_cpu and world == 1:
         line["cpu_baseline"] = cpu_baseline(ref_h.numpy(), qry_h.numpy(), L, k, t, min(args.cpu_sample, n))
+    if world == 1 and not args.no_extra and k == 33:
+        line["extra"] = extra_legs(torch, ctx, dev, ext, args, ref_d, qry_d, offs_d, ref_h, qry_h, int(shared))
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -577,14 +727,23 @@ def reference_arm(args, rank, world, config):
         if r[1] == "port":
             break
     best = min(tried.values())
+    runs = 1
     for _ in range(max(0, min(args.steps, 3) - 1)):      # repeat the best configuration, keep its fastest run
         r = cpu_reference_run(ref, qry, L, sample, sample, k, t, best[2]) if best[1] == "reference" else None
         if r is not None:
             best = min(best, r)
+            runs += 1
     wall, kind, cores = best
     v = sample / wall
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak",
+    # `steps` / `warmup` are what this arm really ran: `runs` timed passes of the fastest process count over the SAMPLE
+    # (ms_per_step = one such pass), after len(tried) - 1 exploratory passes with other process counts
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": runs,
+            "warmup": len(tried) - 1, "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "sample_of": {"reads_per_set": n, "sample_reads_per_set": sample, "fraction": sample / n,
+                          "note": "the filter of the sample holds sample/reads_per_set of the k-mers of the full set (5x emptier at "
+                                  "the default 2 M of 10 M): fewer b/c/d probes per lookup than at full size, i.e. the CPU rate is, if "
+                                  "anything, flattered"},
+            "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                              "host_cpus": os.cpu_count(),

@@ -215,13 +215,14 @@ class Dist:
         th = (C.c_void_p * max(ns, 1))(*d_tags)
         searched = np.zeros(max(ns, 1), dtype=np.uint64)
         shared = np.zeros(max(ns, 1), dtype=np.uint64)
-        stats = np.zeros(11, dtype=np.uint64)
+        stats = np.zeros(12, dtype=np.uint64)
         self._ck(self.ctx.lib.commet_dist_index_and_search(self.handle, t, maxk, shard.handle, n_global, block, ns,
                                                            C.cast(qh, C.c_void_p), C.cast(th, C.c_void_p), _ptr(searched),
                                                            _ptr(shared), _ptr(stats)))
         return dict(chunks=int(stats[0]), indexed_here=int(stats[1]), plan_s=stats[2] * 1e-9, index_s=stats[3] * 1e-9,
                     search_ns=int(stats[4]), merge_s=stats[5] * 1e-9, barrier_s=stats[6] * 1e-9, tests=int(stats[7]),
                     lookups=int(stats[8]), last_chunk=(int(stats[9]), int(stats[10])),
+                    mode="owner-applied records + slice all-gather" if stats[11] else "partial filters + merge",
                     searched=[int(x) for x in searched[:ns]], shared=[int(x) for x in shared[:ns]])
 
     def close(self):

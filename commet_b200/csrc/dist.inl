@@ -54,6 +54,10 @@ struct commet_dist {
     int k = 0;
     std::vector<void *> peers;          // peer filters as seen from this device (entry `rank`: null)
     std::vector<char> via_ipc;          // opened with cudaIpcOpenMemHandle: closed in commet_dist_close
+    // owner-applied insert (kernels.cuh): the peers' record pools, record counters and slab tables as seen from here
+    struct PeerBuf { uint64_t raw = 0; void *mapped = nullptr; bool ipc = false; };
+    std::vector<PeerBuf> p_recs, p_bins2, p_table;
+    std::vector<uint32_t> p_max_q;
 };
 
 extern "C" int commet_dist_open(commet_ctx *c, const commet_comm *comm, int k, commet_dist **out)
@@ -69,6 +73,10 @@ extern "C" int commet_dist_open(commet_ctx *c, const commet_comm *comm, int k, c
     d->k = k;
     d->peers.assign(comm->world, nullptr);
     d->via_ipc.assign(comm->world, 0);
+    d->p_recs.resize(comm->world);
+    d->p_bins2.resize(comm->world);
+    d->p_table.resize(comm->world);
+    d->p_max_q.assign(comm->world, 0);
     if (comm->world > 1) {
         PeerInfo me{};
         me.pid = (uint64_t)getpid();
@@ -113,6 +121,9 @@ extern "C" void commet_dist_close(commet_dist *d)
         cudaStreamSynchronize(d->ctx->stream);
         for (size_t p = 0; p < d->peers.size(); p++)
             if (d->peers[p] && d->via_ipc[p]) cudaIpcCloseMemHandle(d->peers[p]);
+        for (auto *v : {&d->p_recs, &d->p_bins2, &d->p_table})
+            for (auto &b : *v)
+                if (b.mapped && b.ipc) cudaIpcCloseMemHandle(b.mapped);
     }
     delete d;
 }
@@ -140,14 +151,34 @@ k_block_sums(const uint32_t *__restrict__ counts, uint64_t n, uint64_t block, un
 
 struct Resolved { uint64_t found, index, kmers; };      // found: 0 / 1; index: global read; kmers of the range
 
+// sums of the per-read counts over local read ranges (lo, hi): one block per range
+__global__ void __launch_bounds__(256)
+k_range_sums(const uint32_t *__restrict__ counts, const uint64_t *__restrict__ ranges, unsigned long long *__restrict__ sums)
+{
+    const uint64_t lo = ranges[2 * blockIdx.x], hi = ranges[2 * blockIdx.x + 1];
+    unsigned long long s = 0;
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s += counts[i];
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    __shared__ unsigned long long ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < 8; i++) t += ws[i];
+        sums[blockIdx.x] = t;
+    }
+}
+
 // Chunk plan of the whole set from this rank's shard (see the header of this file).  plan: pairs (first, end).
+// chunk_kmers[i]: k-mers of THIS rank's reads of chunk i (what its scatter will emit, times four).
 int dist_plan(commet_dist *d, commet_reads *shard, uint64_t n_global, uint64_t block, uint64_t max_kmer,
-              std::vector<uint64_t> &plan)
+              std::vector<uint64_t> &plan, std::vector<uint64_t> &chunk_kmers)
 {
     commet_ctx *c = d->ctx;
     const commet_comm &cm = d->comm;
     const uint64_t world = (uint64_t)cm.world, rank = (uint64_t)cm.rank;
     plan.clear();
+    chunk_kmers.clear();
     const uint64_t n_local = local_index(n_global, world, rank, block);
     if (shard->n_reads != n_local)
         return fail("rank %d holds %llu reads, its blocks of %llu reads are %llu", cm.rank, (unsigned long long)shard->n_reads,
@@ -165,6 +196,7 @@ int dist_plan(commet_dist *d, commet_reads *shard, uint64_t n_global, uint64_t b
     if (sum < max_kmer) {                       // the limit is never reached: one chunk, nothing lost
         plan.push_back(0);
         plan.push_back(n_global);
+        chunk_kmers.push_back(mine);
         return 0;
     }
     // per-block totals: n_global / block numbers in all
@@ -238,6 +270,89 @@ int dist_plan(commet_dist *d, commet_reads *shard, uint64_t n_global, uint64_t b
         plan.push_back(a.index + 1);
         i = a.index + 2;                                                   // read index+1 is fetched and lost (index_reads.h:60)
     }
+    // this rank's k-mers of every chunk
+    const size_t n_chunks = plan.size() / 2;
+    chunk_kmers.assign(n_chunks, 0);
+    if (n_chunks && n_local) {
+        std::vector<uint64_t> ranges(2 * n_chunks);
+        for (size_t ci = 0; ci < n_chunks; ci++) {
+            ranges[2 * ci] = local_index(plan[2 * ci], world, rank, block);
+            ranges[2 * ci + 1] = local_index(plan[2 * ci + 1], world, rank, block);
+        }
+        DevBuf d_ranges(c), d_sums(c);
+        if (d_ranges.alloc(ranges.size() * sizeof(uint64_t)) != cudaSuccess || d_sums.alloc(n_chunks * sizeof(unsigned long long)) != cudaSuccess)
+            return fail("allocation of chunk sums failed");
+        CK(cudaMemcpyAsync(d_ranges.p, ranges.data(), ranges.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        k_range_sums<<<(unsigned)n_chunks, 256, 0, c->stream>>>(counts.as<uint32_t>(), d_ranges.as<uint64_t>(), d_sums.as<unsigned long long>());
+        c->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(chunk_kmers.data(), d_sums.p, n_chunks * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+struct InsertInfo {                 // what the ranks exchange before an owner-applied insert
+    uint64_t pid;
+    int32_t device;
+    uint32_t max_q;
+    uint64_t recs, bins2, table;    // device addresses inside the owning process
+    uint8_t h_recs[COMMET_IPC_HANDLE_BYTES], h_bins2[COMMET_IPC_HANDLE_BYTES], h_table[COMMET_IPC_HANDLE_BYTES];
+};
+
+int map_peer_buf(commet_ctx *c, commet_dist::PeerBuf &b, uint64_t raw, const uint8_t *handle, bool same_process)
+{
+    if (b.raw == raw && b.mapped) return 0;                    // unchanged since the last call
+    if (b.mapped && b.ipc) CK(cudaIpcCloseMemHandle(b.mapped));
+    b = commet_dist::PeerBuf();
+    if (same_process) {
+        b.mapped = (void *)(uintptr_t)raw;
+    } else {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, sizeof h);
+        CK(cudaIpcOpenMemHandle(&b.mapped, h, cudaIpcMemLazyEnablePeerAccess));
+        b.ipc = true;
+    }
+    b.raw = raw;
+    return 0;
+}
+
+// collective: every rank's record pool, counters and slab table (sized for `bound` records here) mapped everywhere
+int dist_connect_insert(commet_dist *d, int n_bins, uint64_t bound, uint32_t *max_q)
+{
+    commet_ctx *c = d->ctx;
+    const commet_comm &cm = d->comm;
+    int rc = ensure_insert_buffers(c, n_bins, bound, max_q);
+    if (rc > 0) rc = fail("no room for the record pool of %llu records", (unsigned long long)bound);
+    InsertInfo me{};
+    me.pid = (uint64_t)getpid();
+    me.device = c->device;
+    me.max_q = *max_q;
+    if (rc == 0) {
+        me.recs = (uint64_t)(uintptr_t)c->recs;
+        me.bins2 = (uint64_t)(uintptr_t)c->bins2;
+        me.table = (uint64_t)(uintptr_t)c->slab_table;
+        cudaIpcMemHandle_t h;
+        if (cudaIpcGetMemHandle(&h, c->recs) == cudaSuccess) memcpy(me.h_recs, &h, sizeof h); else { cudaGetLastError(); rc = fail("cudaIpcGetMemHandle failed"); }
+        if (rc == 0 && cudaIpcGetMemHandle(&h, c->bins2) == cudaSuccess) memcpy(me.h_bins2, &h, sizeof h); else if (rc == 0) { cudaGetLastError(); rc = fail("cudaIpcGetMemHandle failed"); }
+        if (rc == 0 && cudaIpcGetMemHandle(&h, c->slab_table) == cudaSuccess) memcpy(me.h_table, &h, sizeof h); else if (rc == 0) { cudaGetLastError(); rc = fail("cudaIpcGetMemHandle failed"); }
+    }
+    if (rc != 0) me.recs = 0;                                   // tells the others that this rank cannot take part
+    std::vector<InsertInfo> all(cm.world);
+    if (cm.all_gather(cm.user, &me, all.data(), sizeof me) != 0) return fail("all_gather failed");
+    for (int p = 0; p < cm.world; p++)
+        if (all[p].recs == 0) return rc != 0 ? rc : fail("rank %d could not allocate its record pool", p);
+    for (int p = 0; p < cm.world; p++) {
+        d->p_max_q[p] = all[p].max_q;
+        if (p == cm.rank) {
+            d->p_recs[p].mapped = c->recs; d->p_bins2[p].mapped = c->bins2; d->p_table[p].mapped = c->slab_table;
+            continue;
+        }
+        const bool same = all[p].pid == me.pid;
+        CKR(map_peer_buf(c, d->p_recs[p], all[p].recs, all[p].h_recs, same));
+        CKR(map_peer_buf(c, d->p_bins2[p], all[p].bins2, all[p].h_bins2, same));
+        CKR(map_peer_buf(c, d->p_table[p], all[p].table, all[p].h_table, same));
+    }
     return 0;
 }
 
@@ -259,13 +374,42 @@ extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_
     const uint64_t world = (uint64_t)cm.world, rank = (uint64_t)cm.rank;
     Stopwatch sw;
     uint64_t ns_plan = 0, ns_index = 0, ns_merge = 0, ns_wait = 0;
-    std::vector<uint64_t> plan;
+    std::vector<uint64_t> plan, chunk_kmers;
     if (max_kmer == 0) {
         // nothing is ever inserted (index_reads.h:48: 0 < 0 is false) and every call loses one read: n_global searches
         // of an empty filter tag nothing; one of them gives the same vectors and counters
-        if (n_global) { plan.push_back(0); plan.push_back(0); }
+        if (n_global) { plan.push_back(0); plan.push_back(0); chunk_kmers.push_back(0); }
     } else {
-        CKR(dist_plan(d, shard, n_global, block, max_kmer, plan));
+        CKR(dist_plan(d, shard, n_global, block, max_kmer, plan, chunk_kmers));
+    }
+    const size_t n_chunks = plan.size() / 2;
+    // ---- how the chunks' filters are built: owner-applied records (kernels.cuh) when the regions deal evenly over the
+    // ranks and every rank's records of a chunk fit the 32-bit record counters; else every rank builds a partial
+    // filter and the partials are merged (k_merge_peers).  The decision is taken on exchanged numbers: the same everywhere.
+    bool owner_mode = false;
+    uint32_t max_q = 0;
+    const int n_bins = k >= kRecKeyBits + 2 && k - kRecKeyBits <= 9 ? 1 << (k - kRecKeyBits) : 0;
+    uint64_t tile_bound = 0;
+    if (world > 1 && n_chunks) {
+        uint64_t mine_max = 0;
+        for (uint64_t v : chunk_kmers) mine_max = std::max(mine_max, v);
+        std::vector<uint64_t> all(world * n_chunks, 0);
+        if (cm.all_gather(cm.user, chunk_kmers.data(), all.data(), n_chunks * sizeof(uint64_t)) != 0) return fail("all_gather failed");
+        uint64_t any_max = 0, chunk_max = 0;
+        for (size_t ci = 0; ci < n_chunks; ci++) {
+            uint64_t tot = 0;
+            for (uint64_t r = 0; r < world; r++) { any_max = std::max(any_max, all[r * n_chunks + ci]); tot += all[r * n_chunks + ci]; }
+            chunk_max = std::max(chunk_max, tot);
+        }
+        const char *mode = getenv("COMMET_B200_DIST_MODE");
+        int form = c->insert_form;
+        if (const char *e = getenv("COMMET_B200_INSERT")) form = atoi(e);
+        owner_mode = !(mode && std::string(mode) == "merge") && c->binned_index && !c->region_passes && form == 2 && n_bins >= 2 &&
+                     k >= 28 && n_bins % (int)world == 0 && 4 * any_max < 0xE0000000ull && chunk_max > 0;
+        if (owner_mode) {
+            CKR(dist_connect_insert(d, n_bins, 4 * mine_max + 64, &max_q));
+            tile_bound = 4 * chunk_max / 2048 + (uint64_t)n_bins + 1;
+        }
     }
     ns_plan = sw.lap_ns();
     DevBuf cnt_buf(c);
@@ -274,27 +418,99 @@ extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_
     unsigned long long *d_cnt = cnt_buf.as<unsigned long long>();
     CK(cudaMemsetAsync(d_cnt, 0, n_cnt * sizeof(unsigned long long), c->stream));
     for (int s = 0; s < n_sets; s++) CKR(prepare(c, queries[s], k));
-    const uint64_t clear_bytes = std::max<uint64_t>((commet_filter_bytes(k) + 255) & ~255ull, 256);
+    const uint64_t filter_bytes = commet_filter_bytes(k);
+    const uint64_t clear_bytes = std::max<uint64_t>((filter_bytes + 255) & ~255ull, 256);
     uint64_t indexed_here = 0;
-    SegTimer t_search;
-    for (size_t ci = 0; ci + 1 < plan.size(); ci += 2) {
-        CK(cudaMemsetAsync(c->filter, 0, clear_bytes, c->stream));
-        const uint64_t lo = local_index(plan[ci], world, rank, block), hi = local_index(plan[ci + 1], world, rank, block);
-        sw.lap_ns();
-        if (hi > lo) {
-            CKR(index_range(c, shard, lo, hi - lo, 0));
-            indexed_here += hi - lo;
+    SegTimer t_search, t_gather;
+    DevBuf tiles_buf(c);
+    PeerInsert pi{};
+    PeerFilters pf{};
+    cudaEvent_t ev_gather = nullptr;
+    struct EvGuard { cudaEvent_t *e; ~EvGuard() { if (*e) cudaEventDestroy(*e); } } ev_guard{&ev_gather};
+    if (owner_mode) {
+        if (tiles_buf.alloc(tile_bound * sizeof(OwnerTile)) != cudaSuccess) return fail("allocation of the tile list failed");
+        for (int p = 0; p < cm.world; p++) {
+            pi.recs[p] = static_cast<const uint32_t *>(d->p_recs[p].mapped);
+            pi.fill[p] = static_cast<const uint32_t *>(d->p_bins2[p].mapped);
+            pi.table[p] = static_cast<const uint32_t *>(d->p_table[p].mapped);
+            pi.max_q[p] = d->p_max_q[p];
+            pf.f[p] = p == cm.rank ? reinterpret_cast<uint4 *>(c->filter) : static_cast<uint4 *>(d->peers[p]);
         }
-        if (world > 1) {
-            CK(cudaStreamSynchronize(c->stream));          // my partial filter is complete on the device ...
+        CK(cudaEventCreateWithFlags(&ev_gather, cudaEventDisableTiming));
+        CKR(prepare(c, shard, k));
+    }
+    const int n_own = owner_mode ? n_bins / (int)world : 0, b_first = n_own * (int)rank;
+    const uint64_t slice_bytes = owner_mode ? filter_bytes / world : 0;
+    for (size_t ci = 0; ci + 1 < plan.size(); ci += 2) {
+        const uint64_t lo = local_index(plan[ci], world, rank, block), hi = local_index(plan[ci + 1], world, rank, block);
+        if (owner_mode) {
+            uint32_t *fills = c->bins2 + 1100, *tbase = c->bins2 + 512;
+            unsigned long long *tile_counter = c->bins + 1700;
+            if (ci > 0) {
+                // my slice of the previous chunk is still being pulled by the peers: nobody clears before everybody has it
+                CK(cudaEventSynchronize(ev_gather));
+                sw.lap_ns();
+                if (cm.barrier(cm.user) != 0) return fail("barrier failed");
+                ns_wait += sw.lap_ns();
+            }
+            sw.lap_ns();
+            CK(cudaMemsetAsync(reinterpret_cast<uint8_t *>(c->filter) + slice_bytes * rank, 0, slice_bytes, c->stream));
+            uint64_t hb[2] = {0, 0};
+            if (hi > lo) {
+                CK(cudaMemcpyAsync(&hb[0], shard->offs + lo, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaMemcpyAsync(&hb[1], shard->offs + hi, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+                indexed_here += hi - lo;
+            }
+            CKR(scatter_range(c, shard, hb[0], hb[1], n_bins, max_q));      // an empty range leaves zeroed counters
+            uint32_t overflow = 0;
+            CK(cudaMemcpyAsync(&overflow, c->bins2 + 1031, sizeof overflow, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));          // my records are complete in my slabs ...
+            if (overflow) return fail("record pool too small for chunk %zu", ci / 2);
+            ns_index += sw.lap_ns();
+            if (cm.barrier(cm.user) != 0) return fail("barrier failed");      // ... and so are everybody else's
+            ns_wait += sw.lap_ns();
+            // the records of MY regions, from every rank's slabs (peer reads over NVLink inside the apply kernel)
+            k_owner_fills<2048><<<1, 512, 0, c->stream>>>(pi, cm.world, b_first, n_bins, fills, tbase, tile_counter);
+            k_owner_tiles<2048><<<c->sm_count * 4, 256, 0, c->stream>>>(pi, cm.world, cm.rank, b_first, n_bins, fills, tbase, tiles_buf.as<OwnerTile>());
+            k_owner_apply<2048, true><<<c->sm_count * env_or("COMMET_B200_APPLY_BPS", 8), 256, 0, c->stream>>>(
+                c->filter, tiles_buf.as<OwnerTile>(), tbase, n_bins, b_first + n_own - 1, tile_counter);
+            c->launches += 3;
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(c->stream));          // my slice is final ...
             ns_index += sw.lap_ns();
             if (cm.barrier(cm.user) != 0) return fail("barrier failed");      // ... and so is everybody else's
             ns_wait += sw.lap_ns();
-            CKR(commet_index_merge(c, d->peers.data(), cm.world, cm.rank));
-            CK(cudaStreamSynchronize(c->stream));          // my merged slice has landed in every filter ...
-            ns_merge += sw.lap_ns();
-            if (cm.barrier(cm.user) != 0) return fail("barrier failed");      // ... and so has everybody else's
-            ns_wait += sw.lap_ns();
+            CKR(t_gather.begin(c->stream));
+            const uint64_t n_slice = slice_bytes / 16;
+            const unsigned gg = grid_for(c, n_slice, 256, 8);
+            switch (cm.world) {
+            case 2: k_gather_slices<2><<<gg, 256, 0, c->stream>>>(pf, cm.rank, n_slice); break;
+            case 4: k_gather_slices<4><<<gg, 256, 0, c->stream>>>(pf, cm.rank, n_slice); break;
+            default: k_gather_slices<8><<<gg, 256, 0, c->stream>>>(pf, cm.rank, n_slice); break;
+            }
+            c->launches++;
+            CK(cudaGetLastError());
+            CKR(t_gather.end(c->stream));
+            CK(cudaEventRecord(ev_gather, c->stream));
+        } else {
+            CK(cudaMemsetAsync(c->filter, 0, clear_bytes, c->stream));
+            sw.lap_ns();
+            if (hi > lo) {
+                CKR(index_range(c, shard, lo, hi - lo, chunk_kmers.size() > ci / 2 ? chunk_kmers[ci / 2] : 0));
+                indexed_here += hi - lo;
+            }
+            if (world > 1) {
+                CK(cudaStreamSynchronize(c->stream));          // my partial filter is complete on the device ...
+                ns_index += sw.lap_ns();
+                if (cm.barrier(cm.user) != 0) return fail("barrier failed");      // ... and so is everybody else's
+                ns_wait += sw.lap_ns();
+                CKR(commet_index_merge(c, d->peers.data(), cm.world, cm.rank));
+                CK(cudaStreamSynchronize(c->stream));          // my merged slice has landed in every filter ...
+                ns_merge += sw.lap_ns();
+                if (cm.barrier(cm.user) != 0) return fail("barrier failed");      // ... and so has everybody else's
+                ns_wait += sw.lap_ns();
+            }
         }
         CKR(t_search.begin(c->stream));
         for (int s = 0; s < n_sets; s++) {
@@ -322,12 +538,13 @@ extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_
         stats[2] = ns_plan;
         stats[3] = ns_index;
         stats[4] = (uint64_t)(t_search.total_ms() * 1e6);
-        stats[5] = ns_merge;
+        stats[5] = owner_mode ? (uint64_t)(t_gather.total_ms() * 1e6) : ns_merge;
         stats[6] = ns_wait;
         stats[7] = n_tests;
         stats[8] = n_lookups;
         stats[9] = plan.size() >= 2 ? plan[plan.size() - 2] : 0;       // the last chunk (global reads): what the filter holds now
         stats[10] = plan.size() >= 2 ? plan[plan.size() - 1] : 0;
+        stats[11] = owner_mode ? 1 : 0;
     }
     return 0;
 }

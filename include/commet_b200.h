@@ -171,10 +171,12 @@ typedef struct commet_dist commet_dist;
  * filter (commet_index_begin / commet_index_and_search* with another k) while the handle is open. */
 int commet_dist_open(commet_ctx *ctx, const commet_comm *comm, int k, commet_dist **out);
 /* collective.  shard: this rank's blocks of the index set (n_global reads in all); queries / d_tags / searched /
- * shared: this rank's own query streams, as in commet_index_and_search_staged.  stats[11]: chunks, reads indexed
- * by this rank, then host nanoseconds spent in the plan, the inserts, [4] = device ns of the searches, the merges,
- * the barriers; filter tests and k-mer lookups (with commet_ctx_count_probes); first and end read of the last
- * chunk (what the filter holds when the call returns). */
+ * shared: this rank's own query streams, as in commet_index_and_search_staged.  stats[12]: chunks, reads indexed
+ * by this rank, then host nanoseconds spent in the plan, the inserts, [4] = device ns of the searches, the merges
+ * (device ns of the slice all-gathers when [11] is set), the barriers; filter tests and k-mer lookups (with
+ * commet_ctx_count_probes); first and end read of the last chunk (what the filter holds when the call returns);
+ * [11] = 1 when the chunks' filters were built by owner-applied records + slice all-gather, 0 for partial filters +
+ * merge (COMMET_B200_DIST_MODE=merge forces the latter). */
 int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_kmer, commet_reads *shard, uint64_t n_global,
                                  uint64_t block, int n_sets, commet_reads *const *queries, uint32_t *const *d_tags,
                                  uint64_t *searched, uint64_t *shared, uint64_t *stats);
