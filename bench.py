@@ -442,6 +442,14 @@ def main():
     if args.impl == "reference":
         return reference_arm(args, rank, world, config)
 
+    # stdout carries ONE JSON line: everything libraries print there (NCCL's version banner, warnings) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     import torch
     import torch.distributed as dist
     import commet_b200
@@ -476,13 +484,18 @@ def main():
         # a few bytes: the k-mer totals of the chunk plan)
         from commet_b200 import multi
 
+        # (host-side control messages of a few bytes: a gloo group -- an NCCL collective would cost a launch, two copies and
+        # a device synchronisation each; NCCL stays the backend of the timing all-reduces and of the barriers around them)
+        ctl = dist.new_group(backend="gloo")
+
         def all_gather_bytes(b):
-            t_in = torch.frombuffer(bytearray(b), dtype=torch.uint8).to(dev)
-            out = torch.empty(world * len(b), dtype=torch.uint8, device=dev)
-            dist.all_gather_into_tensor(out, t_in)
-            raw = out.cpu().numpy().tobytes()
-            return [raw[i * len(b):(i + 1) * len(b)] for i in range(world)]
-        dd = commet_b200.Dist(ctx, world, rank, k_arg, dist.barrier, all_gather_bytes)
+            out = [None] * world
+            dist.all_gather_object(out, b, group=ctl)
+            return out
+
+        def ctl_barrier():
+            dist.barrier(group=ctl)
+        dd = commet_b200.Dist(ctx, world, rank, k_arg, ctl_barrier, all_gather_bytes)
         # this rank's shard of the reference set: blocks b = rank (mod world) of BLOCK consecutive reads -- what a
         # rank's loader delivers when every process parses only its own blocks of the files
         BLOCK = multi.DEFAULT_BLOCK
@@ -648,7 +661,7 @@ def main():
         line["cpu_baseline"] = cpu_baseline(ref_h.numpy(), qry_h.numpy(), L, k, t, min(args.cpu_sample, n))
     if world == 1 and not args.no_extra and k == 33:
         line["extra"] = extra_legs(torch, ctx, dev, ext, args, ref_d, qry_d, offs_d, ref_h, qry_h, int(shared))
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -1339,7 +1339,7 @@ static int chunk_loop(commet_ctx *c, int k, int t, uint64_t max_kmer, const std:
     CK(cudaMemsetAsync(d_cnt, 0, n_cnt * sizeof(unsigned long long), c->stream));
     uint64_t n_chunks = 0, n_indexed = 0, n_kmers = 0;
     uint64_t cum = 0, open_reads = 0;
-    bool began = false, dirty = false, pending_drop = false, queries_ready = false;
+    bool began = false, dirty = false, pending_drop = false;
     SegTimer t_index, t_search;
     const uint64_t clear_bytes = std::max<uint64_t>((commet_filter_bytes(k) + 255) & ~255ull, 256);
 
@@ -1361,10 +1361,8 @@ static int chunk_loop(commet_ctx *c, int k, int t, uint64_t max_kmer, const std:
     };
     auto close_chunk = [&]() -> int {
         CKR(open_filter());                 // a chunk without reads still owns an (empty) filter
-        if (!queries_ready) {               // query sets still crossing PCIe are encoded only now
-            for (int s = 0; s < n_sets; s++) CKR(prepare(c, queries[s], k));
-            queries_ready = true;
-        }
+        // (a query stream that is still crossing PCIe is encoded by search_launch right before its own scan: the scans of
+        // the streams that have arrived do not wait for it)
         CKR(t_search.begin(c->stream));
         for (int s = 0; s < n_sets; s++) {
             CK(cudaMemsetAsync(d_cnt + 4 * s + 1, 0, sizeof(unsigned long long), c->stream));
@@ -1525,8 +1523,12 @@ extern "C" int commet_index_and_search(commet_ctx *c, int k, int t, uint64_t max
     if (k < 1 || k > kMaxK) return fail("k=%d unsupported (1..%d)", k, kMaxK);
     if (ioffs[0] != 0) return fail("commet_index_and_search: ioffs[0] must be 0");
     std::vector<commet_reads *> parts;
-    std::vector<commet_reads *> q(n_sets, nullptr);
     std::vector<uint32_t *> dt(n_sets, nullptr);
+    // a large query set is uploaded (and searched) in a few parts cut at multiples of 32 reads -- their tag words are
+    // disjoint ranges of the set's vector -- so that the search of part i runs while part i+1 still crosses PCIe
+    std::vector<commet_reads *> vq;          // the parts of all sets, set after set
+    std::vector<uint32_t *> vtags;
+    std::vector<int> v_set;
     // every H2D copy is queued up front on the copy stream (index parts first); the host never waits for one
     std::vector<uint64_t> cuts = split_parts(ioffs, n_index);
     int rc = 0;
@@ -1539,24 +1541,56 @@ extern "C" int commet_index_and_search(commet_ctx *c, int k, int t, uint64_t max
         if (rc == 0) parts.push_back(r);
         trace("index part: allocations + copies queued");
     }
+    uint64_t q_part_bytes = 256ull << 20;
+    if (const char *e = getenv("COMMET_B200_QUERY_PART_BYTES")) q_part_bytes = std::max<uint64_t>(strtoull(e, nullptr, 10), 1);     // tests
     for (int s = 0; rc == 0 && s < n_sets; s++) {
         if (qoffs[s][0] != 0) { rc = fail("commet_index_and_search: qoffs[%d][0] must be 0", s); break; }
-        rc = reads_upload_async(c, qbases[s], qoffs[s], n_query[s], &q[s]);
-        if (rc == 0) {
-            uint64_t nw = tag_words(n_query[s]);
-            if (c->arena.alloc((void **)&dt[s], nw * 4) != cudaSuccess) rc = fail("tag allocation failed");
-            else if (cudaMemsetAsync(dt[s], 0, nw * 4, c->stream) != cudaSuccess) rc = fail("tag memset failed");
+        const uint64_t nw = tag_words(n_query[s]);
+        if (c->arena.alloc((void **)&dt[s], nw * 4) != cudaSuccess) { rc = fail("tag allocation failed"); break; }
+        if (cudaMemsetAsync(dt[s], 0, nw * 4, c->stream) != cudaSuccess) { rc = fail("tag memset failed"); break; }
+        const uint64_t n = n_query[s], bytes = qoffs[s][n];
+        const uint64_t n_parts = std::max<uint64_t>(1, std::min<uint64_t>(4, bytes / q_part_bytes));
+        uint64_t a = 0;
+        for (uint64_t p = 0; rc == 0 && p < n_parts; p++) {
+            uint64_t b = n;
+            if (p + 1 < n_parts) {
+                const uint64_t target = bytes * (p + 1) / n_parts;
+                b = (uint64_t)(std::lower_bound(qoffs[s], qoffs[s] + n + 1, target) - qoffs[s]) & ~31ull;
+                b = std::min(std::max(b, a), n);
+            }
+            if (b == a && p + 1 < n_parts) continue;
+            commet_reads *r = nullptr;
+            rc = reads_upload_async(c, qbases[s] + qoffs[s][a], qoffs[s] + a, b - a, &r);
+            if (rc == 0) {
+                vq.push_back(r);
+                vtags.push_back(dt[s] + a / 32);
+                v_set.push_back(s);
+            }
+            a = b;
         }
     }
     trace("query sets: allocations + copies queued");
-    if (rc == 0) rc = chunk_loop(c, k, t, max_kmer, parts, n_sets, q.data(), dt.data(), searched, shared, stats);
+    const int nv = (int)vq.size();
+    std::vector<uint64_t> v_searched(std::max(nv, 1), 0), v_shared(std::max(nv, 1), 0);
+    if (rc == 0) rc = chunk_loop(c, k, t, max_kmer, parts, nv, vq.data(), vtags.data(), v_searched.data(), v_shared.data(), stats);
+    if (rc == 0) {
+        for (int s = 0; s < n_sets; s++) {
+            if (searched) searched[s] = 0;
+            if (shared) shared[s] = 0;
+        }
+        for (int v = 0; v < nv; v++) {
+            if (searched) searched[v_set[v]] += v_searched[v];
+            if (shared) shared[v_set[v]] += v_shared[v];
+        }
+    }
     for (int s = 0; rc == 0 && s < n_sets; s++)
         if (cudaMemcpyAsync(tags[s], dt[s], n_query[s] / 8 + 1, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
             rc = fail("tag download failed");
     if (rc == 0 && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail("stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
     for (commet_reads *r : parts) commet_reads_free(r);
     trace("tags downloaded (sync)");
-    for (int s = 0; s < n_sets; s++) { commet_reads_free(q[s]); if (dt[s]) c->arena.free(dt[s]); }
+    for (commet_reads *r : vq) commet_reads_free(r);
+    for (int s = 0; s < n_sets; s++) if (dt[s]) c->arena.free(dt[s]);
     trace("freed");
     g_trace = nullptr;
     return rc;

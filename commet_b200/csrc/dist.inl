@@ -170,7 +170,7 @@ k_range_sums(const uint32_t *__restrict__ counts, const uint64_t *__restrict__ r
 }
 
 // Chunk plan of the whole set from this rank's shard (see the header of this file).  plan: pairs (first, end).
-// chunk_kmers[i]: k-mers of THIS rank's reads of chunk i (what its scatter will emit, times four).
+// chunk_kmers[r * n_chunks + i]: k-mers of rank r's reads of chunk i (what its scatter will emit, times four).
 int dist_plan(commet_dist *d, commet_reads *shard, uint64_t n_global, uint64_t block, uint64_t max_kmer,
               std::vector<uint64_t> &plan, std::vector<uint64_t> &chunk_kmers)
 {
@@ -196,7 +196,7 @@ int dist_plan(commet_dist *d, commet_reads *shard, uint64_t n_global, uint64_t b
     if (sum < max_kmer) {                       // the limit is never reached: one chunk, nothing lost
         plan.push_back(0);
         plan.push_back(n_global);
-        chunk_kmers.push_back(mine);
+        chunk_kmers = totals;                   // one chunk: every rank's share is its total, already exchanged
         return 0;
     }
     // per-block totals: n_global / block numbers in all
@@ -270,9 +270,9 @@ int dist_plan(commet_dist *d, commet_reads *shard, uint64_t n_global, uint64_t b
         plan.push_back(a.index + 1);
         i = a.index + 2;                                                   // read index+1 is fetched and lost (index_reads.h:60)
     }
-    // this rank's k-mers of every chunk
+    // every rank's k-mers of every chunk
     const size_t n_chunks = plan.size() / 2;
-    chunk_kmers.assign(n_chunks, 0);
+    std::vector<uint64_t> mine_c(n_chunks, 0);
     if (n_chunks && n_local) {
         std::vector<uint64_t> ranges(2 * n_chunks);
         for (size_t ci = 0; ci < n_chunks; ci++) {
@@ -286,9 +286,13 @@ int dist_plan(commet_dist *d, commet_reads *shard, uint64_t n_global, uint64_t b
         k_range_sums<<<(unsigned)n_chunks, 256, 0, c->stream>>>(counts.as<uint32_t>(), d_ranges.as<uint64_t>(), d_sums.as<unsigned long long>());
         c->launches++;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(chunk_kmers.data(), d_sums.p, n_chunks * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(mine_c.data(), d_sums.p, n_chunks * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
+    chunk_kmers.assign(world * n_chunks, 0);
+    if (world > 1 && n_chunks) {
+        if (cm.all_gather(cm.user, mine_c.data(), chunk_kmers.data(), n_chunks * sizeof(uint64_t)) != 0) return fail("all_gather failed");
+    } else chunk_kmers = mine_c;
     return 0;
 }
 
@@ -378,7 +382,7 @@ extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_
     if (max_kmer == 0) {
         // nothing is ever inserted (index_reads.h:48: 0 < 0 is false) and every call loses one read: n_global searches
         // of an empty filter tag nothing; one of them gives the same vectors and counters
-        if (n_global) { plan.push_back(0); plan.push_back(0); chunk_kmers.push_back(0); }
+        if (n_global) { plan.push_back(0); plan.push_back(0); chunk_kmers.assign(world, 0); }
     } else {
         CKR(dist_plan(d, shard, n_global, block, max_kmer, plan, chunk_kmers));
     }
@@ -391,15 +395,12 @@ extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_
     const int n_bins = k >= kRecKeyBits + 2 && k - kRecKeyBits <= 9 ? 1 << (k - kRecKeyBits) : 0;
     uint64_t tile_bound = 0;
     if (world > 1 && n_chunks) {
-        uint64_t mine_max = 0;
-        for (uint64_t v : chunk_kmers) mine_max = std::max(mine_max, v);
-        std::vector<uint64_t> all(world * n_chunks, 0);
-        if (cm.all_gather(cm.user, chunk_kmers.data(), all.data(), n_chunks * sizeof(uint64_t)) != 0) return fail("all_gather failed");
-        uint64_t any_max = 0, chunk_max = 0;
+        uint64_t mine_max = 0, any_max = 0, chunk_max = 0;
         for (size_t ci = 0; ci < n_chunks; ci++) {
             uint64_t tot = 0;
-            for (uint64_t r = 0; r < world; r++) { any_max = std::max(any_max, all[r * n_chunks + ci]); tot += all[r * n_chunks + ci]; }
+            for (uint64_t r = 0; r < world; r++) { any_max = std::max(any_max, chunk_kmers[r * n_chunks + ci]); tot += chunk_kmers[r * n_chunks + ci]; }
             chunk_max = std::max(chunk_max, tot);
+            mine_max = std::max(mine_max, chunk_kmers[rank * n_chunks + ci]);
         }
         const char *mode = getenv("COMMET_B200_DIST_MODE");
         int form = c->insert_form;
@@ -417,7 +418,7 @@ extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_
     if (cnt_buf.alloc(n_cnt * sizeof(unsigned long long)) != cudaSuccess) return fail("counter allocation failed");
     unsigned long long *d_cnt = cnt_buf.as<unsigned long long>();
     CK(cudaMemsetAsync(d_cnt, 0, n_cnt * sizeof(unsigned long long), c->stream));
-    for (int s = 0; s < n_sets; s++) CKR(prepare(c, queries[s], k));
+    // (the query streams are prepared by their first search: one that is still crossing PCIe must not hold up the inserts)
     const uint64_t filter_bytes = commet_filter_bytes(k);
     const uint64_t clear_bytes = std::max<uint64_t>((filter_bytes + 255) & ~255ull, 256);
     uint64_t indexed_here = 0;
@@ -497,7 +498,7 @@ extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_
             CK(cudaMemsetAsync(c->filter, 0, clear_bytes, c->stream));
             sw.lap_ns();
             if (hi > lo) {
-                CKR(index_range(c, shard, lo, hi - lo, chunk_kmers.size() > ci / 2 ? chunk_kmers[ci / 2] : 0));
+                CKR(index_range(c, shard, lo, hi - lo, chunk_kmers.size() == world * n_chunks ? chunk_kmers[rank * n_chunks + ci / 2] : 0));
                 indexed_here += hi - lo;
             }
             if (world > 1) {

@@ -153,14 +153,14 @@ def main():
     ctx = commet_b200.Context(local_rank)
     n_ref, L, k, t, nq = args.ref_reads, args.length, args.k, args.t, args.query_reads
 
+    ctl = dist.new_group(backend="gloo") if world > 1 else None      # host-side control messages of a few bytes
+
     def all_gather_bytes(b):
         if world == 1:
             return [b]
-        t_in = torch.frombuffer(bytearray(b), dtype=torch.uint8).to(dev)
-        out = torch.empty(world * len(b), dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(out, t_in)
-        raw = out.cpu().numpy().tobytes()
-        return [raw[i * len(b):(i + 1) * len(b)] for i in range(world)]
+        out = [None] * world
+        dist.all_gather_object(out, b, group=ctl)
+        return out
 
     def all_gather_obj(obj):
         if world == 1:
@@ -171,8 +171,7 @@ def main():
 
     def barrier():
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            dist.barrier(group=ctl)
 
     info, res = run_c4(torch, ctx, dev, world, rank, barrier, all_gather_bytes, n_ref, args.query_sets, nq, L, k, t)
     dt = info["seconds"]

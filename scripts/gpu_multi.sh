@@ -36,3 +36,15 @@ if [ "$c3" = "c3" ]; then
   timeout 900 python scripts/bench_nxn.py --sets 10 --reads 20000000 --gpus $N --reps 1 --out $out/${tag}_nxn_c3_full_${N}gpu.json > $out/${tag}_nxn_c3_${N}gpu.log 2>&1
   echo "c3 n$N rc=$?"; python -c "import json;d=json.load(open('$out/${tag}_nxn_c3_full_${N}gpu.json'));print(d['commet_nxn_run0']['wall_s'], d['commet_nxn_run0']['seconds_at_end_of'], d['generate_s'])" || tail -5 $out/${tag}_nxn_c3_${N}gpu.log
 fi
+if [ "$N" = "2" ] || [ "$N" = "8" ]; then
+  timeout 300 python scripts/group_bench.py --gpus $N > $out/${tag}_group_n$N.json 2> $out/${tag}_group_n$N.err; echo "group n$N rc=$?"; cat $out/${tag}_group_n$N.json
+fi
+if [ "$N" = "2" ]; then
+  # single-pass metrics (no kernel replay: the kernels write peer memory) of the NVLink kernels in the one-process group
+  timeout 600 ncu --metrics gpu__time_duration.sum,nvlrx__bytes.sum,nvltx__bytes.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+      -k regex:'k_owner_apply|k_gather_slices|k_owner_tiles|k_owner_fills|k_bin_scatter2' -c 24 --csv --log-file $out/${tag}_ncu_nvlink_n$N.csv \
+      python scripts/group_bench.py --gpus $N --steps 1 --warmup 1 > /dev/null 2> $out/${tag}_ncu_nvlink_n$N.err; echo "ncu nvlink rc=$?"; tail -12 $out/${tag}_ncu_nvlink_n$N.csv | cut -c1-300
+  COMMET_B200_DIST_MODE=merge timeout 600 ncu --metrics gpu__time_duration.sum,nvlrx__bytes.sum,nvltx__bytes.sum --clock-control none \
+      -k regex:'k_merge_peers' -c 4 --csv --log-file $out/${tag}_ncu_merge_n$N.csv \
+      python scripts/group_bench.py --gpus $N --steps 1 --warmup 1 > /dev/null 2> $out/${tag}_ncu_merge_n$N.err; echo "ncu merge rc=$?"; tail -6 $out/${tag}_ncu_merge_n$N.csv | cut -c1-300
+fi

@@ -171,8 +171,10 @@ def test_index_and_search_chunk_loop(ctx, seed):
 def test_chunk_loop_over_uploaded_parts(ctx, seed, monkeypatch):
     """Host index sets are uploaded in three parts (20/30/50 % of the bases) that are inserted while the next
     one crosses PCIe: chunk boundaries and the fetched-and-lost read must come out the same wherever they fall
-    relative to the part boundaries (inside a part, on its last read, on the first read of the next part)."""
+    relative to the part boundaries (inside a part, on its last read, on the first read of the next part).  Large query
+    sets are uploaded and searched in up to four parts cut at multiples of 32 reads (forced small here too)."""
     monkeypatch.setenv("COMMET_B200_PART_BYTES", str(int(np.random.default_rng(seed).integers(50, 3000))))
+    monkeypatch.setenv("COMMET_B200_QUERY_PART_BYTES", str(int(np.random.default_rng(seed + 100).integers(40, 4000))))
     rng = np.random.default_rng(9000 + seed)
     k = int(rng.integers(8, 19))
     t = int(rng.integers(1, 3))
@@ -182,7 +184,7 @@ def test_chunk_loop_over_uploaded_parts(ctx, seed, monkeypatch):
     total_kmers = sum(max(0, len(r) - k + 1) for r in ref)
     # from "never reached" to dozens of chunks, including limits that land exactly on a read's last k-mer
     maxk = [None, max(1, total_kmers // 2), max(1, total_kmers // 7), max(1, total_kmers // 40), 1][seed % 5]
-    queries = [H.make_query_set(rng, ref, int(rng.integers(1, 300)), max(1, L - 10), L + 10, **DIRT[seed % 3])
+    queries = [H.make_query_set(rng, ref, int(rng.integers(1, 600)), max(1, L - 10), L + 10, **DIRT[seed % 3])
                for _ in range(2)]
     exp_tags, exp = oracle.index_and_search(k, t, H.to_stream(ref), [H.to_stream(q) for q in queries], maxk)
     tags, info = ctx.index_and_search(k, t, H.to_stream(ref), [H.to_stream(q) for q in queries], maxk)
