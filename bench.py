@@ -489,9 +489,10 @@ def main():
         ctl = dist.new_group(backend="gloo")
 
         def all_gather_bytes(b):
-            out = [None] * world
-            dist.all_gather_object(out, b, group=ctl)
-            return out
+            t_in = torch.frombuffer(bytearray(b), dtype=torch.uint8)
+            outs = [torch.empty(len(b), dtype=torch.uint8) for _ in range(world)]
+            dist.all_gather(outs, t_in, group=ctl)
+            return [o.numpy().tobytes() for o in outs]
 
         def ctl_barrier():
             dist.barrier(group=ctl)

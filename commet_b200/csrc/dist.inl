@@ -387,9 +387,10 @@ extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_
         CKR(dist_plan(d, shard, n_global, block, max_kmer, plan, chunk_kmers));
     }
     const size_t n_chunks = plan.size() / 2;
-    // ---- how the chunks' filters are built: owner-applied records (kernels.cuh) when the regions deal evenly over the
-    // ranks and every rank's records of a chunk fit the 32-bit record counters; else every rank builds a partial
-    // filter and the partials are merged (k_merge_peers).  The decision is taken on exchanged numbers: the same everywhere.
+    // ---- how the chunks' filters are built: owner-applied records (kernels.cuh) when the filter has at least one 32 MiB
+    // region per rank and every rank's records of a chunk fit the 32-bit record counters; else every rank builds a
+    // partial filter and the partials are merged (k_merge_peers).  The decision is taken on exchanged numbers: the same
+    // everywhere.
     bool owner_mode = false;
     uint32_t max_q = 0;
     const int n_bins = k >= kRecKeyBits + 2 && k - kRecKeyBits <= 9 ? 1 << (k - kRecKeyBits) : 0;
@@ -406,7 +407,7 @@ extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_
         int form = c->insert_form;
         if (const char *e = getenv("COMMET_B200_INSERT")) form = atoi(e);
         owner_mode = !(mode && std::string(mode) == "merge") && c->binned_index && !c->region_passes && form == 2 && n_bins >= 2 &&
-                     k >= 28 && n_bins % (int)world == 0 && 4 * any_max < 0xE0000000ull && chunk_max > 0;
+                     k >= 28 && n_bins >= (int)world && 4 * any_max < 0xE0000000ull && chunk_max > 0;
         if (owner_mode) {
             CKR(dist_connect_insert(d, n_bins, 4 * mine_max + 64, &max_q));
             tile_bound = 4 * chunk_max / 2048 + (uint64_t)n_bins + 1;
@@ -440,22 +441,23 @@ extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_
         CK(cudaEventCreateWithFlags(&ev_gather, cudaEventDisableTiming));
         CKR(prepare(c, shard, k));
     }
-    const int n_own = owner_mode ? n_bins / (int)world : 0, b_first = n_own * (int)rank;
-    const uint64_t slice_bytes = owner_mode ? filter_bytes / world : 0;
+    DevBuf meta_buf(c);                        // own_bins[512] | fills[512] | tbase[513] | gather list[512]
+    if (owner_mode && meta_buf.alloc(2049 * sizeof(uint32_t)) != cudaSuccess) return fail("allocation of the owner tables failed");
+    std::vector<uint32_t> h_fills((size_t)world * std::max(n_bins, 1)), h_meta(2049);
+    const uint64_t region_bytes = 1ull << kRegionLog2;
     for (size_t ci = 0; ci + 1 < plan.size(); ci += 2) {
         const uint64_t lo = local_index(plan[ci], world, rank, block), hi = local_index(plan[ci + 1], world, rank, block);
         if (owner_mode) {
-            uint32_t *fills = c->bins2 + 1100, *tbase = c->bins2 + 512;
+            uint32_t *d_own = meta_buf.as<uint32_t>(), *d_fills = d_own + 512, *d_tbase = d_own + 1024, *d_glist = d_own + 1537;
             unsigned long long *tile_counter = c->bins + 1700;
             if (ci > 0) {
-                // my slice of the previous chunk is still being pulled by the peers: nobody clears before everybody has it
+                // my regions of the previous chunk are still being pulled by the peers: nobody clears before everybody has them
                 CK(cudaEventSynchronize(ev_gather));
                 sw.lap_ns();
                 if (cm.barrier(cm.user) != 0) return fail("barrier failed");
                 ns_wait += sw.lap_ns();
             }
             sw.lap_ns();
-            CK(cudaMemsetAsync(reinterpret_cast<uint8_t *>(c->filter) + slice_bytes * rank, 0, slice_bytes, c->stream));
             uint64_t hb[2] = {0, 0};
             if (hi > lo) {
                 CK(cudaMemcpyAsync(&hb[0], shard->offs + lo, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
@@ -471,27 +473,72 @@ extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_
             ns_index += sw.lap_ns();
             if (cm.barrier(cm.user) != 0) return fail("barrier failed");      // ... and so are everybody else's
             ns_wait += sw.lap_ns();
+            // ---- the regions are dealt by their record counts: every rank reads every rank's counters (n_bins numbers each)
+            // and computes the same assignment -- largest region first, to the rank with the fewest records so far
+            for (int p = 0; p < cm.world; p++)
+                CK(cudaMemcpyAsync(h_fills.data() + (size_t)p * n_bins, pi.fill[p], (size_t)n_bins * sizeof(uint32_t), cudaMemcpyDefault, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            std::vector<uint64_t> tot(n_bins, 0), load(world, 0);
+            for (int b = 0; b < n_bins; b++)
+                for (int p = 0; p < cm.world; p++) tot[b] += h_fills[(size_t)p * n_bins + b];
+            std::vector<int> order(n_bins), owner(n_bins, 0);
+            for (int b = 0; b < n_bins; b++) order[b] = b;
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tot[x] > tot[y]; });
+            for (int b : order) {
+                int best = 0;
+                for (int p = 1; p < cm.world; p++)
+                    if (load[p] < load[best]) best = p;
+                owner[b] = best;
+                load[best] += tot[b] + 1;                  // + 1: empty regions are dealt evenly too
+            }
+            uint32_t n_own = 0, n_list = 0;
+            for (int b = 0; b < n_bins; b++)
+                if (owner[b] == cm.rank) h_meta[n_own++] = (uint32_t)b;
+            const uint32_t n_pairs = n_own * (uint32_t)world;
+            uint32_t acc = 0;
+            for (uint32_t i = 0; i < n_own; i++)
+                for (int p = 0; p < cm.world; p++) {
+                    const uint32_t f = h_fills[(size_t)p * n_bins + h_meta[i]];
+                    h_meta[512 + i * world + p] = f;
+                    h_meta[1024 + i * world + p] = acc;
+                    acc += (f + 2047) / 2048;
+                }
+            h_meta[1024 + n_pairs] = acc;
+            if (acc > tile_bound) return fail("tile list too small (%u tiles, room for %llu)", acc, (unsigned long long)tile_bound);
+            // the regions to pull, round-robin over their owners (concurrent pieces come from different peers)
+            {
+                std::vector<std::vector<uint32_t>> by_owner(world);
+                for (int b = 0; b < n_bins; b++)
+                    if (owner[b] != cm.rank) by_owner[owner[b]].push_back((uint32_t)b | ((uint32_t)owner[b] << 16));
+                for (size_t j = 0;; j++) {
+                    bool any = false;
+                    for (uint64_t p = 0; p < world; p++)
+                        if (j < by_owner[p].size()) { h_meta[1537 + n_list++] = by_owner[p][j]; any = true; }
+                    if (!any) break;
+                }
+            }
+            CK(cudaMemcpyAsync(d_own, h_meta.data(), 2049 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemsetAsync(tile_counter, 0, sizeof(unsigned long long), c->stream));
+            for (uint32_t i = 0; i < n_own; i++)
+                CK(cudaMemsetAsync(reinterpret_cast<uint8_t *>(c->filter) + (uint64_t)h_meta[i] * region_bytes, 0, region_bytes, c->stream));
             // the records of MY regions, from every rank's slabs (peer reads over NVLink inside the apply kernel)
-            k_owner_fills<2048><<<1, 512, 0, c->stream>>>(pi, cm.world, b_first, n_bins, fills, tbase, tile_counter);
-            k_owner_tiles<2048><<<c->sm_count * 4, 256, 0, c->stream>>>(pi, cm.world, cm.rank, b_first, n_bins, fills, tbase, tiles_buf.as<OwnerTile>());
-            k_owner_apply<2048, true><<<c->sm_count * env_or("COMMET_B200_APPLY_BPS", 8), 256, 0, c->stream>>>(
-                c->filter, tiles_buf.as<OwnerTile>(), tbase, n_bins, b_first + n_own - 1, tile_counter);
-            c->launches += 3;
-            CK(cudaGetLastError());
-            CK(cudaStreamSynchronize(c->stream));          // my slice is final ...
+            if (acc) {
+                k_owner_tiles<2048><<<c->sm_count * 4, 256, 0, c->stream>>>(pi, cm.world, cm.rank, d_own, (int)n_pairs, d_fills, d_tbase, tiles_buf.as<OwnerTile>());
+                k_owner_apply<2048, true><<<c->sm_count * env_or("COMMET_B200_APPLY_BPS", 8), 256, 0, c->stream>>>(
+                    c->filter, tiles_buf.as<OwnerTile>(), d_tbase, (int)n_pairs, tile_counter);
+                c->launches += 2;
+                CK(cudaGetLastError());
+            }
+            CK(cudaStreamSynchronize(c->stream));          // my regions are final ...
             ns_index += sw.lap_ns();
-            if (cm.barrier(cm.user) != 0) return fail("barrier failed");      // ... and so is everybody else's
+            if (cm.barrier(cm.user) != 0) return fail("barrier failed");      // ... and so are everybody else's
             ns_wait += sw.lap_ns();
             CKR(t_gather.begin(c->stream));
-            const uint64_t n_slice = slice_bytes / 16;
-            const unsigned gg = grid_for(c, n_slice, 256, 8);
-            switch (cm.world) {
-            case 2: k_gather_slices<2><<<gg, 256, 0, c->stream>>>(pf, cm.rank, n_slice); break;
-            case 4: k_gather_slices<4><<<gg, 256, 0, c->stream>>>(pf, cm.rank, n_slice); break;
-            default: k_gather_slices<8><<<gg, 256, 0, c->stream>>>(pf, cm.rank, n_slice); break;
+            if (n_list) {
+                k_gather_regions<<<c->sm_count * 8, 256, 0, c->stream>>>(pf, cm.rank, d_glist, n_list, (uint32_t)(region_bytes / 16));
+                c->launches++;
+                CK(cudaGetLastError());
             }
-            c->launches++;
-            CK(cudaGetLastError());
             CKR(t_gather.end(c->stream));
             CK(cudaEventRecord(ev_gather, c->stream));
         } else {

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "commet_b200.h"
@@ -51,17 +52,44 @@ struct PassResult {
 struct Engine {
     commet_ctx *ctx = nullptr;
     commet_group *group = nullptr;
+    std::thread warm;                       // creates the context of the first device while the read files are parsed
+    commet_ctx *warm_ctx = nullptr;
+    std::string warm_err;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
 
-    bool open(uint64_t total_bases)
+    void mark(const char *what) const       // COMMET_B200_TRACE=1: wall clock of the tool's stages on stderr
+    {
+        if (!getenv("COMMET_B200_TRACE")) return;
+        std::cerr << "[commet tool] +" << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()
+                  << " ms " << what << "\n";
+    }
+    static std::vector<int> named_devices()
     {
         std::vector<int> devices;
-        if (const char *e = getenv("COMMET_B200_DEVICES")) {
+        if (const char *e = getenv("COMMET_B200_DEVICES"))
             for (const char *p = e; *p;) {
                 devices.push_back(atoi(p));
                 while (*p && *p != ',') p++;
                 if (*p == ',') p++;
             }
-        } else {
+        return devices;
+    }
+    // CUDA initialisation and the context of the first device take a few hundred milliseconds: started before the
+    // files are read, joined by open()
+    void prewarm()
+    {
+        std::vector<int> named = named_devices();
+        const int dev = named.empty() ? 0 : named[0];
+        warm = std::thread([this, dev]() {
+            if (commet_ctx_create(dev, &warm_ctx) != 0) warm_err = commet_last_error();
+        });
+    }
+    bool open(uint64_t total_bases)
+    {
+        if (warm.joinable()) warm.join();
+        mark("context of the first device ready");
+        std::vector<int> devices = named_devices();
+        if (devices.empty()) {
             int want = 1;
             const int visible = commet_device_count();
             const char *e2 = getenv("COMMET_B200_GPUS");
@@ -71,15 +99,23 @@ struct Engine {
             want = std::max(1, std::min(std::min(want, visible), 8));
             for (int i = 0; i < want; i++) devices.push_back(i);
         }
-        if (devices.size() > 1) return commet_group_create(devices.data(), (int)devices.size(), &group) == 0;
+        if (devices.size() > 1) {
+            if (warm_ctx) { commet_ctx_destroy(warm_ctx); warm_ctx = nullptr; }      // the group creates its own contexts
+            return commet_group_create(devices.data(), (int)devices.size(), &group) == 0;
+        }
+        if (warm_ctx) { ctx = warm_ctx; warm_ctx = nullptr; return true; }
+        if (!warm_err.empty()) return commet_ctx_create(devices.empty() ? 0 : devices[0], &ctx) == 0;   // repeats the failure: sets the message in this thread
         return commet_ctx_create(devices.empty() ? 0 : devices[0], &ctx) == 0;
     }
     void close()
     {
+        if (warm.joinable()) warm.join();
+        if (warm_ctx) commet_ctx_destroy(warm_ctx);
         if (group) commet_group_destroy(group);
         if (ctx) commet_ctx_destroy(ctx);
         group = nullptr;
         ctx = nullptr;
+        warm_ctx = nullptr;
     }
 };
 

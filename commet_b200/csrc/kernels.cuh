@@ -1953,13 +1953,15 @@ k_merge_peers(PeerFilters pf, int me, uint64_t v0, uint64_t v1)
 
 // ------------------------------- multi-GPU: owner-applied insert + slice all-gather ----
 // Merging whole partial filters moves 2 (G-1)/G F bytes per GPU and direction (reduce-scatter + all-gather of the OR).
-// The reduce-scatter half is avoidable: what a rank contributes to a slice of the filter is not a dense slice but
+// The reduce-scatter half is avoidable: what a rank contributes to a part of the filter is not a dense slice but
 // the RECORDS of its reads that fall into it -- (G-1)/G of 16 bytes per k-mer instead of (G-1)/G F.  So the filter's
-// regions are dealt to the ranks (rank r owns regions [r n_bins/G, (r+1) n_bins/G) = slice r of the filter); every rank
-// scatters the records of ITS reads into its own slabs, as on one GPU; then every owner applies the records of ITS
-// regions from ALL ranks' slabs -- the record tiles of the peers are read straight out of their memory over NVLink by
-// the apply kernel itself (no copy pass, the link transfer overlaps the RED.OR) -- and sweeps only its own F/G bytes
-// through L2; finally every rank pulls the finished slices of the others (k_gather_slices).
+// 32 MiB regions are dealt to the ranks; every rank scatters the records of ITS reads into its own slabs, as on one
+// GPU; then every owner applies the records of ITS regions from ALL ranks' slabs -- the record tiles of the peers are
+// read straight out of their memory over NVLink by the apply kernel itself (no copy pass, the link transfer overlaps
+// the RED.OR) -- and sweeps only its own regions through L2; finally every rank pulls the finished regions of the
+// others (k_gather_regions).  The regions are dealt by their record counts (largest first to the least loaded
+// rank, computed identically by every rank from the exchanged counters): key d = a|b piles 13 % of its records
+// into the all-ones region, and real reads are worse, so equal SHARES of the regions are not equal shares of the work.
 struct PeerInsert {
     const uint32_t *recs[kMaxPeers];      // slab pools
     const uint32_t *fill[kMaxPeers];      // records per region
@@ -1972,42 +1974,15 @@ struct OwnerTile {
     uint32_t bin;                         // region (global index)
     uint32_t rt, rn;                      // tile index inside the region, tiles of the region (all sources)
     uint32_t next_fill;                   // records of the next owned region (decides whether it is prefetched)
-    uint32_t pad;
+    uint32_t next_bin;                    // the next owned region (~0: none)
 };
 
-// pairs e = i * world + s (owned region i, source rank s), region-major: fills[e], tbase[e] (first tile), tbase[n_pairs]
-template <int TILE>
-__global__ void __launch_bounds__(512)
-k_owner_fills(PeerInsert pi, int world, int b_first, int n_pairs, uint32_t *__restrict__ fills, uint32_t *__restrict__ tbase,
-              unsigned long long *__restrict__ tile_counter)
-{
-    __shared__ uint32_t wsum[16];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t f = 0;
-    if ((int)tid < n_pairs) f = pi.fill[tid % world][b_first + tid / world];
-    const uint32_t c = (f + TILE - 1) / TILE;
-    uint32_t incl = c;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= (uint32_t)d) incl += v;
-    }
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    uint32_t off = 0;
-    for (uint32_t w = 0; w < warp; w++) off += wsum[w];
-    if ((int)tid < n_pairs) {
-        fills[tid] = f;
-        tbase[tid] = off + incl - c;
-        if ((int)tid == n_pairs - 1) tbase[n_pairs] = off + incl;
-    }
-    if (tid == 0) *tile_counter = 0;
-}
-
-// one thread per tile: where its records are (the slab id is looked up in the source's table, over NVLink for a peer)
+// one thread per tile: where its records are (the slab id is looked up in the source's table, over NVLink for a peer).
+// pairs e = i * world + s (i-th owned region own_bins[i], source rank s), region-major; fills[e] = records of the pair,
+// tbase[e] = its first tile, tbase[n_pairs] = number of tiles -- computed on the host from the ranks' counters.
 template <int TILE>
 __global__ void __launch_bounds__(256)
-k_owner_tiles(PeerInsert pi, int world, int me, int b_first, int n_pairs, const uint32_t *__restrict__ fills,
+k_owner_tiles(PeerInsert pi, int world, int me, const uint32_t *__restrict__ own_bins, int n_pairs, const uint32_t *__restrict__ fills,
               const uint32_t *__restrict__ tbase, OwnerTile *__restrict__ tiles)
 {
     const uint32_t n_tiles = tbase[n_pairs];
@@ -2017,20 +1992,23 @@ k_owner_tiles(PeerInsert pi, int world, int me, int b_first, int n_pairs, const 
             const int mid = (lo + hi + 1) >> 1;
             if (tbase[mid] <= t) lo = mid; else hi = mid - 1;
         }
-        const int e = lo, i = e / world, s = e % world, bin = b_first + i;
+        const int e = lo, i = e / world, s = e % world;
+        const uint32_t bin = own_bins[i];
         const uint32_t lt = t - tbase[e], v0 = lt * TILE;
         const uint32_t slab = pi.table[s][(size_t)bin * pi.max_q[s] + (v0 >> kSlabLog2)] - 1u;
         OwnerTile o;
         o.src = pi.recs[s] + (((size_t)slab << kSlabLog2) + (v0 & (kSlabRecs - 1)));
         o.n = min((uint32_t)TILE, fills[e] - v0) | (s != me ? 0x80000000u : 0u);
-        o.bin = (uint32_t)bin;
+        o.bin = bin;
         o.rt = t - tbase[i * world];
         o.rn = tbase[(i + 1) * world] - tbase[i * world];
         uint32_t nf = 0;
-        if ((i + 1) * world < n_pairs)
+        o.next_bin = 0xFFFFFFFFu;
+        if ((i + 1) * world < n_pairs) {
             for (int q = 0; q < world; q++) nf += fills[(i + 1) * world + q];
+            o.next_bin = own_bins[i + 1];
+        }
         o.next_fill = nf;
-        o.pad = 0;
         tiles[t] = o;
     }
 }
@@ -2038,7 +2016,7 @@ k_owner_tiles(PeerInsert pi, int world, int me, int b_first, int n_pairs, const 
 template <int TILE, bool PREFETCH>
 __global__ void __launch_bounds__(256)
 k_owner_apply(uint32_t *__restrict__ filter, const OwnerTile *__restrict__ tiles, const uint32_t *__restrict__ tbase, int n_pairs,
-              int b_last, unsigned long long *__restrict__ tile_counter)
+              unsigned long long *__restrict__ tile_counter)
 {
     constexpr int U = TILE / (256 * 4);
     __shared__ unsigned long long s_next;
@@ -2062,10 +2040,10 @@ k_owner_apply(uint32_t *__restrict__ filter, const OwnerTile *__restrict__ tiles
             v[it] = make_uint4(0u, 0u, 0u, 0u);
             if (e < n_here) v[it] = remote ? ld_peer_u4(src + (it * 256 + threadIdx.x)) : ld_stream_u4(src + (it * 256 + threadIdx.x), pol);
         }
-        if (PREFETCH && (int)o.bin < b_last && o.next_fill >= (1u << (kRegionLog2 - 8))) {
+        if (PREFETCH && o.next_bin != 0xFFFFFFFFu && o.next_fill >= (1u << (kRegionLog2 - 8))) {
             const uint32_t lines = 1u << (kRegionLog2 - 7);
             const uint32_t l0 = (uint32_t)((uint64_t)lines * o.rt / o.rn), l1 = (uint32_t)((uint64_t)lines * (o.rt + 1) / o.rn);
-            const char *nxt_region = reinterpret_cast<const char *>(filter) + ((uint64_t)(o.bin + 1) << kRegionLog2);
+            const char *nxt_region = reinterpret_cast<const char *>(filter) + ((uint64_t)o.next_bin << kRegionLog2);
             for (uint32_t l = l0 + threadIdx.x; l < l1; l += 256)
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(nxt_region + ((uint64_t)l << 7)));
         }
@@ -2088,21 +2066,27 @@ k_owner_apply(uint32_t *__restrict__ filter, const OwnerTile *__restrict__ tiles
     }
 }
 
-// every rank pulls the finished slices of the other owners into its own filter: G-1 peer loads in flight per thread
-template <int G>
+// every rank pulls the finished regions of the other owners into its own filter.  list[j] = region | owner << 16; the
+// work is cut into pieces of kGatherPiece vectors dealt round-robin over the list, so that the blocks running at any
+// time pull from different peers
+constexpr uint32_t kGatherPiece = 2048;                    // 16-byte vectors per piece (32 KiB)
 __global__ void __launch_bounds__(256)
-k_gather_slices(PeerFilters pf, int me, uint64_t n_slice)         // n_slice: 16-byte vectors per slice
+k_gather_regions(PeerFilters pf, int me, const uint32_t *__restrict__ list, uint32_t n_list, uint32_t region_vecs)
 {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t pieces_per_region = region_vecs / kGatherPiece;
+    const uint64_t n_pieces = (uint64_t)pieces_per_region * n_list;
     uint4 *mine = pf.f[me];
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slice; i += stride) {
-        uint4 part[G];
+    for (uint64_t pc = blockIdx.x; pc < n_pieces; pc += gridDim.x) {
+        const uint32_t j = (uint32_t)(pc % n_list), part = (uint32_t)(pc / n_list);
+        const uint32_t ent = list[j];
+        const uint64_t v0 = (uint64_t)(ent & 0xFFFFu) * region_vecs + (uint64_t)part * kGatherPiece;
+        const uint4 *src = pf.f[ent >> 16] + v0;
+        uint4 *dst = mine + v0;
+        uint4 part_v[kGatherPiece / 256];
 #pragma unroll
-        for (int p = 0; p < G; p++)
-            if (p != me) part[p] = ld_peer_u4(pf.f[p] + (uint64_t)p * n_slice + i);
+        for (int u = 0; u < (int)(kGatherPiece / 256); u++) part_v[u] = ld_peer_u4(src + u * 256 + threadIdx.x);      // 8 peer loads in flight
 #pragma unroll
-        for (int p = 0; p < G; p++)
-            if (p != me) mine[(uint64_t)p * n_slice + i] = part[p];
+        for (int u = 0; u < (int)(kGatherPiece / 256); u++) dst[u * 256 + threadIdx.x] = part_v[u];
     }
 }
 

@@ -119,6 +119,8 @@ int main(int argc, char **argv)
 
     ensure_dir(log_path);
     ensure_dir(out_path);
+    Engine ctx;
+    ctx.prewarm();                   // CUDA comes up while the read files are parsed
 
     // ---- sets, src/index_and_search.cpp:196-234 ------------------------------
     std::map<std::string, SetSpec> index_specs = read_sets(index_file_list);
@@ -150,7 +152,7 @@ int main(int argc, char **argv)
 
     uint64_t total_bases = index_set.bases.size();
     for (auto &s : search_sets) total_bases += s->bases.size();
-    Engine ctx;
+    ctx.mark("read sets parsed, valid-read streams built");
     if (!ctx.open(total_bases)) {
         std::cerr << "index_and_search: " << commet_last_error() << "\n";
         return 1;
@@ -160,6 +162,7 @@ int main(int argc, char **argv)
     std::vector<ReadSet *> queries;
     for (auto &s : search_sets) queries.push_back(s.get());
     PassResult r1 = run_pass(ctx, kmer_size, min_hits, max_kmer, index_set, queries, true);
+    ctx.mark("first pass done");
     for (size_t s = 0; s < queries.size(); s++) {
         std::cout << "\n------------------------------------------------------------------\n";
         std::cout << "Reads from {" << queries[s]->nickname << "} present in raw {" << index_set.nickname << "}\n";
@@ -220,9 +223,11 @@ int main(int argc, char **argv)
         log_file.close();
     }
 
-    ctx.close();
-
+    ctx.mark("passes done");
     // ---- outputs, :397-399 ------------------------------------------------------
     for (auto &s : search_sets) s->save_bv(out_path, index_specs.begin()->first);
+    ctx.mark("vectors written");
+    ctx.close();
+    ctx.mark("device released");
     return 0;
 }

@@ -158,9 +158,10 @@ def main():
     def all_gather_bytes(b):
         if world == 1:
             return [b]
-        out = [None] * world
-        dist.all_gather_object(out, b, group=ctl)
-        return out
+        t_in = torch.frombuffer(bytearray(b), dtype=torch.uint8)
+        outs = [torch.empty(len(b), dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(outs, t_in, group=ctl)
+        return [o.numpy().tobytes() for o in outs]
 
     def all_gather_obj(obj):
         if world == 1:

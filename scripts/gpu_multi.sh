@@ -16,11 +16,10 @@ try:
 except Exception as e: print('no line', e); print(open('$out/${tag}_bench_n$N.err').read()[-1500:])
 PY
 if [ "$N" = "8" ]; then
-  BENCH_NUMA_BIND=0 timeout 400 $TR 29512 bench.py --gpus $N --steps 5 --warmup 3 > $out/${tag}_bench_n${N}_nonuma.json 2> $out/${tag}_bench_n${N}_nonuma.err
   COMMET_B200_DIST_MODE=merge timeout 400 $TR 29513 bench.py --gpus $N --steps 5 --warmup 3 > $out/${tag}_bench_n${N}_mergemode.json 2> $out/${tag}_bench_n${N}_mergemode.err
   python - <<PY
 import json
-for f in ('nonuma','mergemode'):
+for f in ('mergemode',):
     try:
         d=json.load(open('$out/${tag}_bench_n${N}_%s.json' % f)); print(f, d['ms_per_step'], d.get('dist_mode'), d.get('phases_ms_rank0'), d['e2e']['ms_per_step'])
     except Exception as e: print(f, 'no line', e)
