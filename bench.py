@@ -592,11 +592,16 @@ def main():
         tags_d.zero_()
         torch.cuda.current_stream().synchronize()
         idx = ctx.stage_async(ref_loc_h.numpy(), offs_loc_h)
-        q = ctx.stage_async(qry_h.numpy(), offs_h)
-        r = dd.index_and_search(t, idx, n, [q], [tags_d.data_ptr()], block=BLOCK)
+        # the query set goes up in four parts cut at multiples of 32 reads (disjoint tag words), as commet_index_and_search
+        # does with host sets: the search of a part runs while the next one crosses PCIe
+        cuts = [(n * i // 4) & ~31 for i in range(4)] + [n]
+        qs = [ctx.stage_async(qry_h.numpy()[a * L:b * L], offs_h[:b - a + 1]) for a, b in zip(cuts[:-1], cuts[1:])]
+        r = dd.index_and_search(t, idx, n, qs, [tags_d.data_ptr() + 4 * (a // 32) for a in cuts[:-1]], block=BLOCK)
         tags_h.copy_(tags_d.view(torch.uint8)[:n // 8 + 1])
-        idx.free(); q.free()
-        return r["shared"][0]
+        idx.free()
+        for q in qs:
+            q.free()
+        return sum(r["shared"])
 
     for _ in range(max(1, args.warmup)):
         step_e2e()
@@ -646,6 +651,8 @@ def main():
         ceil = random_sector_ceiling(1 << (k - 1))
         line["roofline"] = {"bound": "hbm", "kernel": "k_search", "achieved": ach, "peak": peak, "unit": "GB/s",
                             "frac": ach / peak, "traffic": ncu, "peak_source": peak_src,
+                            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_search launch of this workload in the committed "
+                                              "ncu --set full capture (profiles/ncu_traffic.json), not measured in this run",
                             "algorithmic": f"{probes['tests']} filter bit tests x 32 B sector per launch",
                             "ms_per_launch": srch_ms,
                             "random_sector_ceiling_GBps": ceil, "frac_of_random_sector_ceiling": (ach / ceil) if ceil else None,

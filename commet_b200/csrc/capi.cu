@@ -1641,6 +1641,7 @@ static int filter_run(commet_ctx *c, uint64_t n, int64_t min_len, int64_t max_N,
         DevBuf border(c);
         if (border.alloc((size_t)border_cap * sizeof(BorderRec)) != cudaSuccess) return fail("filter scratch allocation failed");
         CK(cudaMemsetAsync(nb.p, 0, sizeof(unsigned int), c->stream));
+        CK(cudaMemsetAsync(totals.p, 0, n_blocks * 4 * sizeof(unsigned int), c->stream));
         launch((unsigned)n_blocks, fp, n_bv_words, classes.as<uint8_t>(), totals.as<unsigned int>(), border.as<BorderRec>(),
                border_cap, nb.as<unsigned int>());
         c->launches++;
@@ -1742,8 +1743,8 @@ extern "C" int commet_filter_reads_dev(commet_ctx *c, const uint8_t *d_bases, co
     return filter_run(c, n_reads, min_len, max_N, min_shannon, max_reads, d_bv, counters,
                       [&](unsigned n_blocks, const FilterParams &fp, uint64_t n_bv_words, uint8_t *classes, unsigned int *totals,
                           BorderRec *border, unsigned int border_cap, unsigned int *nb) {
-                          k_stage_filter<false><<<n_blocks, 256, 0, c->stream>>>(d_bases, readable, n_bases, d_offs, n_reads, nullptr, fp, d_bv,
-                                                                                 n_bv_words, classes, totals, border, border_cap, nb);
+                          k_stage_filter<false><<<n_blocks * (kFilterBlock / kSF2Threads), kSF2Threads, kSF2TileWords * 12, c->stream>>>(
+                                  d_bases, readable, n_bases, d_offs, n_reads, nullptr, fp, d_bv, n_bv_words, classes, totals, border, border_cap, nb);
                       });
 }
 
@@ -1763,8 +1764,8 @@ extern "C" int commet_reads_from_device_filtered(commet_ctx *c, const uint8_t *d
     int rc = filter_run(c, n_reads, min_len, max_N, min_shannon, max_reads, d_bv, counters,
                         [&](unsigned n_blocks, const FilterParams &fp, uint64_t n_bv_words, uint8_t *classes, unsigned int *totals,
                             BorderRec *border, unsigned int border_cap, unsigned int *nb) {
-                            k_stage_filter<true><<<n_blocks, 256, 0, c->stream>>>(d_bases, readable, n_bases, d_offs, n_reads, r->planes, fp,
-                                                                                  d_bv, n_bv_words, classes, totals, border, border_cap, nb);
+                            k_stage_filter<true><<<n_blocks * (kFilterBlock / kSF2Threads), kSF2Threads, kSF2TileWords * 12, c->stream>>>(
+                                    d_bases, readable, n_bases, d_offs, n_reads, r->planes, fp, d_bv, n_bv_words, classes, totals, border, border_cap, nb);
                         });
     if (rc != 0) { commet_reads_free(r); return rc; }
     *out = r;

@@ -7,7 +7,9 @@
 #include <chrono>
 #include <cstdlib>
 #include <algorithm>
+#include <fstream>
 #include <iostream>
+#include <map>
 #include <string>
 #include <thread>
 #include <vector>
@@ -29,12 +31,57 @@ inline void ensure_dir(const std::string &path)        // src/index_and_search.c
     }
 }
 
-inline void load_set(ReadSet &set, const SetSpec &spec)
+// The search sets' large plain-FASTA files parsed by a background thread while the main thread loads the index set
+// (the reference loads them one after the other, src/index_and_search.cpp:196-234).  Only the silent fast path runs
+// ahead (fast_fasta.hpp); anything else -- other formats, unreadable files, a malformed fof -- is left to the main
+// thread, which reports it where the reference would.
+struct ParseAhead {
+    std::thread th;
+    std::map<std::string, ParsedFile> done;
+
+    void start(const std::string &fof)
+    {
+        th = std::thread([this, fof]() {
+            std::ifstream in(fof.c_str());
+            std::string line;
+            while (in.good() && std::getline(in, line)) {
+                const size_t colon = line.find(':');
+                if (colon == std::string::npos) continue;
+                std::string rest = line.substr(colon + 1);
+                size_t p = 0;
+                while (p <= rest.size()) {
+                    size_t q = rest.find(';', p);
+                    if (q == std::string::npos) q = rest.size();
+                    std::string item = rest.substr(p, q - p);
+                    const size_t comma = item.find(',');
+                    if (comma != std::string::npos) item = item.substr(0, comma);
+                    const size_t a = item.find_first_not_of(" \t\r"), b = item.find_last_not_of(" \t\r");
+                    if (a != std::string::npos) {
+                        const std::string fname = item.substr(a, b - a + 1);
+                        ParsedFile pf;
+                        pf.fname = fname;
+                        if (!done.count(fname) && parse_fasta_parallel(fname, pf)) done[fname] = std::move(pf);
+                    }
+                    p = q + 1;
+                }
+            }
+        });
+    }
+    ParsedFile *take(const std::string &fname)
+    {
+        if (th.joinable()) th.join();
+        auto it = done.find(fname);
+        return it == done.end() ? nullptr : &it->second;
+    }
+    ~ParseAhead() { if (th.joinable()) th.join(); }
+};
+
+inline void load_set(ReadSet &set, const SetSpec &spec, ParseAhead *ahead = nullptr)
 {
     for (size_t i = 0; i < spec.files.size(); i++) {
         if (spec.bvs[i].empty()) std::cout << "open " << spec.files[i] << "\n";
         else std::cout << "open " << spec.files[i] << "," << spec.bvs[i] << "\n";
-        set.add_file(spec.files[i], spec.bvs[i]);
+        set.add_file(spec.files[i], spec.bvs[i], ahead ? ahead->take(spec.files[i]) : nullptr);
     }
 }
 

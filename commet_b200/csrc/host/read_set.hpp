@@ -24,14 +24,15 @@ struct SetFile {
 struct ReadSet {
     std::string nickname;
     std::vector<SetFile> files;
-    std::vector<uint8_t> bases;         // valid-read stream
+    ByteVec bases;                      // valid-read stream
     std::vector<uint64_t> offs{0};
 
     uint64_t n_valid() const { return offs.size() - 1; }
 
     // FileManager::addFile (file_manager.h:117-222).  bv_name empty -> all reads valid.
     // Returns false if the file was ignored (message already printed).
-    bool add_file(const std::string &fname, const std::string &bv_name)
+    // `parsed`: the file's records if they were parsed ahead of time (pass.hpp: ParseAhead), else null
+    bool add_file(const std::string &fname, const std::string &bv_name, ParsedFile *parsed = nullptr)
     {
         SetFile sf;
         // file_manager.h:119-143: an unreadable file is reported by the first-byte probe ("file file" is the reference's
@@ -48,7 +49,9 @@ struct ReadSet {
             return false;
         }
         if (!readable) std::cerr << "Cannot open file file " << fname << " -> ignore\n";
-        if (!parse_reads_file(fname, sf.data, " -> ignore\n")) {
+        if (parsed && readable) {
+            sf.data = std::move(*parsed);
+        } else if (!parse_reads_file(fname, sf.data, " -> ignore\n")) {
             if (!readable) exit(1);
             return false;
         }
@@ -101,7 +104,7 @@ struct ReadSet {
                 }
             }
             if (!keep) {
-                std::vector<uint8_t>().swap(pf.seq);
+                ByteVec().swap(pf.seq);
                 std::vector<uint64_t>().swap(pf.off);
             }
         }

@@ -16,7 +16,9 @@
 #include <fstream>
 #include <iostream>
 #include <string>
+#include <memory>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "fast_fasta.hpp"
@@ -25,13 +27,24 @@ namespace commet_host {
 
 enum class Format { Fasta, Fastq, Unknown };
 
+// byte buffer whose resize() does not zero-fill: the parallel loader sizes the sequence buffer first and writes every
+// byte of it afterwards -- value-initialising a gigabyte on one core cost as much as parsing it on sixteen
+template <class T>
+struct DefaultInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = DefaultInitAlloc<U>; };
+    using std::allocator<T>::allocator;
+    template <class U> void construct(U *p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void *>(p)) U; }
+    template <class U, class... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+using ByteVec = std::vector<uint8_t, DefaultInitAlloc<uint8_t>>;
+
 struct ParsedFile {
     std::string fname;
     Format format = Format::Unknown;
     bool gz = false;
     uint64_t nb_reads = 0;            // the reference's count (bit-vector size)
     std::vector<uint64_t> off;        // nb_reads+1 offsets into seq
-    std::vector<uint8_t> seq;
+    ByteVec seq;
 };
 
 inline bool slurp_plain(const std::string &fname, std::string &out)
@@ -173,7 +186,7 @@ inline bool parse_fasta_parallel(const std::string &fname, ParsedFile &pf)
     parallel_for([&](size_t c) { m.pass<false>(c, nullptr, 0, nullptr, 0); });
     m.finish_scan();
     pf.seq.resize(m.n_bytes);
-    pf.off.assign(m.n_records + 1, 0);
+    pf.off.resize(m.n_records + 1);
     pf.off[m.n_records] = m.n_bytes;
     std::vector<uint64_t> pos(nc + 1, 0), rec(nc + 1, 0);
     for (size_t c = 0; c < nc; c++) { pos[c + 1] = pos[c] + m.bytes[c]; rec[c + 1] = rec[c] + m.records[c]; }

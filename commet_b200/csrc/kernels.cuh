@@ -1249,7 +1249,7 @@ __device__ __forceinline__ bool scan_both(const uint32_t *__restrict__ filter, c
 // BOTH: 0 = the reference's order (forward scan, then reverse); > 0 = one pass over both strands with BOTH
 // positions per strand and batch (scan_both)
 template <bool COUNT, int BOTH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_search(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
          const uint64_t *__restrict__ offs, uint64_t n_reads, int k, int t,
          uint32_t *__restrict__ tags, unsigned long long *__restrict__ counters,
@@ -1598,11 +1598,6 @@ k_filter(const uint4 *__restrict__ planes, const uint64_t *__restrict__ offs, ui
 // vector loads per 32-base word); its H/L/V bits are computed as k_encode does; the per-read A/C/G/T/other counts
 // are popcounts of those bits restricted to the read's range -- no per-byte counting at all; with PLANES the bits
 // are also stored as the stream's bit-planes, so a set that is filtered AND indexed is read from HBM once.
-// A group of 4 lanes owns a read and sweeps it 128 bytes at a time (lane g takes the 32-byte words w0+g, w0+g+4, ...
-// of the stream, aligned to the stream, not to the read); a word is STORED by the read that contains its first byte
-// (each word has exactly one such read), the words at the two ends of a read are also computed by its neighbours.
-// A warp works on 8 reads at a time and on 128 consecutive reads (4 words of the bit vector) in all; a block covers
-// the same 1024 reads as k_filter and produces the same outputs (bits, class bytes, block totals, undecided records).
 // `bases`: 16-byte aligned, readable up to `readable` bytes (a multiple of 16 >= the last offset = n_bases).
 __device__ __forceinline__ void encode32(uint4 q0, uint4 q1, uint32_t &H, uint32_t &L, uint32_t &V)
 {
@@ -1622,104 +1617,102 @@ __device__ __forceinline__ void encode32(uint4 q0, uint4 q1, uint32_t &H, uint32
     }
 }
 
+// The same fusion with k_encode's regularity.  A block takes 1024 consecutive reads (the unit of k_filter's outputs)
+// and sweeps the WORDS of their span of the stream, a tile of kSF2TileWords at a time: thread t encodes words t, t+1024,
+// ... -- every word once, perfectly balanced, coalesced 32-byte loads -- into shared memory (and, with PLANES, into
+// the stream's bit-planes: a word is stored by the block whose span holds its first byte); then thread t counts ITS read
+// from the shared-memory bits of the part of the read that lies in the tile.  No per-read loop over global memory, no
+// word encoded twice inside a block, no lane waiting for the longest read of its warp.
+constexpr int kSF2Threads = 512;                        // reads per block; two blocks per SM: one sweeps while the other counts
+constexpr int kSF2TileWords = 2032;                     // 65 024 bases; 24 KB of shared memory per block
+
 template <bool PLANES>
-__global__ void __launch_bounds__(256, 4)
-k_stage_filter(const uint8_t *__restrict__ bases, uint64_t readable, uint64_t n_bases, const uint64_t *__restrict__ offs, uint64_t n_reads,
-               uint4 *__restrict__ planes, FilterParams fp, uint32_t *__restrict__ bv, uint64_t n_bv_words,
-               uint8_t *__restrict__ classes, unsigned int *__restrict__ block_totals, BorderRec *__restrict__ border,
-               unsigned int border_cap, unsigned int *__restrict__ n_border)
+__global__ void __launch_bounds__(kSF2Threads, 2)
+k_stage_filter(const uint8_t *__restrict__ bases, uint64_t readable, uint64_t n_bases, const uint64_t *__restrict__ offs,
+                uint64_t n_reads, uint4 *__restrict__ planes, FilterParams fp, uint32_t *__restrict__ bv, uint64_t n_bv_words,
+                uint8_t *__restrict__ classes, unsigned int *__restrict__ block_totals, BorderRec *__restrict__ border,
+                unsigned int border_cap, unsigned int *__restrict__ n_border)
 {
+    extern __shared__ uint32_t sf2_smem[];              // H[T] | L[T] | V[T]
+    uint32_t *sH = sf2_smem, *sL = sH + kSF2TileWords, *sV = sL + kSF2TileWords;
     __shared__ unsigned int tot[4];
-    if (threadIdx.x < 4) tot[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 2, gl = lane & 3;
-    const uint32_t gmask = 0xFu << (4 * grp);
-    const uint64_t r0 = (uint64_t)blockIdx.x * kFilterBlock + (uint64_t)warp * 128;
-    unsigned int wtot[4] = {0, 0, 0, 0};                      // rm_len, rm_N, rm_shannon, selected (lane 0)
-    // lane i owns read rbase + i: its offsets (coalesced, fetched one word of the bit vector ahead), its class, its bit
-    uint64_t nx_o = 0, nx_e = 0;
-    if (r0 + lane < n_reads) { nx_o = offs[r0 + lane]; nx_e = offs[r0 + lane + 1]; }
-    for (int j = 0; j < 4; j++) {
-        const uint64_t my_r = r0 + 32 * j + lane;
-        const uint64_t my_o = nx_o, my_e = nx_e;
-        nx_o = nx_e = 0;
-        if (j < 3 && my_r + 32 < n_reads) { nx_o = offs[my_r + 32]; nx_e = offs[my_r + 33]; }
-        unsigned int mine[4] = {0, 0, 0, 0};
-        for (int st = 0; st < 4; st++) {                       // 8 reads per step: read 8*st + grp of the 32
-            const int src = 8 * st + (int)grp;
-            const uint64_t o = __shfl_sync(0xffffffffu, my_o, src), e = __shfl_sync(0xffffffffu, my_e, src);
-            unsigned int cnt[4] = {0, 0, 0, 0};
-            // without planes a read that fails the length test is not read at all (filter_reads.cpp:189 comes first)
-            if (e > o && (PLANES || (long long)(e - o) >= fp.min_len)) {
-                for (uint64_t w = (o >> 5) + gl; (w << 5) < e; w += 4) {
-                    const uint64_t c = w << 5;
-                    const uint4 q0 = ld_nc_u4(reinterpret_cast<const uint4 *>(bases + c));
-                    uint4 q1 = make_uint4(0u, 0u, 0u, 0u);
-                    if (c + 16 < readable) q1 = ld_nc_u4(reinterpret_cast<const uint4 *>(bases + c + 16));
-                    uint32_t H, L, V;
-                    encode32(q0, q1, H, L, V);
-                    uint32_t m = ~0u;
-                    if (c < o) m &= ~0u << (o - c);
-                    if (c + 32 > e) m &= ~0u >> (c + 32 - e);
-                    if (PLANES && c >= o) {
-                        // nothing is valid past the end of the stream, whatever bytes lie there
-                        planes[w] = make_uint4(H, L, c + 32 > n_bases ? (V & (~0u >> (c + 32 - n_bases))) : V, 0u);
-                    }
-                    const uint32_t vm = V & m;
-                    cnt[0] += __popc(~H & ~L & vm);
-                    cnt[1] += __popc(~H & L & vm);
-                    cnt[2] += __popc(H & ~L & vm);
-                    cnt[3] += __popc(H & L & vm);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++) {                       // the reduction names the group's own lanes only
-                cnt[q] += __shfl_xor_sync(gmask, cnt[q], 1);
-                cnt[q] += __shfl_xor_sync(gmask, cnt[q], 2);
-            }
-            __syncwarp();
-            // hand the counts of read 8*st + g to its owner lane
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const unsigned int t = __shfl_sync(0xffffffffu, cnt[q], 4 * (lane & 7));
-                if ((int)(lane >> 3) == st) mine[q] = t;
-            }
-        }
-        // classification: one read per lane (the Shannon term is the expensive part; all 32 lanes work)
-        int cls = -1;
-        if (my_r < n_reads) {
-            const long long len = (long long)(my_e - my_o);
-            if (len < fp.min_len) cls = 1;
-            else {
-                unsigned int cnt[5] = {mine[0], mine[1], mine[2], mine[3], 0};
-                cnt[4] = (unsigned int)len - (cnt[0] + cnt[1] + cnt[2] + cnt[3]);
-                cls = classify_counts(len, cnt, fp);
-                if (cls == 4) {
-                    const unsigned int slot = atomicAdd(n_border, 1u);
-                    if (slot < border_cap) {
-                        BorderRec br;
-                        br.read = my_r;
-                        for (int q = 0; q < 5; q++) br.cnt[q] = cnt[q];
-                        br.len = (unsigned int)len;
-                        border[slot] = br;
-                    }
-                    cls = 0;    // provisional; the host patches classes/bits/totals
-                }
-            }
-            if (classes) classes[my_r] = (uint8_t)cls;
-        }
-        __syncwarp();
-        const uint32_t sel = __ballot_sync(0xffffffffu, cls == 0);
-        const uint64_t word = (r0 >> 5) + j;
-        if (lane == 0 && word < n_bv_words) bv[word] = sel;         // padding bits stay 0
-        wtot[3] += __popc(sel);
-#pragma unroll
-        for (int q = 1; q <= 3; q++) wtot[q - 1] += __popc(__ballot_sync(0xffffffffu, cls == q));
+    __shared__ uint64_t s_span[2];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t r_first = (uint64_t)blockIdx.x * kSF2Threads, r = r_first + tid;
+    if (tid < 4) tot[tid] = 0;
+    if (tid == 0) {
+        const uint64_t r_last = min(r_first + (uint64_t)kSF2Threads, n_reads);
+        s_span[0] = r_first < n_reads ? offs[r_first] : 0;
+        s_span[1] = r_first < n_reads ? offs[r_last] : 0;
     }
-    if (lane == 0)
-        for (int q = 0; q < 4; q++) if (wtot[q]) atomicAdd(&tot[q], wtot[q]);
+    uint64_t my_o = 0, my_e = 0;
+    if (r < n_reads) { my_o = offs[r]; my_e = offs[r + 1]; }
     __syncthreads();
-    if (threadIdx.x < 4) block_totals[4 * (uint64_t)blockIdx.x + threadIdx.x] = tot[threadIdx.x];
+    const uint64_t o_first = s_span[0], e_last = s_span[1];
+    const uint64_t ws = o_first >> 5, we = (e_last + 31) >> 5;
+    unsigned int cnt[5] = {0, 0, 0, 0, 0};
+    for (uint64_t tw = ws; tw < we; tw += kSF2TileWords) {
+        const uint32_t n_w = (uint32_t)min((uint64_t)kSF2TileWords, we - tw);
+        for (uint32_t i = tid; i < n_w; i += kSF2Threads) {
+            const uint64_t w = tw + i, c = w << 5;
+            const uint4 q0 = ld_nc_u4(reinterpret_cast<const uint4 *>(bases + c));
+            uint4 q1 = make_uint4(0u, 0u, 0u, 0u);
+            if (c + 16 < readable) q1 = ld_nc_u4(reinterpret_cast<const uint4 *>(bases + c + 16));
+            uint32_t H, L, V;
+            encode32(q0, q1, H, L, V);
+            if (c + 32 > n_bases) V &= ~0u >> (c + 32 - n_bases);      // nothing is valid past the end of the stream
+            sH[i] = H; sL[i] = L; sV[i] = V;
+            if (PLANES && c >= o_first) planes[w] = make_uint4(H, L, V, 0u);
+        }
+        __syncthreads();
+        const uint64_t lo = max(my_o, tw << 5), hi = min(my_e, (tw + kSF2TileWords) << 5);
+        if (lo < hi) {
+            for (uint64_t w = lo >> 5; (w << 5) < hi; w++) {
+                const uint32_t i = (uint32_t)(w - tw);
+                const uint64_t c = w << 5;
+                uint32_t m = sV[i];
+                if (c < lo) m &= ~0u << (lo - c);
+                if (c + 32 > hi) m &= ~0u >> (c + 32 - hi);
+                const uint32_t H = sH[i], L = sL[i];
+                cnt[0] += __popc(~H & ~L & m);
+                cnt[1] += __popc(~H & L & m);
+                cnt[2] += __popc(H & ~L & m);
+                cnt[3] += __popc(H & L & m);
+            }
+        }
+        __syncthreads();
+    }
+    int cls = -1;
+    if (r < n_reads) {
+        const long long len = (long long)(my_e - my_o);
+        if (len < fp.min_len) cls = 1;                              // filter_reads.cpp:189
+        else {
+            cnt[4] = (unsigned int)len - (cnt[0] + cnt[1] + cnt[2] + cnt[3]);
+            cls = classify_counts(len, cnt, fp);
+            if (cls == 4) {
+                const unsigned int slot = atomicAdd(n_border, 1u);
+                if (slot < border_cap) {
+                    BorderRec br;
+                    br.read = r;
+                    for (int q = 0; q < 5; q++) br.cnt[q] = cnt[q];
+                    br.len = (unsigned int)len;
+                    border[slot] = br;
+                }
+                cls = 0;    // provisional; the host patches classes/bits/totals
+            }
+        }
+        if (classes) classes[r] = (uint8_t)cls;
+    }
+    const uint32_t sel = __ballot_sync(0xffffffffu, cls == 0);
+    if ((tid & 31) == 0 && (r >> 5) < n_bv_words) bv[r >> 5] = sel;   // padding bits stay 0
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const uint32_t mc = __ballot_sync(0xffffffffu, cls == (c == 3 ? 0 : c + 1));
+        if ((tid & 31) == 0 && mc) atomicAdd(&tot[c], __popc(mc));
+    }
+    __syncthreads();
+    // (two blocks share the totals of one k_filter block of 1024 reads: the host zeroes them before the launch)
+    if (tid < 4 && tot[tid]) atomicAdd(&block_totals[4 * (r_first / kFilterBlock) + tid], tot[tid]);
 }
 
 // apply host decisions for the undecided reads: newcls[i] for border[i].read

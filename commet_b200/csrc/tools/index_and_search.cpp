@@ -121,6 +121,8 @@ int main(int argc, char **argv)
     ensure_dir(out_path);
     Engine ctx;
     ctx.prewarm();                   // CUDA comes up while the read files are parsed
+    ParseAhead ahead;
+    ahead.start(search_file_list);   // ... and the search sets' FASTA files while the index set is loaded
 
     // ---- sets, src/index_and_search.cpp:196-234 ------------------------------
     std::map<std::string, SetSpec> index_specs = read_sets(index_file_list);
@@ -137,7 +139,7 @@ int main(int argc, char **argv)
     for (auto &kv : search_specs) {
         std::unique_ptr<ReadSet> s(new ReadSet);
         s->nickname = kv.first;
-        load_set(*s, kv.second);
+        load_set(*s, kv.second, &ahead);
         search_sets.push_back(std::move(s));
         if (full) break;
     }
@@ -227,7 +229,9 @@ int main(int argc, char **argv)
     // ---- outputs, :397-399 ------------------------------------------------------
     for (auto &s : search_sets) s->save_bv(out_path, index_specs.begin()->first);
     ctx.mark("vectors written");
-    ctx.close();
-    ctx.mark("device released");
-    return 0;
+    // every output is on disk: the process ends without tearing the CUDA context down (the driver reclaims the device
+    // memory of a dead process; an orderly teardown of a 15 GB context was measured at 30-440 ms)
+    std::cout.flush();
+    std::cerr.flush();
+    std::_Exit(0);
 }

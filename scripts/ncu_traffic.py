@@ -31,7 +31,7 @@ def main(src, dst):
             e["note"] = NOTES[m.group(1)]
         kernels[m.group(1)] = e
     out = {"source": f"{src} (ncu --set full --clock-control none --import-source on, one launch each, "
-                     "bench.py --steps 1 --warmup 0 --no-cpu; scripts/gpu_round.sh)",
+                     "bench.py --steps 1 --warmup 0 --no-cpu --no-extra)",
            "workload": {"reads_per_set": 10000000, "read_len": 100, "k": 33, "t": 2}, "kernels": kernels}
     json.dump(out, open(dst, "w"), indent=1)
     print(json.dumps(out, indent=1))

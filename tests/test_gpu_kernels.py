@@ -403,6 +403,23 @@ def test_bvop_and_popcount(ctx, n):
         ctx.bvop(cb.BV_AND, a, np.zeros(a.size + 1, np.uint8))
 
 
+def test_popcount_of_several_vectors_in_one_call(ctx):
+    """commet_bv_popcount_batch_dev: nb_one (all n/8+1 bytes, clamped to n: boolean_vector.h:244-270) of vectors of
+    different sizes with one read-back"""
+    import torch
+    rng = np.random.default_rng(12)
+    sizes = [0, 1, 7, 8, 129, 4099, 1_000_003, 64]
+    vecs = [rng.integers(0, 256, size=n // 8 + 1).astype(np.uint8) for n in sizes]
+    vecs[3][:] = 0xFF                                    # 16 set bits in a vector of 8: the count is clamped
+    dev = [torch.zeros((v.size + 15) // 16 * 16, dtype=torch.uint8, device="cuda:0") for v in vecs]
+    for d, v in zip(dev, vecs):
+        d[:v.size] = torch.as_tensor(v, device="cuda:0")
+    torch.cuda.synchronize()
+    got = ctx.nb_one_device_batch([d.data_ptr() for d in dev], sizes)
+    assert got == [oracle.nb_one(v, n) for v, n in zip(vecs, sizes)]
+    assert got[3] == 8
+
+
 def test_bvop_known_answer_not_counts_padding(ctx):
     """NOT of a 2000/10000 vector reports 8008 (padding bits flipped, clamped popcount)."""
     import commet_b200 as cb
