@@ -973,6 +973,7 @@ static int scatter_range(commet_ctx *c, commet_reads *r, uint64_t s0, uint64_t s
     const unsigned sbps = env_or("COMMET_B200_SCATTER_BPS", tw <= 96 ? 3 : 2);
     CK(cudaMemsetAsync(c->bins2, 0, 2048 * sizeof(uint32_t), c->stream));
     CK(cudaMemsetAsync(c->slab_table, 0, (size_t)n_bins * max_q * sizeof(uint32_t), c->stream));
+    if (s1 <= s0) return 0;                          // nothing to scatter: zeroed counters, no launch
     if (tw <= 64) launch_scatter2<64>(c, r, s0, s1, c->k, n_bins, fill, max_q, n_slabs, sbps);
     else if (tw <= 96) launch_scatter2<96>(c, r, s0, s1, c->k, n_bins, fill, max_q, n_slabs, sbps);
     else launch_scatter2<128>(c, r, s0, s1, c->k, n_bins, fill, max_q, n_slabs, sbps);

@@ -20,6 +20,30 @@
 
 namespace commet_host {
 
+// Background threads of a tool (CUDA start-up, files parsed ahead) must not be running when exit() -- the reference's
+// way out of every fatal error -- starts tearing the process down: they are joined by an atexit handler.
+inline std::vector<std::thread *> &tool_threads()
+{
+    static std::vector<std::thread *> v;
+    return v;
+}
+inline void join_tool_threads()
+{
+    for (std::thread *t : tool_threads())
+        if (t->joinable() && t->get_id() != std::this_thread::get_id()) t->join();
+}
+inline void watch_thread(std::thread *t)
+{
+    static bool registered = false;
+    if (!registered) { atexit(join_tool_threads); registered = true; }
+    tool_threads().push_back(t);
+}
+inline void unwatch_thread(std::thread *t)           // the owner has joined it and is going away
+{
+    std::vector<std::thread *> &v = tool_threads();
+    v.erase(std::remove(v.begin(), v.end(), t), v.end());
+}
+
 inline void ensure_dir(const std::string &path)        // src/index_and_search.cpp:178-191
 {
     struct stat info;
@@ -66,6 +90,7 @@ struct ParseAhead {
                 }
             }
         });
+        watch_thread(&th);
     }
     ParsedFile *take(const std::string &fname)
     {
@@ -73,7 +98,7 @@ struct ParseAhead {
         auto it = done.find(fname);
         return it == done.end() ? nullptr : &it->second;
     }
-    ~ParseAhead() { if (th.joinable()) th.join(); }
+    ~ParseAhead() { if (th.joinable()) th.join(); unwatch_thread(&th); }
 };
 
 inline void load_set(ReadSet &set, const SetSpec &spec, ParseAhead *ahead = nullptr)
@@ -130,6 +155,7 @@ struct Engine {
         warm = std::thread([this, dev]() {
             if (commet_ctx_create(dev, &warm_ctx) != 0) warm_err = commet_last_error();
         });
+        watch_thread(&warm);
     }
     bool open(uint64_t total_bases)
     {
@@ -154,6 +180,7 @@ struct Engine {
         if (!warm_err.empty()) return commet_ctx_create(devices.empty() ? 0 : devices[0], &ctx) == 0;   // repeats the failure: sets the message in this thread
         return commet_ctx_create(devices.empty() ? 0 : devices[0], &ctx) == 0;
     }
+    ~Engine() { if (warm.joinable()) warm.join(); unwatch_thread(&warm); }
     void close()
     {
         if (warm.joinable()) warm.join();
