@@ -24,8 +24,8 @@ namespace commet_host {
 // way out of every fatal error -- starts tearing the process down: they are joined by an atexit handler.
 inline std::vector<std::thread *> &tool_threads()
 {
-    static std::vector<std::thread *> v;
-    return v;
+    static std::vector<std::thread *> *v = new std::vector<std::thread *>;      // never destroyed: used by an atexit handler
+    return *v;
 }
 inline void join_tool_threads()
 {
