@@ -1248,6 +1248,8 @@ __device__ __forceinline__ bool scan_both(const uint32_t *__restrict__ filter, c
 // counters[2] += filter byte tests, counters[3] += k-mer lookups (reference semantics).
 // BOTH: 0 = the reference's order (forward scan, then reverse); > 0 = one pass over both strands with BOTH
 // positions per strand and batch (scan_both)
+// (compiled for 4 resident blocks per SM = 64 registers: measured against 3, 5 and 6 -- 85, 48 and 40 registers -- at
+// k=33 and k=27, profiles/r02_search_occupancy_ab.txt; both directions lose, up to 1.6x at k=27)
 template <bool COUNT, int BOTH>
 __global__ void __launch_bounds__(256, 4)
 k_search(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,

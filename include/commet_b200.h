@@ -50,8 +50,9 @@ void *commet_ctx_stream(commet_ctx *ctx);
 int commet_ctx_count_probes(commet_ctx *ctx, int on);
 /* How filters larger than L2 (k >= 28) are fed; the filter bits are the same in every mode.
  *   0: direct RED.OR into the DRAM-resident filter
- *   1: (default) keys partitioned (sorted) by 32 MiB filter region into a record buffer, then applied region by
- *      region so that every RED.OR hits L2
+ *   1: (default) keys partitioned by 32 MiB filter region into a record pool, then applied region by region so that
+ *      every RED.OR hits L2.  Two forms exist: 102 (default) = records in slabs handed out on demand, no histogram
+ *      pass; 101 = histogram, exclusive scan, scatter into exact ranges (round 1).  101 / 102 select a form explicitly.
  *   16..30: region passes: 2^R passes over the stream, pass r inserting only the keys of the r-th 2^mode-byte
  *      region (region membership = bit-parallel match on the first R bases); measured slower, kept for A/B */
 int commet_ctx_binned_index(commet_ctx *ctx, int on);

@@ -148,7 +148,8 @@ def test_sharded_index_merge_search_two_gpus(tmp_path, k, t, maxk, seed):
 @pytest.mark.skipif(_n_gpus() < 1, reason="needs a GPU")
 @pytest.mark.parametrize("world,k,t,maxk,block,seed", [(2, 16, 2, None, 64, 1), (2, 20, 2, 60000, 100, 2), (2, 29, 2, 90000, 7, 3),
                                                        (3, 20, 2, 60000, 33, 4), (4, 20, 1, 50000, 50, 5), (4, 29, 2, 90000, 16, 6),
-                                                       (8, 16, 2, None, 64, 7), (8, 20, 2, 60000, 25, 8), (8, 29, 2, 90000, 16, 9), (2, 31, 1, 70000, 40, 10)])
+                                                       (8, 16, 2, None, 64, 7), (8, 20, 2, 60000, 25, 8), (8, 29, 2, 90000, 16, 9), (2, 31, 1, 70000, 40, 10),
+                                                       (4, 29, 2, 30000, 1000, 19)])      # blocks larger than chunks: ranks without reads in a chunk, one without any
 def test_distributed_reference_set_ranks(tmp_path, world, k, t, maxk, block, seed):
     """2, 3, 4 and 8 ranks (one GPU each while the box has them, else sharing GPUs: the IPC mapping is per process), each
     holding only its block-cyclic shard of the reference set, uploaded with commet_reads_upload_async: global chunk
