@@ -1227,6 +1227,17 @@ static int search_launch(commet_ctx *c, commet_reads *r, int k, int t, uint32_t 
         else                             // 73 registers, 3 resident blocks per SM
             k_search_dyn<4, 3><<<gd, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel, cursor);
     } else if (c->count_probes) COMMET_SEARCH(true, 0);
+    else if (env_or("COMMET_B200_SEARCH_VARIANT", 0) == 44)      // A/B: round 1's shape -- 4 positions per strand and batch, 4 blocks per SM
+        COMMET_SEARCH(false, 4);
+    else if (c->search_both == 4 && k <= 30 && env_or("COMMET_B200_SEARCH_VARIANT", 0) != 25)
+        // keys of at most 30 bits (filters up to 512 MiB, the L2-resident ones among them): 32-bit windows and keys, 40
+        // registers, 6 resident blocks per SM -- the scan is latency-bound there and lives on resident warps
+        // (profiles/r02_search_occupancy_ab.txt: 290 ms against 366 ms at k=27 = 71 % of the L2 random-sector ceiling)
+        k_search<false, 2, 6, true><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
+    else if (c->search_both == 4)
+        // 2 positions per strand and batch (4 a-probes in flight per lane), 5 resident blocks per SM at 48 registers:
+        // 18.6 against 19.2 ms at k=33
+        k_search<false, 2, 5><<<g, 256, 0, c->stream>>>(c->filter, r->planes, r->offs, r->n_reads, k, t, d_tags, d_counters, r->sel);
     else if (c->search_both == 2) COMMET_SEARCH(false, 2);
     else if (c->search_both == 8) COMMET_SEARCH(false, 8);
     else if (c->search_both) COMMET_SEARCH(false, 4);

@@ -77,6 +77,13 @@ __device__ __forceinline__ Keys make_keys(uint64_t hv, uint64_t lv, int k, uint6
 
 // BloomFilter byte/mask (bloom_filter.h:112-131) in the u32-word view
 __device__ __forceinline__ uint64_t key_word(uint64_t key) { return key >> 3; }
+__device__ __forceinline__ uint32_t key_word(uint32_t key) { return key >> 3; }
+__device__ __forceinline__ uint32_t key_bit(uint32_t key, int j)
+{
+    const uint32_t byte = (key >> 1) & 3u;
+    const uint32_t in_byte = (key & 1u) ? (3 - j) : (7 - j);
+    return 1u << (byte * 8 + in_byte);
+}
 __device__ __forceinline__ uint32_t key_bit(uint64_t key, int j)
 {
     uint32_t byte = (uint32_t)(key >> 1) & 3u;
@@ -1165,16 +1172,37 @@ __device__ __forceinline__ bool scan_strand(const uint32_t *__restrict__ filter,
 // few batches instead of after a full fruitless forward scan, and a forward copy wastes one batch of reverse
 // probes.  Each strand keeps its own hit count and its own next position, so every strand's greedy count is
 // exactly the reference's.
-template <int U>
-__device__ __forceinline__ bool scan_both(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
-                                          uint64_t o, uint32_t npos, int k, int t, uint64_t mask)
+// K32: keys of at most 30 bits (filters of at most 512 MiB, among them the L2-resident ones): the plane windows, the keys
+// and the mask are 32-bit values and two plane words are enough -- a third fewer registers, one more resident block.
+template <bool K32> struct KeyType { typedef uint64_t type; };
+template <> struct KeyType<true> { typedef uint32_t type; };
+__device__ __forceinline__ uint64_t fwd_key(uint64_t v, int k) { return __brevll(v) >> (64 - k); }
+__device__ __forceinline__ uint32_t fwd_key(uint32_t v, int k) { return __brev(v) >> (32 - k); }
+
+// b, c, d of one position after its a-bit was found set, in the reference's order (bloom_filter.h:124-131)
+template <class KT>
+__device__ __forceinline__ bool probe_bcd_of(const uint32_t *__restrict__ filter, KT a, KT lw, int k, KT mask, bool rev)
 {
+    const KT b = rev ? (KT)(~lw & mask) : fwd_key(lw, k);
+    if (!(ld_probe_u32(filter + key_word(b)) & key_bit(b, 1))) return false;
+    const KT c = a ^ b;
+    if (!(ld_probe_u32(filter + key_word(c)) & key_bit(c, 2))) return false;
+    const KT d = a | b;
+    return (ld_probe_u32(filter + key_word(d)) & key_bit(d, 3)) != 0;
+}
+
+template <int U, bool K32>
+__device__ __forceinline__ bool scan_both(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
+                                          uint64_t o, uint32_t npos, int k, int t, uint64_t mask64)
+{
+    typedef typename KeyType<K32>::type KT;
+    const KT mask = (KT)mask64;
     uint64_t wi = o >> 5;
-    uint4 q0 = planes[wi], q1 = planes[wi + 1], q2 = planes[wi + 2];
+    uint4 q0 = planes[wi], q1 = planes[wi + 1], q2 = make_uint4(0u, 0u, 0u, 0u);
+    if (!K32) q2 = planes[wi + 2];
     int seen_f = 0, seen_r = 0;
     uint32_t nf = 0, nr = 0;                         // next position of each strand (>= npos: strand finished)
     int focus = 0;                                   // 0: both strands, 1: forward only, 2: reverse only
-    unsigned int dummy = 0;
     while (true) {
         const bool use_f = focus != 2 && nf < npos, use_r = focus != 1 && nr < npos;
         if (!use_f && !use_r) {
@@ -1186,7 +1214,11 @@ __device__ __forceinline__ bool scan_both(const uint32_t *__restrict__ filter, c
         uint64_t b = o + p;
         uint64_t need = b >> 5;
         if (need != wi) {
-            if (need < wi || need - wi >= 3) {       // a resumed strand may be behind the window
+            if (K32) {
+                if (need == wi + 1) { q0 = q1; q1 = planes[wi + 2]; }
+                else { q0 = planes[need]; q1 = planes[need + 1]; }      // a jump, or a resumed strand behind the window
+                wi = need;
+            } else if (need < wi || need - wi >= 3) {                   // a resumed strand may be behind the window
                 wi = need;
                 q0 = planes[wi]; q1 = planes[wi + 1]; q2 = planes[wi + 2];
             } else {
@@ -1211,14 +1243,14 @@ __device__ __forceinline__ bool scan_both(const uint32_t *__restrict__ filter, c
         // positions of this batch each strand still has to look at
         const uint32_t mf = !use_f || nf >= p + U ? 0u : (nf > p ? (m & (~0u << (nf - p))) : m);
         const uint32_t mr = !use_r || nr >= p + U ? 0u : (nr > p ? (m & (~0u << (nr - p))) : m);
-        uint64_t hv = window64(q0.x, q1.x, q2.x, sh);
-        uint64_t lv = window64(q0.y, q1.y, q2.y, sh);
+        const KT hv = K32 ? (KT)__funnelshift_r(q0.x, q1.x, sh) : (KT)window64(q0.x, q1.x, q2.x, sh);
+        const KT lv = K32 ? (KT)__funnelshift_r(q0.y, q1.y, sh) : (KT)window64(q0.y, q1.y, q2.y, sh);
         uint32_t af[U], ar[U];
-        uint64_t kf[U], kr[U];
+        KT kf[U], kr[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            kf[u] = __brevll(hv >> u) >> (64 - k);
-            kr[u] = ~(hv >> u) & mask;
+            kf[u] = fwd_key((KT)(hv >> u), k);
+            kr[u] = (KT)(~(hv >> u) & mask);
             af[u] = ar[u] = 0;
             if ((mf >> u) & 1u) af[u] = ld_probe_u32(filter + key_word(kf[u]));
             if ((mr >> u) & 1u) ar[u] = ld_probe_u32(filter + key_word(kr[u]));
@@ -1226,14 +1258,10 @@ __device__ __forceinline__ bool scan_both(const uint32_t *__restrict__ filter, c
         bool hit_f = false, hit_r = false;
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            if (!hit_f && ((mf >> u) & 1u) && (af[u] & key_bit(kf[u], 0))) {
-                Keys q = make_keys(hv >> u, lv >> u, k, mask, false);
-                if (probe_bcd(filter, q, dummy)) { hit_f = true; seen_f++; nf = p + (uint32_t)u + (uint32_t)k; }
-            }
-            if (!hit_r && ((mr >> u) & 1u) && (ar[u] & key_bit(kr[u], 0))) {
-                Keys q = make_keys(hv >> u, lv >> u, k, mask, true);
-                if (probe_bcd(filter, q, dummy)) { hit_r = true; seen_r++; nr = p + (uint32_t)u + (uint32_t)k; }
-            }
+            if (!hit_f && ((mf >> u) & 1u) && (af[u] & key_bit(kf[u], 0)) &&
+                probe_bcd_of<KT>(filter, kf[u], (KT)(lv >> u), k, mask, false)) { hit_f = true; seen_f++; nf = p + (uint32_t)u + (uint32_t)k; }
+            if (!hit_r && ((mr >> u) & 1u) && (ar[u] & key_bit(kr[u], 0)) &&
+                probe_bcd_of<KT>(filter, kr[u], (KT)(lv >> u), k, mask, true)) { hit_r = true; seen_r++; nr = p + (uint32_t)u + (uint32_t)k; }
         }
         // `seen >= t` is only looked at after a hit (search_reads.h:55-57): t <= 1 behaves as t = 1
         if ((hit_f && seen_f >= t) || (hit_r && seen_r >= t)) return true;
@@ -1250,8 +1278,8 @@ __device__ __forceinline__ bool scan_both(const uint32_t *__restrict__ filter, c
 // positions per strand and batch (scan_both)
 // (compiled for 4 resident blocks per SM = 64 registers: measured against 3, 5 and 6 -- 85, 48 and 40 registers -- at
 // k=33 and k=27, profiles/r02_search_occupancy_ab.txt; both directions lose, up to 1.6x at k=27)
-template <bool COUNT, int BOTH>
-__global__ void __launch_bounds__(256, 4)
+template <bool COUNT, int BOTH, int MINB = 4, bool K32 = false>
+__global__ void __launch_bounds__(256, MINB)
 k_search(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
          const uint64_t *__restrict__ offs, uint64_t n_reads, int k, int t,
          uint32_t *__restrict__ tags, unsigned long long *__restrict__ counters,
@@ -1273,7 +1301,7 @@ k_search(const uint32_t *__restrict__ filter, const uint4 *__restrict__ planes,
             f = scan_strand<COUNT>(filter, planes, o, npos, k, t, mask, false, tests, lookups);
             if (!f) f = scan_strand<COUNT>(filter, planes, o, npos, k, t, mask, true, tests, lookups);
         } else {
-            f = scan_both<(BOTH > 0 ? BOTH : 1)>(filter, planes, o, npos, k, t, mask);
+            f = scan_both<(BOTH > 0 ? BOTH : 1), K32>(filter, planes, o, npos, k, t, mask);
         }
         if (f) {
             atomicOr(&tags[r >> 5], 1u << (r & 31));
