@@ -172,8 +172,31 @@ def bind_to_gpu_numa_node(index: int):
         p = torch.cuda.get_device_properties(index)
         bdf = f"{getattr(p, 'pci_domain_id', 0):04x}:{p.pci_bus_id:02x}:{getattr(p, 'pci_device_id', 0):02x}.0"
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        info = {"bdf": bdf, "node": node}
         if node < 0:
-            return {"bdf": bdf, "node": node}
+            # sysfs does not say (virtualised topology): ask the driver which CPUs are close to this GPU and take the
+            # node of the first of them -- unless the answer is "all of them", which carries no information
+            info["nodes_online"] = open("/sys/devices/system/node/online").read().strip()
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bdf.encode())
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            near = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+            info["nvml_cpus"] = len(near)
+            if not near or len(near) >= os.cpu_count():
+                return info
+            import glob
+            for d in glob.glob("/sys/devices/system/node/node[0-9]*"):
+                lst = set()
+                for part in open(d + "/cpulist").read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    if lo:
+                        lst.update(range(int(lo), int(hi or lo) + 1))
+                if min(near) in lst:
+                    node = int(d.rsplit("node", 1)[1])
+            if node < 0:
+                return info
+            info["node_from_nvml"] = node
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
@@ -184,7 +207,8 @@ def bind_to_gpu_numa_node(index: int):
         libc = ctypes.CDLL("libc.so.6", use_errno=True)
         mask = ctypes.c_ulong(1 << node)
         rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(node + 2))     # x86-64 set_mempolicy(MPOL_PREFERRED)
-        return {"bdf": bdf, "node": node, "cpus": len(use), "set_mempolicy": int(rc)}
+        info.update({"node": node, "cpus": len(use), "set_mempolicy": int(rc)})
+        return info
     except Exception as e:                                                           # never fatal: it is an A/B switch
         return {"error": str(e)[:200]}
 

@@ -1513,7 +1513,17 @@ static std::vector<uint64_t> split_parts(const uint64_t *offs, uint64_t n_reads)
     uint64_t min_part = 64ull << 20;
     if (const char *e = getenv("COMMET_B200_PART_BYTES")) min_part = std::max<uint64_t>(strtoull(e, nullptr, 10), 1);   // tests
     if (n_bases >= 4 * min_part) {
-        const double frac[2] = {0.2, 0.5};
+        std::vector<double> frac = {0.2, 0.5};
+        if (const char *e = getenv("COMMET_B200_PART_FRACS")) {          // tuning: increasing cut positions in (0,1), comma separated
+            frac.clear();
+            for (const char *q = e; *q;) {
+                char *end = nullptr;
+                double f = strtod(q, &end);
+                if (end == q) break;
+                if (f > 0.0 && f < 1.0) frac.push_back(f);
+                q = *end ? end + 1 : end;
+            }
+        }
         for (double f : frac) {
             uint64_t target = (uint64_t)(f * (double)n_bases);
             uint64_t r = (uint64_t)(std::lower_bound(offs, offs + n_reads + 1, target) - offs);
@@ -1555,13 +1565,14 @@ extern "C" int commet_index_and_search(commet_ctx *c, int k, int t, uint64_t max
     }
     uint64_t q_part_bytes = 256ull << 20;
     if (const char *e = getenv("COMMET_B200_QUERY_PART_BYTES")) q_part_bytes = std::max<uint64_t>(strtoull(e, nullptr, 10), 1);     // tests
+    const uint64_t max_q_parts = std::max(1u, env_or("COMMET_B200_QUERY_PARTS", 4));
     for (int s = 0; rc == 0 && s < n_sets; s++) {
         if (qoffs[s][0] != 0) { rc = fail("commet_index_and_search: qoffs[%d][0] must be 0", s); break; }
         const uint64_t nw = tag_words(n_query[s]);
         if (c->arena.alloc((void **)&dt[s], nw * 4) != cudaSuccess) { rc = fail("tag allocation failed"); break; }
         if (cudaMemsetAsync(dt[s], 0, nw * 4, c->stream) != cudaSuccess) { rc = fail("tag memset failed"); break; }
         const uint64_t n = n_query[s], bytes = qoffs[s][n];
-        const uint64_t n_parts = std::max<uint64_t>(1, std::min<uint64_t>(4, bytes / q_part_bytes));
+        const uint64_t n_parts = std::max<uint64_t>(1, std::min<uint64_t>(max_q_parts, bytes / q_part_bytes));
         uint64_t a = 0;
         for (uint64_t p = 0; rc == 0 && p < n_parts; p++) {
             uint64_t b = n;
