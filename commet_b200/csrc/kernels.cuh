@@ -94,9 +94,38 @@ __device__ __forceinline__ uint32_t key_bit(uint64_t key, int j)
 // ------------------------------------------------------------- staging ----
 // ASCII -> H/L/V planes, 32 bases per thread via two 16-byte vector loads.
 // `bases` is zero-padded to a multiple of 32 bytes.
-__device__ __forceinline__ uint32_t gather4(uint32_t x)   // bits 0,8,16,24 -> bits 0..3
+//
+// Four bases (one 32-bit word c of the ASCII stream) at a time, every bit of interest brought to bit 7 of its byte by a
+// LEFT shift (c7 needs none; a left shift can issue as a multiply on the FMA pipe, leaving the ALU pipe to the logic):
+//   H = c2 (A,C -> 0; G,T -> 1), L = c1 ^ c2 (A,G -> 0; C,T -> 1)                             hash_key.h:65-91
+//   V (alphabet.h:44-58, `ACGTacgt`): with q = c2 & ~c1 ("is T" among the four), a byte is valid iff
+//       c7 = 0, c6 = 1, (c5 = case, ignored), c4 = q, c3 = 0, c0 = ~q
+//     A 0100 0001   C 0100 0011   G 0100 0111   T 0101 0100
+// The four flags of a word (bits 7, 15, 23, 31) are gathered into the top nibble of flags * 0x00204081 (partial
+// products 7+21, 15+14, 23+7, 31+0 = bits 28..31; the other twelve land on distinct lower bits or above bit 31: no
+// carries), and a funnel shift pushes that nibble into the plane word -- words taken last to first, so word j's
+// nibble ends at bits 4j..4j+3.  Per word: 6 shifts, 6 three-input logic ops, 3 multiplies, 3 funnel shifts.
+__device__ __forceinline__ void encode_word(uint32_t c, uint32_t &H, uint32_t &L, uint32_t &V)
 {
-    return ((x * 0x00204081u) >> 21) & 0xFu;
+    constexpr uint32_t M7 = 0x80808080u, K = 0x00204081u;
+    const uint32_t x6 = c << 1, x4 = c << 3, x3 = c << 4, x2 = c << 5, x1 = c << 6, x0 = c << 7;
+    const uint32_t q = x2 & ~x1;
+    const uint32_t a = (x0 ^ q) & ~(x4 ^ q);
+    const uint32_t b = ~x3 & x6 & ~c;
+    const uint32_t v = a & b & M7;
+    const uint32_t h = x2 & M7;
+    const uint32_t l = (x1 ^ x2) & M7;
+    H = __funnelshift_l(h * K, H, 4);
+    L = __funnelshift_l(l * K, L, 4);
+    V = __funnelshift_l(v * K, V, 4);
+}
+
+__device__ __forceinline__ void encode32(uint4 q0, uint4 q1, uint32_t &H, uint32_t &L, uint32_t &V)
+{
+    const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    H = L = V = 0;
+#pragma unroll
+    for (int j = 7; j >= 0; j--) encode_word(w[j], H, L, V);
 }
 
 __global__ void __launch_bounds__(256)
@@ -106,20 +135,8 @@ k_encode(const uint4 *__restrict__ bases16, uint4 *__restrict__ planes, uint64_t
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
         uint4 q0 = ld_nc_u4(bases16 + 2 * i);
         uint4 q1 = ld_nc_u4(bases16 + 2 * i + 1);
-        uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-        uint32_t H = 0, L = 0, V = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            uint32_t c = w[j];
-            uint32_t h = (c >> 2) & 0x01010101u;                 // A,C ->0  G,T ->1
-            uint32_t l = ((c >> 1) ^ (c >> 2)) & 0x01010101u;    // A,G ->0  C,T ->1
-            uint32_t x = c | 0x20202020u;                         // fold case
-            uint32_t v = (__vcmpeq4(x, 0x61616161u) | __vcmpeq4(x, 0x63636363u) |
-                          __vcmpeq4(x, 0x67676767u) | __vcmpeq4(x, 0x74747474u)) & 0x01010101u;
-            H |= gather4(h) << (4 * j);
-            L |= gather4(l) << (4 * j);
-            V |= gather4(v) << (4 * j);
-        }
+        uint32_t H, L, V;
+        encode32(q0, q1, H, L, V);
         planes[i] = make_uint4(H, L, V, 0u);
     }
 }
@@ -1629,24 +1646,6 @@ k_filter(const uint4 *__restrict__ planes, const uint64_t *__restrict__ offs, ui
 // are popcounts of those bits restricted to the read's range -- no per-byte counting at all; with PLANES the bits
 // are also stored as the stream's bit-planes, so a set that is filtered AND indexed is read from HBM once.
 // `bases`: 16-byte aligned, readable up to `readable` bytes (a multiple of 16 >= the last offset = n_bases).
-__device__ __forceinline__ void encode32(uint4 q0, uint4 q1, uint32_t &H, uint32_t &L, uint32_t &V)
-{
-    const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-    H = L = V = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const uint32_t c = w[j];
-        const uint32_t h = (c >> 2) & 0x01010101u;                 // A,C ->0  G,T ->1
-        const uint32_t l = ((c >> 1) ^ (c >> 2)) & 0x01010101u;    // A,G ->0  C,T ->1
-        const uint32_t x = c | 0x20202020u;                         // fold case
-        const uint32_t v = (__vcmpeq4(x, 0x61616161u) | __vcmpeq4(x, 0x63636363u) |
-                            __vcmpeq4(x, 0x67676767u) | __vcmpeq4(x, 0x74747474u)) & 0x01010101u;
-        H |= gather4(h) << (4 * j);
-        L |= gather4(l) << (4 * j);
-        V |= gather4(v) << (4 * j);
-    }
-}
-
 // The same fusion with k_encode's regularity.  A block takes 1024 consecutive reads (the unit of k_filter's outputs)
 // and sweeps the WORDS of their span of the stream, a tile of kSF2TileWords at a time: thread t encodes words t, t+1024,
 // ... -- every word once, perfectly balanced, coalesced 32-byte loads -- into shared memory (and, with PLANES, into
