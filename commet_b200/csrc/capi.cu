@@ -1753,6 +1753,21 @@ extern "C" int commet_filter_reads_range(commet_ctx *c, commet_reads *r, uint64_
     return 0;
 }
 
+// the fused staging + selection kernel; n_blocks counts k_filter blocks of kFilterBlock reads (the unit of `totals`)
+template <bool PLANES>
+static void launch_stage_filter(commet_ctx *c, unsigned n_blocks, const uint8_t *d_bases, uint64_t readable, uint64_t n_bases,
+                                const uint64_t *d_offs, uint64_t n_reads, uint4 *planes, const FilterParams &fp, uint32_t *d_bv,
+                                uint64_t n_bv_words, uint8_t *classes, unsigned int *totals, BorderRec *border,
+                                unsigned int border_cap, unsigned int *nb)
+{
+    if (env_or("COMMET_B200_SF_THREADS", 512) == 256)       // A/B (profiles/): four blocks of 256 reads per SM
+        k_stage_filter<PLANES, 256><<<n_blocks * (kFilterBlock / 256), 256, sf2_tile_words<256>() * 12, c->stream>>>(
+                d_bases, readable, n_bases, d_offs, n_reads, planes, fp, d_bv, n_bv_words, classes, totals, border, border_cap, nb);
+    else
+        k_stage_filter<PLANES, 512><<<n_blocks * (kFilterBlock / 512), 512, sf2_tile_words<512>() * 12, c->stream>>>(
+                d_bases, readable, n_bases, d_offs, n_reads, planes, fp, d_bv, n_bv_words, classes, totals, border, border_cap, nb);
+}
+
 extern "C" int commet_filter_reads_dev(commet_ctx *c, const uint8_t *d_bases, const uint64_t *d_offs, uint64_t n_reads,
                                        int64_t min_len, int64_t max_N, float min_shannon, int64_t max_reads,
                                        uint32_t *d_bv, uint64_t *counters)
@@ -1766,8 +1781,8 @@ extern "C" int commet_filter_reads_dev(commet_ctx *c, const uint8_t *d_bases, co
     return filter_run(c, n_reads, min_len, max_N, min_shannon, max_reads, d_bv, counters,
                       [&](unsigned n_blocks, const FilterParams &fp, uint64_t n_bv_words, uint8_t *classes, unsigned int *totals,
                           BorderRec *border, unsigned int border_cap, unsigned int *nb) {
-                          k_stage_filter<false><<<n_blocks * (kFilterBlock / kSF2Threads), kSF2Threads, kSF2TileWords * 12, c->stream>>>(
-                                  d_bases, readable, n_bases, d_offs, n_reads, nullptr, fp, d_bv, n_bv_words, classes, totals, border, border_cap, nb);
+                          launch_stage_filter<false>(c, n_blocks, d_bases, readable, n_bases, d_offs, n_reads, nullptr, fp, d_bv, n_bv_words,
+                                                     classes, totals, border, border_cap, nb);
                       });
 }
 
@@ -1787,8 +1802,8 @@ extern "C" int commet_reads_from_device_filtered(commet_ctx *c, const uint8_t *d
     int rc = filter_run(c, n_reads, min_len, max_N, min_shannon, max_reads, d_bv, counters,
                         [&](unsigned n_blocks, const FilterParams &fp, uint64_t n_bv_words, uint8_t *classes, unsigned int *totals,
                             BorderRec *border, unsigned int border_cap, unsigned int *nb) {
-                            k_stage_filter<true><<<n_blocks * (kFilterBlock / kSF2Threads), kSF2Threads, kSF2TileWords * 12, c->stream>>>(
-                                    d_bases, readable, n_bases, d_offs, n_reads, r->planes, fp, d_bv, n_bv_words, classes, totals, border, border_cap, nb);
+                            launch_stage_filter<true>(c, n_blocks, d_bases, readable, n_bases, d_offs, n_reads, r->planes, fp, d_bv, n_bv_words,
+                                                      classes, totals, border, border_cap, nb);
                         });
     if (rc != 0) { commet_reads_free(r); return rc; }
     *out = r;

@@ -1647,30 +1647,32 @@ k_filter(const uint4 *__restrict__ planes, const uint64_t *__restrict__ offs, ui
 // are also stored as the stream's bit-planes, so a set that is filtered AND indexed is read from HBM once.
 // `bases`: 16-byte aligned, readable up to `readable` bytes (a multiple of 16 >= the last offset = n_bases).
 // The same fusion with k_encode's regularity.  A block takes 1024 consecutive reads (the unit of k_filter's outputs)
-// and sweeps the WORDS of their span of the stream, a tile of kSF2TileWords at a time: thread t encodes words t, t+1024,
+// and sweeps the WORDS of their span of the stream, a tile of sf2_tile_words() at a time: thread t encodes words t, t+1024,
 // ... -- every word once, perfectly balanced, coalesced 32-byte loads -- into shared memory (and, with PLANES, into
 // the stream's bit-planes: a word is stored by the block whose span holds its first byte); then thread t counts ITS read
 // from the shared-memory bits of the part of the read that lies in the tile.  No per-read loop over global memory, no
 // word encoded twice inside a block, no lane waiting for the longest read of its warp.
-constexpr int kSF2Threads = 512;                        // reads per block; two blocks per SM: one sweeps while the other counts
-constexpr int kSF2TileWords = 2032;                     // 65 024 bases; 24 KB of shared memory per block
+// THREADS reads per block, 1024 / THREADS blocks per SM (one sweeps while another counts); a tile of 4 * THREADS - 16
+// words (12 bytes of shared memory each): 2032 words = 65 024 bases = 24 KB for 512 threads
+template <int THREADS> __host__ __device__ constexpr int sf2_tile_words() { return 4 * THREADS - 16; }
 
-template <bool PLANES>
-__global__ void __launch_bounds__(kSF2Threads, 2)
+template <bool PLANES, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k_stage_filter(const uint8_t *__restrict__ bases, uint64_t readable, uint64_t n_bases, const uint64_t *__restrict__ offs,
                 uint64_t n_reads, uint4 *__restrict__ planes, FilterParams fp, uint32_t *__restrict__ bv, uint64_t n_bv_words,
                 uint8_t *__restrict__ classes, unsigned int *__restrict__ block_totals, BorderRec *__restrict__ border,
                 unsigned int border_cap, unsigned int *__restrict__ n_border)
 {
+    constexpr int T_WORDS = sf2_tile_words<THREADS>();
     extern __shared__ uint32_t sf2_smem[];              // H[T] | L[T] | V[T]
-    uint32_t *sH = sf2_smem, *sL = sH + kSF2TileWords, *sV = sL + kSF2TileWords;
+    uint32_t *sH = sf2_smem, *sL = sH + T_WORDS, *sV = sL + T_WORDS;
     __shared__ unsigned int tot[4];
     __shared__ uint64_t s_span[2];
     const uint32_t tid = threadIdx.x;
-    const uint64_t r_first = (uint64_t)blockIdx.x * kSF2Threads, r = r_first + tid;
+    const uint64_t r_first = (uint64_t)blockIdx.x * THREADS, r = r_first + tid;
     if (tid < 4) tot[tid] = 0;
     if (tid == 0) {
-        const uint64_t r_last = min(r_first + (uint64_t)kSF2Threads, n_reads);
+        const uint64_t r_last = min(r_first + (uint64_t)THREADS, n_reads);
         s_span[0] = r_first < n_reads ? offs[r_first] : 0;
         s_span[1] = r_first < n_reads ? offs[r_last] : 0;
     }
@@ -1680,9 +1682,9 @@ k_stage_filter(const uint8_t *__restrict__ bases, uint64_t readable, uint64_t n_
     const uint64_t o_first = s_span[0], e_last = s_span[1];
     const uint64_t ws = o_first >> 5, we = (e_last + 31) >> 5;
     unsigned int cnt[5] = {0, 0, 0, 0, 0};
-    for (uint64_t tw = ws; tw < we; tw += kSF2TileWords) {
-        const uint32_t n_w = (uint32_t)min((uint64_t)kSF2TileWords, we - tw);
-        for (uint32_t i = tid; i < n_w; i += kSF2Threads) {
+    for (uint64_t tw = ws; tw < we; tw += T_WORDS) {
+        const uint32_t n_w = (uint32_t)min((uint64_t)T_WORDS, we - tw);
+        for (uint32_t i = tid; i < n_w; i += THREADS) {
             const uint64_t w = tw + i, c = w << 5;
             const uint4 q0 = ld_nc_u4(reinterpret_cast<const uint4 *>(bases + c));
             uint4 q1 = make_uint4(0u, 0u, 0u, 0u);
@@ -1694,7 +1696,7 @@ k_stage_filter(const uint8_t *__restrict__ bases, uint64_t readable, uint64_t n_
             if (PLANES && c >= o_first) planes[w] = make_uint4(H, L, V, 0u);
         }
         __syncthreads();
-        const uint64_t lo = max(my_o, tw << 5), hi = min(my_e, (tw + kSF2TileWords) << 5);
+        const uint64_t lo = max(my_o, tw << 5), hi = min(my_e, (tw + T_WORDS) << 5);
         if (lo < hi) {
             for (uint64_t w = lo >> 5; (w << 5) < hi; w++) {
                 const uint32_t i = (uint32_t)(w - tw);
