@@ -1760,11 +1760,12 @@ static void launch_stage_filter(commet_ctx *c, unsigned n_blocks, const uint8_t 
                                 uint64_t n_bv_words, uint8_t *classes, unsigned int *totals, BorderRec *border,
                                 unsigned int border_cap, unsigned int *nb)
 {
-    if (env_or("COMMET_B200_SF_THREADS", 512) == 256)       // A/B (profiles/): four blocks of 256 reads per SM
-        k_stage_filter<PLANES, 256><<<n_blocks * (kFilterBlock / 256), 256, sf2_tile_words<256>() * 12, c->stream>>>(
+    // four blocks of 256 reads per SM: 6 % faster than two of 512 (profiles/r02_stage_filter_threads_ab.txt; the env selects the other)
+    if (env_or("COMMET_B200_SF_THREADS", 256) == 512)
+        k_stage_filter<PLANES, 512><<<n_blocks * (kFilterBlock / 512), 512, sf2_tile_words<512>() * 12, c->stream>>>(
                 d_bases, readable, n_bases, d_offs, n_reads, planes, fp, d_bv, n_bv_words, classes, totals, border, border_cap, nb);
     else
-        k_stage_filter<PLANES, 512><<<n_blocks * (kFilterBlock / 512), 512, sf2_tile_words<512>() * 12, c->stream>>>(
+        k_stage_filter<PLANES, 256><<<n_blocks * (kFilterBlock / 256), 256, sf2_tile_words<256>() * 12, c->stream>>>(
                 d_bases, readable, n_bases, d_offs, n_reads, planes, fp, d_bv, n_bv_words, classes, totals, border, border_cap, nb);
 }
 
