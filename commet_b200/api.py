@@ -71,6 +71,9 @@ _SIGS = {
     "commet_dist_index_and_search": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "commet_dist_close": (None, [C.c_void_p]),
+    "commet_dist_plan_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
+                                        C.c_uint64, C.c_void_p, C.c_void_p]),
+    "commet_dist_deal_regions": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "commet_group_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "commet_group_destroy": (None, [C.c_void_p]),
     "commet_group_size": (C.c_int, [C.c_void_p]),
@@ -235,6 +238,61 @@ class Dist:
             self.close()
         except Exception:
             pass
+
+
+def _comm_struct(world: int, rank: int, barrier, all_gather_bytes, errbox: list):
+    """a commet_comm over two Python callables (kept alive by the returned tuple)"""
+
+    def _barrier(_user):
+        try:
+            barrier()
+            return 0
+        except Exception as e:                  # an exception must not unwind through the C frames
+            errbox.append(e)
+            return -1
+
+    def _all_gather(_user, p_in, p_out, nbytes):
+        try:
+            parts = all_gather_bytes(C.string_at(p_in, nbytes))
+            C.memmove(p_out, b"".join(parts), nbytes * world)
+            return 0
+        except Exception as e:
+            errbox.append(e)
+            return -1
+
+    cbs = (_BARRIER_FN(_barrier), _ALLGATHER_FN(_all_gather))
+    return _CommStruct(world, rank, None, *cbs), cbs
+
+
+def dist_plan_host(world: int, rank: int, counts_local, n_global: int, block: int, maxk: int, barrier, all_gather_bytes,
+                   cap_chunks: int = 1 << 16):
+    """commet_dist_plan_host: the library's multi-rank chunk plan from host-side counts (no device).  Collective.
+    Returns ([(first, end), ...], chunk_kmers[world][n_chunks])."""
+    lib = load_library()
+    counts_local = np.ascontiguousarray(counts_local, dtype=np.uint32)
+    errbox: list = []
+    comm, _keep = _comm_struct(world, rank, barrier, all_gather_bytes, errbox)
+    bounds = np.zeros(2 * cap_chunks, dtype=np.uint64)
+    ck = np.zeros(world * cap_chunks, dtype=np.uint64)
+    n = C.c_uint64(0)
+    rc = lib.commet_dist_plan_host(C.byref(comm), _ptr(counts_local) if counts_local.size else None, counts_local.size, n_global,
+                                   block, maxk, _ptr(bounds), cap_chunks, C.byref(n), _ptr(ck))
+    if rc != 0:
+        raise CommetError(lib.commet_last_error().decode()) from (errbox[0] if errbox else None)
+    nc = int(n.value)
+    return ([(int(bounds[2 * i]), int(bounds[2 * i + 1])) for i in range(nc)],
+            ck[:world * nc].reshape(world, nc).astype(np.int64) if nc else np.zeros((world, 0), dtype=np.int64))
+
+
+def deal_regions(fills) -> np.ndarray:
+    """commet_dist_deal_regions: owner rank of every filter region from fills[world][n_bins] (records per rank and region)"""
+    lib = load_library()
+    fills = np.ascontiguousarray(fills, dtype=np.uint32)
+    world, n_bins = fills.shape
+    owner = np.zeros(n_bins, dtype=np.int32)
+    if lib.commet_dist_deal_regions(_ptr(fills), world, n_bins, _ptr(owner)) != 0:
+        raise CommetError(lib.commet_last_error().decode())
+    return owner
 
 
 class Group:

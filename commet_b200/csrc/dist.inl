@@ -169,23 +169,88 @@ k_range_sums(const uint32_t *__restrict__ counts, const uint64_t *__restrict__ r
     }
 }
 
-// Chunk plan of the whole set from this rank's shard (see the header of this file).  plan: pairs (first, end).
+// Where the per-read k-mer counts of a rank's shard live: on the device (the product's loop) or in a host array
+// (commet_dist_plan_host: the same walk, for the CPU tests of the multi-rank logic).  The walk below only ever asks for
+// per-block sums, the counts of one block, and sums over a few ranges.
+struct DeviceCounts {
+    commet_ctx *c;
+    const uint32_t *counts;             // device
+    uint64_t n_local;
+    int block_sums(uint64_t block, uint64_t my_blocks, uint64_t *out)
+    {
+        DevBuf sums(c);
+        if (sums.alloc(my_blocks * sizeof(unsigned long long)) != cudaSuccess) return fail("allocation of block sums failed");
+        k_block_sums<<<(unsigned)my_blocks, 256, 0, c->stream>>>(counts, n_local, block, sums.as<unsigned long long>());
+        c->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out, sums.p, my_blocks * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+    int fetch(uint64_t l0, uint64_t l1, std::vector<uint32_t> &blk)
+    {
+        blk.resize(l1 - l0);
+        if (l1 > l0) {
+            CK(cudaMemcpyAsync(blk.data(), counts + l0, (l1 - l0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        }
+        return 0;
+    }
+    int range_sums(const std::vector<uint64_t> &ranges, uint64_t *out)
+    {
+        const size_t n = ranges.size() / 2;
+        DevBuf d_ranges(c), d_sums(c);
+        if (d_ranges.alloc(ranges.size() * sizeof(uint64_t)) != cudaSuccess || d_sums.alloc(n * sizeof(unsigned long long)) != cudaSuccess)
+            return fail("allocation of chunk sums failed");
+        CK(cudaMemcpyAsync(d_ranges.p, ranges.data(), ranges.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        k_range_sums<<<(unsigned)n, 256, 0, c->stream>>>(counts, d_ranges.as<uint64_t>(), d_sums.as<unsigned long long>());
+        c->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out, d_sums.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+};
+
+struct HostCounts {
+    const uint32_t *counts;             // host
+    uint64_t n_local;
+    int block_sums(uint64_t block, uint64_t my_blocks, uint64_t *out)
+    {
+        for (uint64_t j = 0; j < my_blocks; j++) {
+            uint64_t acc = 0;
+            for (uint64_t i = j * block; i < std::min(n_local, (j + 1) * block); i++) acc += counts[i];
+            out[j] = acc;
+        }
+        return 0;
+    }
+    int fetch(uint64_t l0, uint64_t l1, std::vector<uint32_t> &blk)
+    {
+        blk.assign(counts + l0, counts + l1);
+        return 0;
+    }
+    int range_sums(const std::vector<uint64_t> &ranges, uint64_t *out)
+    {
+        for (size_t j = 0; j < ranges.size() / 2; j++) {
+            uint64_t acc = 0;
+            for (uint64_t i = ranges[2 * j]; i < ranges[2 * j + 1]; i++) acc += counts[i];
+            out[j] = acc;
+        }
+        return 0;
+    }
+};
+
+// Chunk plan of the whole set from this rank's counts (see the header of this file).  plan: pairs (first, end).
 // chunk_kmers[r * n_chunks + i]: k-mers of rank r's reads of chunk i (what its scatter will emit, times four).
-int dist_plan(commet_dist *d, commet_reads *shard, uint64_t n_global, uint64_t block, uint64_t max_kmer,
-              std::vector<uint64_t> &plan, std::vector<uint64_t> &chunk_kmers)
+// `total`: the sum of this rank's counts.
+template <class Counts>
+int dist_plan_walk(const commet_comm &cm, Counts &src, uint64_t total, uint64_t n_global, uint64_t block, uint64_t max_kmer,
+                   std::vector<uint64_t> &plan, std::vector<uint64_t> &chunk_kmers)
 {
-    commet_ctx *c = d->ctx;
-    const commet_comm &cm = d->comm;
     const uint64_t world = (uint64_t)cm.world, rank = (uint64_t)cm.rank;
+    const uint64_t n_local = src.n_local;
     plan.clear();
     chunk_kmers.clear();
-    const uint64_t n_local = local_index(n_global, world, rank, block);
-    if (shard->n_reads != n_local)
-        return fail("rank %d holds %llu reads, its blocks of %llu reads are %llu", cm.rank, (unsigned long long)shard->n_reads,
-                    (unsigned long long)n_global, (unsigned long long)n_local);
-    DevBuf counts(c);
-    unsigned long long total = 0;
-    CKR(count_kmers(c, shard, d->k, counts, &total));
     std::vector<uint64_t> totals(world, 0);
     uint64_t mine = total;
     if (world > 1) { if (cm.all_gather(cm.user, &mine, totals.data(), sizeof mine) != 0) return fail("all_gather failed"); }
@@ -203,15 +268,7 @@ int dist_plan(commet_dist *d, commet_reads *shard, uint64_t n_global, uint64_t b
     const uint64_t n_blocks = (n_global + block - 1) / block;
     const uint64_t my_blocks = (n_local + block - 1) / block, slots = (n_blocks + world - 1) / world;
     std::vector<uint64_t> mine_b(slots, 0), all_b(slots * world, 0);
-    if (my_blocks) {
-        DevBuf sums(c);
-        if (sums.alloc(my_blocks * sizeof(unsigned long long)) != cudaSuccess) return fail("allocation of block sums failed");
-        k_block_sums<<<(unsigned)my_blocks, 256, 0, c->stream>>>(counts.as<uint32_t>(), n_local, block, sums.as<unsigned long long>());
-        c->launches++;
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(mine_b.data(), sums.p, my_blocks * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-    }
+    if (my_blocks) CKR(src.block_sums(block, my_blocks, mine_b.data()));
     if (world > 1) { if (cm.all_gather(cm.user, mine_b.data(), all_b.data(), slots * sizeof(uint64_t)) != 0) return fail("all_gather failed"); }
     else all_b = mine_b;
     std::vector<uint64_t> csT(n_blocks);          // inclusive prefix over the global blocks
@@ -229,11 +286,7 @@ int dist_plan(commet_dist *d, commet_reads *shard, uint64_t n_global, uint64_t b
         Resolved r{0, 0, 0};
         if (owner == rank) {
             const uint64_t l0 = local_index(g0, world, rank, block), l1 = local_index(g1, world, rank, block);
-            blk.resize(l1 - l0);
-            if (l1 > l0) {
-                CK(cudaMemcpyAsync(blk.data(), counts.as<uint32_t>() + l0, (l1 - l0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-                CK(cudaStreamSynchronize(c->stream));
-            }
+            CKR(src.fetch(l0, l1, blk));
             uint64_t acc = 0;
             for (uint64_t i = 0; i < l1 - l0; i++) {
                 acc += blk[i];
@@ -251,7 +304,7 @@ int dist_plan(commet_dist *d, commet_reads *shard, uint64_t n_global, uint64_t b
     uint64_t i = 0;
     while (i < n_global) {
         const uint64_t b = i / block;
-        Resolved a;
+        Resolved a{0, 0, 0};
         CKR(ask(i, std::min((b + 1) * block, n_global), 0, a));            // from read i to the end of its block
         if (!a.found) {
             // whole blocks after b: the first one in which the running count reaches max_kmer
@@ -279,21 +332,51 @@ int dist_plan(commet_dist *d, commet_reads *shard, uint64_t n_global, uint64_t b
             ranges[2 * ci] = local_index(plan[2 * ci], world, rank, block);
             ranges[2 * ci + 1] = local_index(plan[2 * ci + 1], world, rank, block);
         }
-        DevBuf d_ranges(c), d_sums(c);
-        if (d_ranges.alloc(ranges.size() * sizeof(uint64_t)) != cudaSuccess || d_sums.alloc(n_chunks * sizeof(unsigned long long)) != cudaSuccess)
-            return fail("allocation of chunk sums failed");
-        CK(cudaMemcpyAsync(d_ranges.p, ranges.data(), ranges.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-        k_range_sums<<<(unsigned)n_chunks, 256, 0, c->stream>>>(counts.as<uint32_t>(), d_ranges.as<uint64_t>(), d_sums.as<unsigned long long>());
-        c->launches++;
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(mine_c.data(), d_sums.p, n_chunks * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        CKR(src.range_sums(ranges, mine_c.data()));
     }
     chunk_kmers.assign(world * n_chunks, 0);
     if (world > 1 && n_chunks) {
         if (cm.all_gather(cm.user, mine_c.data(), chunk_kmers.data(), n_chunks * sizeof(uint64_t)) != 0) return fail("all_gather failed");
     } else chunk_kmers = mine_c;
     return 0;
+}
+
+int dist_plan(commet_dist *d, commet_reads *shard, uint64_t n_global, uint64_t block, uint64_t max_kmer,
+              std::vector<uint64_t> &plan, std::vector<uint64_t> &chunk_kmers)
+{
+    commet_ctx *c = d->ctx;
+    const commet_comm &cm = d->comm;
+    plan.clear();
+    chunk_kmers.clear();
+    const uint64_t n_local = local_index(n_global, (uint64_t)cm.world, (uint64_t)cm.rank, block);
+    if (shard->n_reads != n_local)
+        return fail("rank %d holds %llu reads, its blocks of %llu reads are %llu", cm.rank, (unsigned long long)shard->n_reads,
+                    (unsigned long long)n_global, (unsigned long long)n_local);
+    DevBuf counts(c);
+    unsigned long long total = 0;
+    CKR(count_kmers(c, shard, d->k, counts, &total));
+    DeviceCounts src{c, counts.as<uint32_t>(), n_local};
+    return dist_plan_walk(cm, src, (uint64_t)total, n_global, block, max_kmer, plan, chunk_kmers);
+}
+
+// The regions of the filter dealt to the ranks by their record counts (fills[p * n_bins + b]: records rank p holds for region
+// b): largest region first, to the rank with the fewest records so far -- every rank computes the same assignment from
+// the same numbers.  (+ 1 per region: empty regions are dealt evenly too.)
+void deal_regions(const uint32_t *fills, int world, int n_bins, int *owner)
+{
+    std::vector<uint64_t> tot(n_bins, 0), load(world, 0);
+    for (int b = 0; b < n_bins; b++)
+        for (int p = 0; p < world; p++) tot[b] += fills[(size_t)p * n_bins + b];
+    std::vector<int> order(n_bins);
+    for (int b = 0; b < n_bins; b++) order[b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tot[x] > tot[y]; });
+    for (int b : order) {
+        int best = 0;
+        for (int p = 1; p < world; p++)
+            if (load[p] < load[best]) best = p;
+        owner[b] = best;
+        load[best] += tot[b] + 1;
+    }
 }
 
 struct InsertInfo {                 // what the ranks exchange before an owner-applied insert
@@ -478,19 +561,8 @@ extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_
             for (int p = 0; p < cm.world; p++)
                 CK(cudaMemcpyAsync(h_fills.data() + (size_t)p * n_bins, pi.fill[p], (size_t)n_bins * sizeof(uint32_t), cudaMemcpyDefault, c->stream));
             CK(cudaStreamSynchronize(c->stream));
-            std::vector<uint64_t> tot(n_bins, 0), load(world, 0);
-            for (int b = 0; b < n_bins; b++)
-                for (int p = 0; p < cm.world; p++) tot[b] += h_fills[(size_t)p * n_bins + b];
-            std::vector<int> order(n_bins), owner(n_bins, 0);
-            for (int b = 0; b < n_bins; b++) order[b] = b;
-            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tot[x] > tot[y]; });
-            for (int b : order) {
-                int best = 0;
-                for (int p = 1; p < cm.world; p++)
-                    if (load[p] < load[best]) best = p;
-                owner[b] = best;
-                load[best] += tot[b] + 1;                  // + 1: empty regions are dealt evenly too
-            }
+            std::vector<int> owner(n_bins, 0);
+            deal_regions(h_fills.data(), cm.world, n_bins, owner.data());
             uint32_t n_own = 0, n_list = 0;
             for (int b = 0; b < n_bins; b++)
                 if (owner[b] == cm.rank) h_meta[n_own++] = (uint32_t)b;
@@ -594,6 +666,41 @@ extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_
         stats[10] = plan.size() >= 2 ? plan[plan.size() - 1] : 0;
         stats[11] = owner_mode ? 1 : 0;
     }
+    return 0;
+}
+
+// ---- host-only entry points to the multi-rank logic (no device, no context): the CPU tests drive them over gloo ------
+// The chunk plan of a set whose per-read k-mer counts are dealt block-cyclically over the ranks: `counts` = this rank's
+// counts in local order.  bounds: n_chunks pairs (first, end); chunk_kmers[r * n_chunks + i].  Collective.
+extern "C" int commet_dist_plan_host(const commet_comm *comm, const uint32_t *counts, uint64_t n_local, uint64_t n_global,
+                                     uint64_t block, uint64_t max_kmer, uint64_t *bounds, uint64_t cap_chunks, uint64_t *n_chunks,
+                                     uint64_t *chunk_kmers)
+{
+    if (!comm || comm->world < 1 || comm->rank < 0 || comm->rank >= comm->world || block == 0 || !n_chunks)
+        return fail("commet_dist_plan_host: bad arguments");
+    if (comm->world > 1 && (!comm->all_gather || !comm->barrier)) return fail("commet_dist_plan_host: callbacks missing");
+    if (n_local != local_index(n_global, (uint64_t)comm->world, (uint64_t)comm->rank, block))
+        return fail("rank %d holds %llu counts, its blocks of %llu reads are %llu", comm->rank, (unsigned long long)n_local,
+                    (unsigned long long)n_global,
+                    (unsigned long long)local_index(n_global, (uint64_t)comm->world, (uint64_t)comm->rank, block));
+    HostCounts src{counts, n_local};
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n_local; i++) total += counts[i];
+    std::vector<uint64_t> plan, ck;
+    CKR(dist_plan_walk(*comm, src, total, n_global, block, max_kmer, plan, ck));
+    *n_chunks = plan.size() / 2;
+    if (*n_chunks > cap_chunks) return fail("commet_dist_plan_host: %llu chunks, room for %llu", (unsigned long long)*n_chunks, (unsigned long long)cap_chunks);
+    if (bounds) memcpy(bounds, plan.data(), plan.size() * sizeof(uint64_t));
+    if (chunk_kmers) memcpy(chunk_kmers, ck.data(), ck.size() * sizeof(uint64_t));
+    return 0;
+}
+
+// owner[b] of every filter region from the record counts fills[p * n_bins + b] of all ranks (what every rank computes
+// before an owner-applied insert)
+extern "C" int commet_dist_deal_regions(const uint32_t *fills, int world, int n_bins, int *owner)
+{
+    if (!fills || !owner || world < 1 || n_bins < 1) return fail("commet_dist_deal_regions: bad arguments");
+    deal_regions(fills, world, n_bins, owner);
     return 0;
 }
 

@@ -152,8 +152,10 @@ int commet_index_merge(commet_ctx *ctx, void *const *d_filters, int n_ranks, int
 /* ---- multi-GPU: the chunk loop of src/index_and_search.cpp:255-277 with the index set dealt over the ranks ----
  * One rank = one GPU.  Block b of `block` consecutive reads of the index set's valid-read stream lives on rank
  * b % world: a rank stages only its own blocks (its SHARD, reads in global order), and every chunk is a contiguous
- * range of local reads on every rank.  Per chunk every rank inserts its reads into its own filter, the partial
- * filters are merged by commet_index_merge, and every rank probes its own query streams.  The stop rule of
+ * range of local reads on every rank.  Per chunk every rank turns its reads into key records; every region of the
+ * filter is applied by ONE owner rank, which reads its peers' records out of their memory, and the finished regions
+ * are gathered by everybody (or, for small k / COMMET_B200_DIST_MODE=merge: every rank inserts into its own filter
+ * and the partial filters are merged by commet_index_merge); then every rank probes its own query streams.  The stop rule of
  * index_reads (include/index_reads.h:48-49,60) is evaluated on k-mer counts the ranks exchange: totals, then
  * per-block totals, then the one read that closes each chunk -- the plan equals commet_chunk_plan's on the whole set.
  *
@@ -182,6 +184,18 @@ int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_kmer, comme
                                  uint64_t block, int n_sets, commet_reads *const *queries, uint32_t *const *d_tags,
                                  uint64_t *searched, uint64_t *shared, uint64_t *stats);
 void commet_dist_close(commet_dist *d);
+/* The host logic of that loop on its own -- no device, no context -- so that it can be driven on CPU-only hosts (the
+ * world_size-2/3 gloo tests; a planner that only has the counts).
+ * commet_dist_plan_host: collective; the chunk plan (include/index_reads.h:41-63 on the whole set) from per-read k-mer
+ * counts dealt block-cyclically over the ranks: `counts` = this rank's, in local order (n_local of them).  bounds:
+ * *n_chunks pairs (first read, end read) in global numbering -- the read after `end` is the one fetched and lost;
+ * chunk_kmers[r * *n_chunks + i] = k-mers rank r contributes to chunk i.  Fails if there are more than cap_chunks.
+ * commet_dist_deal_regions: the owner rank of every filter region from all ranks' record counts
+ * (fills[p * n_bins + b]), as every rank computes it before an owner-applied insert. */
+int commet_dist_plan_host(const commet_comm *comm, const uint32_t *counts, uint64_t n_local, uint64_t n_global,
+                          uint64_t block, uint64_t max_kmer, uint64_t *bounds, uint64_t cap_chunks, uint64_t *n_chunks,
+                          uint64_t *chunk_kmers);
+int commet_dist_deal_regions(const uint32_t *fills, int world, int n_bins, int *owner);
 
 /* The same over several GPUs of ONE process, behind the signature of commet_index_and_search: a thread per
  * device stages its shard of the index set and its slice of every query set (contiguous reads, cut at multiples

@@ -284,3 +284,112 @@ def test_two_level_distributed_plan_equals_the_global_walk():
             counts[rng.integers(0, n, size=max(1, n // 4))] = 0
         maxk = int(rng.choice([1, 2, 5, 17, 60, 10 ** 6]))
         assert _plan_in_lockstep(counts, world, block, maxk) == multi.chunk_bounds(counts, maxk), (trial, n, world, block, maxk)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the LIBRARY's multi-rank host logic (commet_b200/csrc/dist.inl), not its Python mirror: the chunk plan from counts
+# dealt over the ranks (commet_dist_plan_host = the walk commet_dist_index_and_search runs, on host counts) with its
+# collectives served by gloo, and the dealing of the filter regions to owner ranks
+# ----------------------------------------------------------------------------------------------------------------
+def _plan_counts(seed, n):
+    """per-read k-mer counts with everything the stop rule trips over: zeros, runs of zeros, a few huge reads"""
+    rng = np.random.default_rng(seed)
+    c = rng.integers(0, 120, n).astype(np.uint32)
+    c[rng.random(n) < 0.15] = 0
+    if n > 40:
+        z = int(rng.integers(0, n - 30))
+        c[z:z + 25] = 0
+        c[rng.integers(0, n, 3)] = 5000
+    return c
+
+
+def _worker_plan(rank, world, port, cases, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from commet_b200 import api
+
+        def all_gather_bytes(b):
+            t_in = torch.frombuffer(bytearray(b), dtype=torch.uint8)
+            outs = [torch.empty(len(b), dtype=torch.uint8) for _ in range(world)]
+            dist.all_gather(outs, t_in)
+            return [o.numpy().tobytes() for o in outs]
+
+        res = []
+        for seed, n, block, maxk in cases:
+            counts = _plan_counts(seed, n)
+            mine = counts[multi.owned_mask(n, world, rank, block)]
+            plan, ck = api.dist_plan_host(world, rank, mine, n, block, maxk, dist.barrier, all_gather_bytes)
+            res.append((plan, ck.tolist()))
+        import pickle
+        (Path(out_dir) / f"plan{rank}.pkl").write_bytes(pickle.dumps(res))
+    finally:
+        dist.destroy_process_group()
+
+
+PLAN_CASES = [(1, 900, 64, 10 ** 9), (2, 900, 64, 4000), (3, 700, 7, 9000), (4, 500, 1, 2500), (5, 1000, 50, 1), (6, 64, 64, 300),
+              (7, 333, 16, 5000), (8, 2000, 100, 20000), (9, 10, 4, 10 ** 6), (10, 0, 8, 100), (11, 1, 8, 1), (12, 129, 64, 5001)]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_library_chunk_plan_over_gloo_equals_the_global_walk(tmp_path, world):
+    """commet_dist_plan_host on every rank's block-cyclic share of the counts = the stop rule walked over all counts
+    (index_reads.h:48-49,60), the read after every chunk lost; every rank gets the same plan; the per-rank k-mer
+    shares of every chunk are the sums of that rank's counts inside it"""
+    import pickle
+    mp.spawn(_worker_plan, args=(world, _free_port(), PLAN_CASES, str(tmp_path)), nprocs=world, join=True)
+    got = [pickle.loads((tmp_path / f"plan{r}.pkl").read_bytes()) for r in range(world)]
+    multi_chunk = 0
+    for ci, (seed, n, block, maxk) in enumerate(PLAN_CASES):
+        counts = _plan_counts(seed, n)
+        want = multi.chunk_bounds(counts, maxk)
+        for r in range(world):
+            plan, ck = got[r][ci]
+            assert plan == want, (world, r, PLAN_CASES[ci], plan[:4], want[:4])
+            mask = multi.owned_mask(n, world, r, block)
+            for p in range(world):
+                pm = multi.owned_mask(n, world, p, block)
+                assert ck[p] == [int(counts[a:b][pm[a:b]].sum()) for a, b in want], (world, r, p, PLAN_CASES[ci])
+            del mask
+        multi_chunk += len(want) > 2
+    assert multi_chunk >= 6             # chunk boundaries inside blocks, on block edges, lost reads at block starts
+
+
+def test_library_plan_single_rank_and_argument_checks():
+    from commet_b200 import api
+    for seed, n, block, maxk in PLAN_CASES:
+        counts = _plan_counts(seed, n)
+        plan, ck = api.dist_plan_host(1, 0, counts, n, block, maxk, lambda: None, lambda b: [b])
+        assert plan == multi.chunk_bounds(counts, maxk)
+        assert ck.tolist() == [[int(counts[a:b].sum()) for a, b in plan]]
+    with pytest.raises(api.CommetError, match="holds"):            # a rank that does not hold its blocks
+        api.dist_plan_host(2, 0, np.zeros(10, dtype=np.uint32), 100, 8, 50, lambda: None, lambda b: [b, b])
+    with pytest.raises(api.CommetError, match="room for"):
+        api.dist_plan_host(1, 0, np.full(100, 10, dtype=np.uint32), 100, 8, 10, lambda: None, lambda b: [b], cap_chunks=3)
+
+
+def test_library_region_dealing_is_a_balanced_partition():
+    from commet_b200 import api
+    rng = np.random.default_rng(7)
+    for world in (1, 2, 3, 4, 8):
+        for n_bins in (world, 16, 128, 512):
+            if n_bins < world:
+                continue
+            # the d-key regions are hot (3/4 of its bits are ones): a few regions hold several times the mean
+            tot = rng.integers(1000, 3000, n_bins).astype(np.int64)
+            tot[rng.integers(0, n_bins, max(1, n_bins // 16))] *= 5
+            fills = np.zeros((world, n_bins), dtype=np.uint32)
+            for b in range(n_bins):
+                fills[:, b] = rng.multinomial(int(tot[b]), np.ones(world) / world)
+            owner = api.deal_regions(fills)
+            assert owner.shape == (n_bins,) and owner.min() >= 0 and owner.max() < world
+            load = np.array([int(tot[owner == p].sum()) for p in range(world)])
+            # greedy largest-first: no rank exceeds the mean by more than the largest region
+            assert load.max() <= tot.sum() / world + tot.max(), (world, n_bins, load)
+            if n_bins >= 8 * world:
+                assert load.max() <= 1.1 * tot.sum() / world, (world, n_bins, load)
+            again = api.deal_regions(fills)
+            assert np.array_equal(owner, again)             # deterministic: every rank computes the same owners
+    empty = api.deal_regions(np.zeros((4, 128), dtype=np.uint32))
+    assert np.bincount(empty, minlength=4).tolist() == [32, 32, 32, 32]     # empty regions are dealt evenly too
