@@ -179,3 +179,59 @@ def test_parallel_fasta_path_of_the_tools_equals_the_sequential_one(driver, tmp_
     rows = outs[0].split(b"\n")
     assert rows[0] == b"SET\tbig\t1\t%d" % n
     assert rows[1] == arr[0].tobytes() and rows[n] == arr[n - 1].tobytes()
+
+
+def test_encode_arithmetic_of_the_staging_kernels_on_every_byte(tmp_path):
+    """encode_word / encode32 (commet_b200/csrc/kernels.cuh: what k_encode and k_stage_filter compute per 32 bases) compiled
+    for the host out of the kernel source: H, L and the validity bit of every byte value in every lane of a word, with
+    arbitrary neighbours, against the per-character definition (hash_key.h:65-91 A=00 C=01 G=10 T=11; alphabet.h:44-58)."""
+    import subprocess
+    src = (ROOT / "commet_b200" / "csrc" / "kernels.cuh").read_text()
+    fn = src[src.index("__device__ __forceinline__ void encode_word("):src.index("__global__ void __launch_bounds__(256)\nk_encode(")]
+    (tmp_path / "e.cpp").write_text(r'''
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#define __device__
+#define __forceinline__ inline
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) { return (hi << s) | (lo >> (32 - s)); }
+''' + fn + r'''
+static bool is_in(uint8_t c) { return c && strchr("ACGTacgt", c) != nullptr; }
+int main() {
+    std::mt19937_64 rng(1);
+    unsigned long long checked = 0;
+    for (int round = 0; round < 2048; round++) {
+        uint8_t b[32];
+        for (int i = 0; i < 32; i++) {
+            uint64_t r = rng();
+            b[i] = round % 3 == 0 ? (uint8_t)r : (round % 3 == 1 ? "ACGTacgtNn-*"[r % 12] : "ACGT"[r % 4]);
+        }
+        for (int lane = 0; lane < 32; lane++)
+            for (int v = 0; v < 256; v += (round < 8 ? 1 : 37)) {           // every value in every lane for the first rounds
+                uint8_t s[32];
+                memcpy(s, b, 32);
+                s[lane] = (uint8_t)(v + (round < 8 ? 0 : round) & 255);
+                uint4 q0, q1;
+                memcpy(&q0, s, 16);
+                memcpy(&q1, s + 16, 16);
+                uint32_t H, L, V;
+                encode32(q0, q1, H, L, V);
+                for (int i = 0; i < 32; i++) {
+                    const uint8_t c = s[i];
+                    const uint32_t h = (c >> 2) & 1u, l = ((c >> 1) ^ (c >> 2)) & 1u, ok = is_in(c);
+                    if (((H >> i) & 1u) != h || ((L >> i) & 1u) != l || ((V >> i) & 1u) != ok) {
+                        printf("byte %d of the word = 0x%02x: H %u/%u L %u/%u V %u/%u\n", i, c, (H >> i) & 1u, h, (L >> i) & 1u, l, (V >> i) & 1u, ok);
+                        return 1;
+                    }
+                    checked++;
+                }
+            }
+    }
+    printf("ok %llu\n", checked);
+    return 0;
+}''')
+    subprocess.run(["g++", "-std=c++17", "-O2", "-o", str(tmp_path / "e"), str(tmp_path / "e.cpp")], check=True)
+    out = subprocess.run([str(tmp_path / "e")], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("ok "), out.stdout + out.stderr
