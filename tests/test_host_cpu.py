@@ -235,3 +235,68 @@ int main() {
     subprocess.run(["g++", "-std=c++17", "-O2", "-o", str(tmp_path / "e"), str(tmp_path / "e.cpp")], check=True)
     out = subprocess.run([str(tmp_path / "e")], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("ok "), out.stdout + out.stderr
+
+
+def test_key_arithmetic_of_the_kernels_against_the_oracle_filter(tmp_path):
+    """make_keys / key_word / key_bit (commet_b200/csrc/kernels.cuh: the four keys of a k-mer as windows of the bit-planes and
+    their place in the filter) compiled for the host out of the kernel source: the filter they build from a read equals the
+    oracle's (hash_key.h:65-91, bloom_filter.h:112-131), and the reverse keys of the reverse complement are the forward
+    keys of the read, mirrored (hash_key.h:99-125)."""
+    import subprocess
+    import numpy as np
+    from oracle import oracle
+    src = (ROOT / "commet_b200" / "csrc" / "kernels.cuh").read_text()
+    fn = src[src.index("struct Keys { uint64_t a, b, c, d; };"):src.index("// ------------------------------------------------------------- staging ----")]
+    (tmp_path / "k.cpp").write_text(r'''
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#define __device__
+#define __forceinline__ inline
+static inline uint64_t __brevll(uint64_t x) { uint64_t r = 0; for (int i = 0; i < 64; i++) r |= ((x >> i) & 1ull) << (63 - i); return r; }
+''' + fn + r'''
+static int code(char c) { switch (c) { case 'A': return 0; case 'C': return 1; case 'G': return 2; default: return 3; } }
+// plane windows of the k-mer starting at p: bit i = base p + i
+static void planes(const std::string &s, size_t p, int k, uint64_t &hv, uint64_t &lv)
+{
+    hv = lv = 0;
+    for (int i = 0; i < k; i++) { int c = code(s[p + i]); hv |= (uint64_t)(c >> 1) << i; lv |= (uint64_t)(c & 1) << i; }
+}
+int main(int argc, char **argv)
+{
+    const int k = atoi(argv[1]);
+    const std::string s = argv[2];
+    std::string rc(s.rbegin(), s.rend());
+    for (char &c : rc) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'A';
+    const uint64_t mask = k == 64 ? ~0ull : (1ull << k) - 1;
+    std::vector<uint32_t> filt((((size_t)1 << (k - 1)) + 3) / 4, 0);
+    const size_t n = s.size() - k + 1;
+    for (size_t p = 0; p < n; p++) {
+        uint64_t hv, lv;
+        planes(s, p, k, hv, lv);
+        Keys f = make_keys(hv, lv, k, mask, false);
+        const uint64_t key[4] = {f.a, f.b, f.c, f.d};
+        for (int j = 0; j < 4; j++) filt[key_word(key[j])] |= key_bit(key[j], j);
+        planes(rc, n - 1 - p, k, hv, lv);
+        Keys r = make_keys(hv, lv, k, mask, true);
+        if (r.a != f.a || r.b != f.b || r.c != f.c || r.d != f.d) { printf("reverse keys differ at %zu\n", p); return 1; }
+        if (k <= 32 && (key_word((uint32_t)f.a) != key_word(f.a) || key_bit((uint32_t)f.d, 3) != key_bit(f.d, 3))) { puts("32-bit overloads differ"); return 1; }
+    }
+    const uint8_t *b = reinterpret_cast<const uint8_t *>(filt.data());
+    for (size_t i = 0; i < ((size_t)1 << (k - 1)); i++) printf("%02x", b[i]);
+    puts("");
+    return 0;
+}''')
+    subprocess.run(["g++", "-std=c++17", "-O2", "-o", str(tmp_path / "k"), str(tmp_path / "k.cpp")], check=True)
+    rng = np.random.default_rng(3)
+    for k in (1, 2, 3, 4, 5, 8, 11, 13, 16, 17):
+        for _ in range(3):
+            seq = "".join("ACGT"[i] for i in rng.integers(0, 4, int(rng.integers(k, k + 60))))
+            out = subprocess.run([str(tmp_path / "k"), str(k), seq], capture_output=True, text=True)
+            assert out.returncode == 0, out.stdout
+            got = np.frombuffer(bytes.fromhex(out.stdout.strip()), dtype=np.uint8)
+            want = np.zeros(oracle.filter_bytes(k), dtype=np.uint8)
+            oracle.index_chunk(want, k, np.frombuffer(seq.encode(), dtype=np.uint8), np.array([0, len(seq)], dtype=np.uint64), 0, 1 << 62)
+            assert np.array_equal(got, want), (k, seq)
