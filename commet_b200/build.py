@@ -39,7 +39,8 @@ def _stale(target: Path, sources) -> bool:
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> Path:
-    srcs = [CSRC / "capi.cu", CSRC / "kernels.cuh", CSRC / "dist.inl", ROOT / "include" / "commet_b200.h"]
+    srcs = [CSRC / "capi.cu", CSRC / "kernels.cuh", *sorted((CSRC / "kernels").glob("*.cuh")), CSRC / "dist.inl",
+            ROOT / "include" / "commet_b200.h"]
     if force or _stale(LIB, srcs):
         LIB.parent.mkdir(parents=True, exist_ok=True)
         cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "capi.cu")]

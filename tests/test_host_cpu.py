@@ -182,11 +182,11 @@ def test_parallel_fasta_path_of_the_tools_equals_the_sequential_one(driver, tmp_
 
 
 def test_encode_arithmetic_of_the_staging_kernels_on_every_byte(tmp_path):
-    """encode_word / encode32 (commet_b200/csrc/kernels.cuh: what k_encode and k_stage_filter compute per 32 bases) compiled
+    """encode_word / encode32 (commet_b200/csrc/kernels/staging.cuh: what k_encode and k_stage_filter compute per 32 bases) compiled
     for the host out of the kernel source: H, L and the validity bit of every byte value in every lane of a word, with
     arbitrary neighbours, against the per-character definition (hash_key.h:65-91 A=00 C=01 G=10 T=11; alphabet.h:44-58)."""
     import subprocess
-    src = (ROOT / "commet_b200" / "csrc" / "kernels.cuh").read_text()
+    src = (ROOT / "commet_b200" / "csrc" / "kernels" / "staging.cuh").read_text()
     fn = src[src.index("__device__ __forceinline__ void encode_word("):src.index("__global__ void __launch_bounds__(256)\nk_encode(")]
     (tmp_path / "e.cpp").write_text(r'''
 #include <cstdint>
@@ -238,15 +238,15 @@ int main() {
 
 
 def test_key_arithmetic_of_the_kernels_against_the_oracle_filter(tmp_path):
-    """make_keys / key_word / key_bit (commet_b200/csrc/kernels.cuh: the four keys of a k-mer as windows of the bit-planes and
+    """make_keys / key_word / key_bit (commet_b200/csrc/kernels/common.cuh: the four keys of a k-mer as windows of the bit-planes and
     their place in the filter) compiled for the host out of the kernel source: the filter they build from a read equals the
     oracle's (hash_key.h:65-91, bloom_filter.h:112-131), and the reverse keys of the reverse complement are the forward
     keys of the read, mirrored (hash_key.h:99-125)."""
     import subprocess
     import numpy as np
     from oracle import oracle
-    src = (ROOT / "commet_b200" / "csrc" / "kernels.cuh").read_text()
-    fn = src[src.index("struct Keys { uint64_t a, b, c, d; };"):src.index("// ------------------------------------------------------------- staging ----")]
+    src = (ROOT / "commet_b200" / "csrc" / "kernels" / "common.cuh").read_text()
+    fn = src[src.index("struct Keys { uint64_t a, b, c, d; };"):src.rindex("}  // namespace commet")]
     (tmp_path / "k.cpp").write_text(r'''
 #include <cstdint>
 #include <cstdio>
