@@ -39,7 +39,7 @@ def _stale(target: Path, sources) -> bool:
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> Path:
-    srcs = [CSRC / "capi.cu", CSRC / "kernels.cuh", *sorted((CSRC / "kernels").glob("*.cuh")), CSRC / "dist.inl",
+    srcs = [CSRC / "capi.cu", *sorted((CSRC / "capi").glob("*.inl")), CSRC / "kernels.cuh", *sorted((CSRC / "kernels").glob("*.cuh")),
             ROOT / "include" / "commet_b200.h"]
     if force or _stale(LIB, srcs):
         LIB.parent.mkdir(parents=True, exist_ok=True)

@@ -287,7 +287,7 @@ def test_two_level_distributed_plan_equals_the_global_walk():
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# the LIBRARY's multi-rank host logic (commet_b200/csrc/dist.inl), not its Python mirror: the chunk plan from counts
+# the LIBRARY's multi-rank host logic (commet_b200/csrc/capi/dist.inl), not its Python mirror: the chunk plan from counts
 # dealt over the ranks (commet_dist_plan_host = the walk commet_dist_index_and_search runs, on host counts) with its
 # collectives served by gloo, and the dealing of the filter regions to owner ranks
 # ----------------------------------------------------------------------------------------------------------------
