@@ -524,14 +524,18 @@ extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_
         CK(cudaEventCreateWithFlags(&ev_gather, cudaEventDisableTiming));
         CKR(prepare(c, shard, k));
     }
-    DevBuf meta_buf(c);                        // own_bins[512] | fills[512] | tbase[513] | gather list[512]
-    if (owner_mode && meta_buf.alloc(2049 * sizeof(uint32_t)) != cudaSuccess) return fail("allocation of the owner tables failed");
-    std::vector<uint32_t> h_fills((size_t)world * std::max(n_bins, 1)), h_meta(2049);
+    // owner tables: own_bins[n_bins] | fills[pairs] | tbase[pairs + 1] | gather list[n_bins], pairs = (own region, source rank):
+    // the regions are dealt by record count, so a rank may own more than n_bins / world of them -- sized for any dealing
+    const size_t nb1 = (size_t)std::max(n_bins, 1), cap_pairs = nb1 * world;
+    const size_t o_fills = nb1, o_tbase = o_fills + cap_pairs, o_glist = o_tbase + cap_pairs + 1, n_meta = o_glist + nb1;
+    DevBuf meta_buf(c);
+    if (owner_mode && meta_buf.alloc(n_meta * sizeof(uint32_t)) != cudaSuccess) return fail("allocation of the owner tables failed");
+    std::vector<uint32_t> h_fills((size_t)world * nb1), h_meta(n_meta);
     const uint64_t region_bytes = 1ull << kRegionLog2;
     for (size_t ci = 0; ci + 1 < plan.size(); ci += 2) {
         const uint64_t lo = local_index(plan[ci], world, rank, block), hi = local_index(plan[ci + 1], world, rank, block);
         if (owner_mode) {
-            uint32_t *d_own = meta_buf.as<uint32_t>(), *d_fills = d_own + 512, *d_tbase = d_own + 1024, *d_glist = d_own + 1537;
+            uint32_t *d_own = meta_buf.as<uint32_t>(), *d_fills = d_own + o_fills, *d_tbase = d_own + o_tbase, *d_glist = d_own + o_glist;
             unsigned long long *tile_counter = c->bins + 1700;
             if (ci > 0) {
                 // my regions of the previous chunk are still being pulled by the peers: nobody clears before everybody has them
@@ -571,11 +575,11 @@ extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_
             for (uint32_t i = 0; i < n_own; i++)
                 for (int p = 0; p < cm.world; p++) {
                     const uint32_t f = h_fills[(size_t)p * n_bins + h_meta[i]];
-                    h_meta[512 + i * world + p] = f;
-                    h_meta[1024 + i * world + p] = acc;
+                    h_meta[o_fills + i * world + p] = f;
+                    h_meta[o_tbase + i * world + p] = acc;
                     acc += (f + 2047) / 2048;
                 }
-            h_meta[1024 + n_pairs] = acc;
+            h_meta[o_tbase + n_pairs] = acc;
             if (acc > tile_bound) return fail("tile list too small (%u tiles, room for %llu)", acc, (unsigned long long)tile_bound);
             // the regions to pull, round-robin over their owners (concurrent pieces come from different peers)
             {
@@ -585,11 +589,11 @@ extern "C" int commet_dist_index_and_search(commet_dist *d, int t, uint64_t max_
                 for (size_t j = 0;; j++) {
                     bool any = false;
                     for (uint64_t p = 0; p < world; p++)
-                        if (j < by_owner[p].size()) { h_meta[1537 + n_list++] = by_owner[p][j]; any = true; }
+                        if (j < by_owner[p].size()) { h_meta[o_glist + n_list++] = by_owner[p][j]; any = true; }
                     if (!any) break;
                 }
             }
-            CK(cudaMemcpyAsync(d_own, h_meta.data(), 2049 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(d_own, h_meta.data(), n_meta * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
             CK(cudaMemsetAsync(tile_counter, 0, sizeof(unsigned long long), c->stream));
             for (uint32_t i = 0; i < n_own; i++)
                 CK(cudaMemsetAsync(reinterpret_cast<uint8_t *>(c->filter) + (uint64_t)h_meta[i] * region_bytes, 0, region_bytes, c->stream));
