@@ -40,3 +40,36 @@ def test_reference_arm_line():
 
 def test_reference_arm_other_ranks_do_nothing():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}).strip() == ""
+
+
+def test_roofline_traffic_file_is_what_the_committed_capture_says(tmp_path):
+    """bench.py reads roofline.traffic from profiles/ncu_traffic.json: that file must be exactly what
+    scripts/ncu_traffic.py derives from the committed ncu --set full summary, and carry the search kernel of the
+    bench workload (bench.ncu_traffic returns it for C2 and nothing for another workload)."""
+    dst = tmp_path / "t.json"
+    r = subprocess.run([sys.executable, str(ROOT / "scripts" / "ncu_traffic.py"), str(ROOT / "profiles" / "r02_ncu_full_summary.csv"),
+                        str(dst)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    want = json.loads(dst.read_text())
+    got = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+    assert got["kernels"] == want["kernels"] and got["workload"] == want["workload"]
+    sys.path.insert(0, str(ROOT))
+    import bench
+    c2 = {"reads_per_set": 10_000_000, "read_len": 100, "k": 33, "t": 2}
+    s = got["kernels"]["k_search"]
+    assert bench.ncu_traffic("k_search", c2) == s["dram_bytes_per_launch"] and abs(s["dram_bytes_per_launch"] - s["dram_read"] - s["dram_write"]) <= 2
+    assert bench.ncu_traffic("k_search", {**c2, "k": 27}) is None
+    # 64-byte fills: between one and two 32-byte sectors per reference-semantics bit test of the committed bench line
+    line = json.loads((ROOT / "profiles" / "r02_bench_n1.json").read_text())
+    tests_ = line["kernels"]["n_probes"]
+    assert 32 * tests_ < s["dram_bytes_per_launch"] < 64 * tests_
+
+
+def test_committed_launch_summary_is_what_the_committed_launch_list_says():
+    """profiles/r02_launches_summary.txt = scripts/launch_summary.py over profiles/r02_launches.csv (the ncu launch list of
+    bench.py --steps 2 --warmup 1): the kernel shares DESIGN.md quotes come from the committed list"""
+    r = subprocess.run([sys.executable, str(ROOT / "scripts" / "launch_summary.py"), str(ROOT / "profiles" / "r02_launches.csv")],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == (ROOT / "profiles" / "r02_launches_summary.txt").read_text().strip()
+    assert "k_search<0, 2, 5, 0>" in r.stdout and "k_bin_apply2<2048, 1>" in r.stdout and "k_bin_scatter2<96>" in r.stdout
