@@ -15,7 +15,7 @@ static float shannon_from_counts(const unsigned int cnt[5], unsigned int len)
     return fabsf(index);
 }
 
-// Shared tail of the two filter kernels: `launch` runs k_filter (bit-planes) or k_filter_ascii (fused with the
+// Shared tail of the two filter kernels: `launch` runs k_filter (bit-planes) or k_stage_filter (fused with the
 // staging pass); then the undecided reads are settled, the -m cutoff located and the counters fetched.
 template <class Launch>
 static int filter_run(commet_ctx *c, uint64_t n, int64_t min_len, int64_t max_N, float min_shannon, int64_t max_reads,

@@ -140,9 +140,9 @@ k_filter(const uint4 *__restrict__ planes, const uint64_t *__restrict__ offs, ui
 // are popcounts of those bits restricted to the read's range -- no per-byte counting at all; with PLANES the bits
 // are also stored as the stream's bit-planes, so a set that is filtered AND indexed is read from HBM once.
 // `bases`: 16-byte aligned, readable up to `readable` bytes (a multiple of 16 >= the last offset = n_bases).
-// The same fusion with k_encode's regularity.  A block takes 1024 consecutive reads (the unit of k_filter's outputs)
-// and sweeps the WORDS of their span of the stream, a tile of sf2_tile_words() at a time: thread t encodes words t, t+1024,
-// ... -- every word once, perfectly balanced, coalesced 32-byte loads -- into shared memory (and, with PLANES, into
+// The same fusion with k_encode's regularity.  A block takes THREADS consecutive reads (kFilterBlock / THREADS blocks
+// share one unit of k_filter's outputs) and sweeps the WORDS of their span of the stream, a tile of sf2_tile_words() at a
+// time: thread t encodes words t, t + THREADS, ... -- every word once, perfectly balanced, coalesced 32-byte loads -- into shared memory (and, with PLANES, into
 // the stream's bit-planes: a word is stored by the block whose span holds its first byte); then thread t counts ITS read
 // from the shared-memory bits of the part of the read that lies in the tile.  No per-read loop over global memory, no
 // word encoded twice inside a block, no lane waiting for the longest read of its warp.
