@@ -51,8 +51,21 @@ def _write_set(rng, tmp, name, reads_per_file, with_bv):
 
 @pytest.mark.parametrize("seed", range(40))
 def test_index_and_search_fuzz(tmp_path, seed):
+    _index_and_search_case(tmp_path, seed, None)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7, 22, 24, 27, 29])
+def test_index_and_search_small_and_large_k(tmp_path, k):
+    """the k the fuzz above does not draw: k <= 3 (max_kmer = 1e9 / 2^(33-k) truncates to 0: nothing is ever indexed and
+    every call of index_reads loses a read, index_reads.h:48-49,60), single-byte filters, and filters of 2 MiB to 256 MiB"""
+    _index_and_search_case(tmp_path, 500 + k, k)
+
+
+def _index_and_search_case(tmp_path, seed, k_forced):
     rng = np.random.default_rng(1000 + seed)
     k = int(rng.integers(8, 21))
+    if k_forced is not None:
+        k = k_forced
     t = int(rng.integers(0, 4))
     L = int(rng.integers(k, 4 * k))
     dirt = dict(p_N=float(rng.choice([0, 0.02])), p_lower=float(rng.choice([0, 0.3])),
